@@ -1,0 +1,66 @@
+/* rqb_planner.h -- host-side construction of the solve program.
+ *
+ * Replaces, for the B200 build, the reference's precode_matrix_gen /
+ * precode_matrix_invert (lib/precode.c:90-97,347-377) and the permutation half
+ * of precode_matrix_intermediate (lib/precode.c:379-389): it analyses the
+ * sparse constraint matrix of one source block and emits the device program
+ * described in rqb_program.h.  No symbol data is touched on the host.
+ */
+#ifndef RQB_PLANNER_H
+#define RQB_PLANNER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rqb_rfc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int K;                   /* source symbols of the block (selects K')                      */
+  int overhead;            /* LT rows beyond K' (received repair symbols - missing symbols) */
+  const uint32_t *isi;     /* [K'+overhead] internal symbol id of the LT row k              */
+  const uint32_t *in_row;  /* [K'+overhead] input (staging) row with that symbol's bytes,   */
+                           /*               RQB_ROW_NONE for an all-zero symbol (padding)   */
+  int want_c;              /* emit all L intermediate symbols to c_out (row = index)        */
+  int n_out;               /* encoding symbols to emit to sym_out (row k = out_isi[k])      */
+  const uint32_t *out_isi; /* [n_out] internal symbol ids                                   */
+} rqb_plan_request;
+
+typedef struct {
+  int i, u;            /* peeled rows / inactivated columns (cf. schedule.i, .u)   */
+  int nb, rho, nfree;  /* binary residual rows, their GF(2) rank, columns left for HDPC */
+  int levels_fwd;      /* dependency depth of the sparse triangular solve          */
+  int n_levels, n_tasks, n_pages;
+  size_t n_srcs, n_gf_srcs, n_horner;
+  size_t nnz;
+  double t_matrix, t_peel, t_dense, t_emit; /* seconds */
+} rqb_plan_stats;
+
+typedef struct rqb_plan {
+  rqb_params P;
+  int K, overhead;
+  uint32_t n_slots;    /* shared-memory rows per CTA                           */
+  uint32_t *load_src;  /* [n_slots] input row loaded into the slot, or ROW_NONE */
+  uint32_t n_pages;
+  uint8_t *pages;      /* n_pages * RQB_PAGE_BYTES                              */
+  uint32_t n_c_rows;   /* rows written to c_out (L or 0)                        */
+  uint32_t n_out;
+  rqb_plan_stats st;
+} rqb_plan;
+
+/* 0 = ok, 1 = matrix rank < L (more symbols needed; the reference's
+ * precode_matrix_invert returns NULL, lib/precode.c:368-370), <0 = bad request */
+int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out);
+void rqb_plan_free(rqb_plan *p);
+
+int rqb_params_init(int K, rqb_params *P);
+/* host-side Tuple / index helpers over the built-in tables */
+int rqb_host_lt_indices(const rqb_params *P, uint32_t X, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
