@@ -1,0 +1,153 @@
+/* rqb200.h -- C ABI of the B200 hot path underneath the nanorq.h API.
+ *
+ * These are the entry points a reference-side binding would call instead of
+ * the reference's internal solver seam:
+ *
+ *   rqb_solver_*      replaces precode_matrix_gen / precode_matrix_invert /
+ *                     precode_matrix_intermediate (reference include/precode.h:10-12,
+ *                     lib/precode.c:90,347,379) and decode_row (lib/nanorq.c:184)
+ *                     for one source block resident on the GPU;
+ *   rqb_rowops_*      replaces the per-row oblas seam oaxpy / oaddrow / oscal
+ *                     (reference deps/oblas/oblas.h:28-30) with a batched call;
+ *   rqb_schedule_*    replays a reference-format schedule (sched_op list + marks,
+ *                     include/sched.h:6-27; lib/precode.c:23-32) on the device.
+ *
+ * Plain pointers and sizes only.  All functions return 0 on success; negative
+ * values are argument/state errors, positive values are documented per call.
+ * Nothing here falls back to the CPU: without a CUDA device every compute
+ * entry point fails with RQB_E_NODEVICE.
+ */
+#ifndef RQB200_H
+#define RQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQB_OK 0
+#define RQB_NEED_MORE 1      /* matrix rank < L: add symbols and retry     */
+#define RQB_E_ARG (-1)
+#define RQB_E_NODEVICE (-100) /* no CUDA device / CUDA error (see rqb_last_error) */
+#define RQB_E_TOOBIG (-101)  /* block does not fit the shared-memory solver */
+
+#define RQB_NO_ROW 0xFFFFFFFFu
+
+const char *rqb_last_error(void);
+int rqb_device_count(void);
+int rqb_set_device(int dev);
+unsigned long long rqb_kernel_launches(void);
+
+/* ---- RFC 6330 construction helpers (host, integer only) */
+typedef struct {
+  int Kprime, S, H, W, L, P, P1, U, B, J;
+} rqb_block_params;
+int rqb_block_params_init(int K, rqb_block_params *out);              /* lib/params.c:21 */
+int rqb_lt_row_indices(int K, uint32_t isi, uint32_t *out /*>=40*/); /* lib/params.c:47 */
+
+/* ---- one source block on the device ------------------------------------ */
+typedef struct rqb_solver rqb_solver;
+
+/* K source symbols of T bytes; room for max_in input rows (>= K) and max_out
+ * emitted symbols per solve. */
+int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32_t max_out);
+/* K_params selects K' (the reference uses block 0's parameters for every block of
+ * an object, lib/nanorq.c:289,372, so a shorter block may be padded further) */
+int rqb_solver_create_ex(rqb_solver **out, int K, int K_params, size_t T, uint32_t max_in, uint32_t max_out);
+void rqb_solver_destroy(rqb_solver *s);
+/* pinned host staging area for the input rows: max_in rows of rqb_solver_pitch bytes */
+uint8_t *rqb_solver_staging(rqb_solver *s);
+size_t rqb_solver_pitch(const rqb_solver *s);
+/* copy staging rows [first, first+n) to the device (asynchronous) */
+int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n);
+
+typedef struct {
+  int overhead;            /* LT rows beyond K'                                          */
+  const uint32_t *isi;     /* [K'+overhead] internal symbol id of LT row k               */
+  const uint32_t *in_row;  /* [K'+overhead] staging row holding it, RQB_NO_ROW = zeros   */
+  int want_c;              /* keep the L intermediate symbols on the device              */
+  uint32_t n_out;          /* symbols to emit with the solve                             */
+  const uint32_t *out_isi; /* [n_out]                                                    */
+} rqb_solve_request;
+
+/* analyse the block and stage the program on the device.  Returns RQB_NEED_MORE
+ * when the constraint matrix is singular.  encode_plan != 0 selects (and caches
+ * process-wide, per K) the plan of an encoder: isi = identity, rows 0..K-1. */
+int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req);
+int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_repair_with_solve);
+/* launch the solve kernel (asynchronous on the solver's stream) */
+int rqb_solver_run(rqb_solver *s);
+/* LT-combine further symbols from the intermediate symbols kept by want_c */
+int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n);
+/* wait for everything queued on this solver */
+int rqb_solver_sync(rqb_solver *s);
+/* copy results back: emitted symbols [first, first+n) of the last run/emit, or
+ * intermediate symbols; dst rows are dst_pitch apart, T bytes each */
+int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch);
+int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch);
+/* pinned host mirror of the emitted symbols (valid after fetch with dst == NULL) */
+const uint8_t *rqb_solver_sym_mirror(rqb_solver *s);
+/* device time of the last rqb_solver_run in milliseconds (CUDA events) */
+int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms);
+
+typedef struct {
+  int i, u, nb, rho, nfree, levels_fwd, n_levels, n_tasks, n_pages;
+  size_t n_srcs, n_gf_srcs, n_horner, nnz;
+  double t_matrix, t_peel, t_dense, t_emit;
+  uint32_t n_slots;
+  int vec_bytes;
+} rqb_solver_stats;
+int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
+
+/* run several solvers' pending programs as ONE kernel launch (gridDim.y = n);
+ * all must share T and device.  Asynchronous on solvers[0]'s stream. */
+int rqb_solver_run_batch(rqb_solver **solvers, int n);
+
+/* host-only: build the plan and hand back the raw program (tests / tooling);
+ * free with rqb_plan_blob_free. */
+typedef struct {
+  uint32_t n_slots, n_pages, page_bytes;
+  const uint32_t *load_src;
+  const uint8_t *pages;
+  rqb_solver_stats stats;
+  void *opaque;
+} rqb_plan_blob;
+int rqb_plan_blob_build(int K_params, const rqb_solve_request *req, rqb_plan_blob *out);
+void rqb_plan_blob_free(rqb_plan_blob *b);
+
+/* ---- batched row operations out of HBM --------------------------------- */
+/* binary-compatible with the reference's sched_op (include/sched.h:6-10) */
+typedef struct {
+  uint8_t beta; /* >=1: D[i] ^= beta*D[j] (oaxpy/oaddrow) ; 0: D[i] *= (uint8_t)j (oscal) */
+  uint32_t i;
+  uint32_t j;
+} rqb_op;
+
+typedef struct rqb_matrix rqb_matrix; /* rows x T bytes resident in HBM */
+int rqb_matrix_create(rqb_matrix **out, size_t rows, size_t T);
+void rqb_matrix_destroy(rqb_matrix *m);
+size_t rqb_matrix_pitch(const rqb_matrix *m);
+int rqb_matrix_upload(rqb_matrix *m, size_t first, size_t n, const uint8_t *src, size_t src_pitch);
+int rqb_matrix_download(rqb_matrix *m, size_t first, size_t n, uint8_t *dst, size_t dst_pitch);
+int rqb_matrix_fill_random(rqb_matrix *m, uint64_t seed); /* device-side fill, for benchmarks */
+/* one batch of mutually independent ops = one kernel launch */
+int rqb_rowops_apply(rqb_matrix *m, const rqb_op *ops, size_t n);
+/* same, ops already on the device (rqb_ops_upload), with CUDA-event timing */
+typedef struct rqb_oplist rqb_oplist;
+int rqb_ops_upload(rqb_oplist **out, const rqb_op *ops, size_t n);
+void rqb_ops_free(rqb_oplist *l);
+int rqb_rowops_apply_dev(rqb_matrix *m, const rqb_oplist *l, int repeats, float *ms_total);
+
+/* replay a reference-format schedule: ops applied in the order of
+ * precode_matrix_apply_sched (lib/precode.c:23-32) followed by the two row
+ * permutations of precode_matrix_intermediate (lib/precode.c:379-389).
+ * The host only levelises the op list; every row operation runs on the device. */
+int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long mark0, long mark1,
+                        const int *di, size_t rows, const int *c, size_t cols, float *ms_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

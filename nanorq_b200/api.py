@@ -1,0 +1,520 @@
+"""ctypes mirror of include/nanorq.h, include/io.h and include/rqb200.h.
+
+Names and argument meaning follow the C headers (which follow the reference's
+include/nanorq.h:16-83).  Nothing here computes on symbol bytes: every call goes
+through libnanorq_b200.so, and the library fails loudly when no CUDA device is
+visible (there is no CPU fallback)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnanorq_b200.so")
+
+SYM_DUP, SYM_IGN, SYM_ADDED, SYM_ERR = 2, 1, 0, -1
+NO_ROW = 0xFFFFFFFF
+RQB_NEED_MORE = 1
+RQB_E_NODEVICE = -100
+RQB_E_TOOBIG = -101
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+vp = C.c_void_p
+
+
+class BlockParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("Kprime", "S", "H", "W", "L", "P", "P1", "U", "B", "J")]
+
+
+class _SolveRequest(C.Structure):
+    _fields_ = [("overhead", C.c_int), ("isi", u32p), ("in_row", u32p), ("want_c", C.c_int),
+                ("n_out", C.c_uint32), ("out_isi", u32p)]
+
+
+class SolverStats(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("i", "u", "nb", "rho", "nfree", "levels_fwd", "n_levels", "n_tasks", "n_pages")] + \
+               [(n, C.c_size_t) for n in ("n_srcs", "n_gf_srcs", "n_horner", "nnz")] + \
+               [(n, C.c_double) for n in ("t_matrix", "t_peel", "t_dense", "t_emit")] + \
+               [("n_slots", C.c_uint32), ("vec_bytes", C.c_int)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class PlanBlob(C.Structure):
+    _fields_ = [("n_slots", C.c_uint32), ("n_pages", C.c_uint32), ("page_bytes", C.c_uint32),
+                ("load_src", u32p), ("pages", u8p), ("stats", SolverStats), ("opaque", vp)]
+
+
+class Op(C.Structure):
+    """binary-compatible with the reference's sched_op (include/sched.h:6-10)"""
+    _fields_ = [("beta", C.c_uint8), ("i", C.c_uint32), ("j", C.c_uint32)]
+
+
+OP_DTYPE = np.dtype({"names": ["beta", "i", "j"], "formats": [np.uint8, np.uint32, np.uint32],
+                     "offsets": [0, 4, 8], "itemsize": 12})
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libnanorq_b200.so is not built: run `python -m nanorq_b200.build` "
+            "(or __graft_entry__.build()); there is no pure-Python/CPU fallback")
+    L = C.CDLL(LIB_PATH)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sz = C.c_size_t
+    # nanorq.h
+    sig("nanorq_encoder_new", vp, sz, C.c_uint16, C.c_uint8)
+    sig("nanorq_encoder_new_ex", vp, sz, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint8)
+    sig("nanorq_generate_symbols", C.c_bool, vp, C.c_uint8, vp)
+    sig("nanorq_free", None, vp)
+    sig("nanorq_oti_common", C.c_uint64, vp)
+    sig("nanorq_oti_scheme_specific", C.c_uint32, vp)
+    sig("nanorq_transfer_length", sz, vp)
+    sig("nanorq_symbol_size", sz, vp)
+    sig("nanorq_blocks", sz, vp)
+    sig("nanorq_block_symbols", sz, vp, C.c_uint8)
+    sig("nanorq_tag", C.c_uint32, C.c_uint8, C.c_uint32)
+    sig("nanorq_max_blocks", sz, vp)
+    sig("nanorq_precalculate", C.c_bool, vp)
+    sig("nanorq_encode", sz, vp, vp, C.c_uint32, C.c_uint8, vp)
+    sig("nanorq_encoder_cleanup", None, vp, C.c_uint8)
+    sig("nanorq_encoder_reset", None, vp, C.c_uint8)
+    sig("nanorq_decoder_new", vp, C.c_uint64, C.c_uint32)
+    sig("nanorq_set_max_esi", C.c_bool, vp, C.c_uint32)
+    sig("nanorq_decoder_add_symbol", C.c_int, vp, vp, C.c_uint32, vp)
+    sig("nanorq_num_missing", sz, vp, C.c_uint8)
+    sig("nanorq_num_repair", sz, vp, C.c_uint8)
+    sig("nanorq_repair_block", C.c_bool, vp, vp, C.c_uint8)
+    # io.h
+    sig("ioctx_from_file", vp, C.c_char_p, C.c_int)
+    sig("ioctx_mmap_file", vp, C.c_char_p, C.c_int)
+    sig("ioctx_from_mem", vp, vp, sz)
+    # rqb200.h
+    sig("rqb_last_error", C.c_char_p)
+    sig("rqb_device_count", C.c_int)
+    sig("rqb_set_device", C.c_int, C.c_int)
+    sig("rqb_kernel_launches", C.c_ulonglong)
+    sig("rqb_block_params_init", C.c_int, C.c_int, C.POINTER(BlockParams))
+    sig("rqb_lt_row_indices", C.c_int, C.c_int, C.c_uint32, u32p)
+    sig("rqb_solver_create", C.c_int, C.POINTER(vp), C.c_int, sz, C.c_uint32, C.c_uint32)
+    sig("rqb_solver_create_ex", C.c_int, C.POINTER(vp), C.c_int, C.c_int, sz, C.c_uint32, C.c_uint32)
+    sig("rqb_solver_destroy", None, vp)
+    sig("rqb_solver_staging", vp, vp)
+    sig("rqb_solver_pitch", sz, vp)
+    sig("rqb_solver_upload", C.c_int, vp, C.c_uint32, C.c_uint32)
+    sig("rqb_solver_plan", C.c_int, vp, C.POINTER(_SolveRequest))
+    sig("rqb_solver_plan_encode", C.c_int, vp, C.c_int, C.c_uint32)
+    sig("rqb_solver_run", C.c_int, vp)
+    sig("rqb_solver_emit", C.c_int, vp, u32p, C.c_uint32)
+    sig("rqb_solver_sync", C.c_int, vp)
+    sig("rqb_solver_fetch_syms", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
+    sig("rqb_solver_fetch_c", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
+    sig("rqb_solver_sym_mirror", vp, vp)
+    sig("rqb_solver_last_kernel_ms", C.c_int, vp, C.POINTER(C.c_float))
+    sig("rqb_solver_get_stats", C.c_int, vp, C.POINTER(SolverStats))
+    sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
+    sig("rqb_plan_blob_build", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.POINTER(PlanBlob))
+    sig("rqb_plan_blob_free", None, C.POINTER(PlanBlob))
+    sig("rqb_matrix_create", C.c_int, C.POINTER(vp), sz, sz)
+    sig("rqb_matrix_destroy", None, vp)
+    sig("rqb_matrix_pitch", sz, vp)
+    sig("rqb_matrix_upload", C.c_int, vp, sz, sz, vp, sz)
+    sig("rqb_matrix_download", C.c_int, vp, sz, sz, vp, sz)
+    sig("rqb_matrix_fill_random", C.c_int, vp, C.c_uint64)
+    sig("rqb_rowops_apply", C.c_int, vp, vp, sz)
+    sig("rqb_ops_upload", C.c_int, C.POINTER(vp), vp, sz)
+    sig("rqb_ops_free", None, vp)
+    sig("rqb_rowops_apply_dev", C.c_int, vp, vp, C.c_int, C.POINTER(C.c_float))
+    sig("rqb_schedule_replay", C.c_int, vp, vp, sz, C.c_long, C.c_long, C.POINTER(C.c_int), sz,
+        C.POINTER(C.c_int), sz, C.POINTER(C.c_float))
+    _lib = L
+    return L
+
+
+# every symbol include/*.h declares (checked by the CPU test-suite)
+EXPORTED_SYMBOLS = [
+    "nanorq_encoder_new", "nanorq_encoder_new_ex", "nanorq_generate_symbols", "nanorq_free",
+    "nanorq_oti_common", "nanorq_oti_scheme_specific", "nanorq_transfer_length", "nanorq_symbol_size",
+    "nanorq_blocks", "nanorq_block_symbols", "nanorq_tag", "nanorq_max_blocks", "nanorq_precalculate",
+    "nanorq_encode", "nanorq_encoder_cleanup", "nanorq_encoder_reset", "nanorq_decoder_new",
+    "nanorq_set_max_esi", "nanorq_decoder_add_symbol", "nanorq_num_missing", "nanorq_num_repair",
+    "nanorq_repair_block", "ioctx_from_file", "ioctx_mmap_file", "ioctx_from_mem",
+    "rqb_last_error", "rqb_device_count", "rqb_set_device", "rqb_kernel_launches",
+    "rqb_block_params_init", "rqb_lt_row_indices", "rqb_solver_create", "rqb_solver_create_ex",
+    "rqb_solver_destroy", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
+    "rqb_solver_plan", "rqb_solver_plan_encode", "rqb_solver_run", "rqb_solver_emit",
+    "rqb_solver_sync", "rqb_solver_fetch_syms", "rqb_solver_fetch_c", "rqb_solver_sym_mirror",
+    "rqb_solver_last_kernel_ms", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_plan_blob_build",
+    "rqb_plan_blob_free", "rqb_matrix_create", "rqb_matrix_destroy", "rqb_matrix_pitch",
+    "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
+    "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
+]
+
+
+def last_error():
+    return lib().rqb_last_error().decode()
+
+
+def device_count():
+    return lib().rqb_device_count()
+
+
+def set_device(dev):
+    _check(lib().rqb_set_device(dev), "rqb_set_device")
+
+
+def kernel_launches():
+    return int(lib().rqb_kernel_launches())
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, last_error()))
+
+
+def block_params(K):
+    p = BlockParams()
+    if lib().rqb_block_params_init(K, C.byref(p)) != 0:
+        raise ValueError("bad K %r" % (K,))
+    return p
+
+
+def lt_row_indices(K, isi):
+    out = (C.c_uint32 * 40)()
+    n = lib().rqb_lt_row_indices(K, isi, out)
+    return list(out[:n])
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class SolveRequest:
+    """rqb_solve_request: which LT rows exist, where their bytes are, what to emit."""
+
+    def __init__(self, isi, in_row, overhead=0, want_c=True, out_isi=()):
+        self.isi = _u32(isi)
+        self.in_row = _u32(in_row)
+        self.out_isi = _u32(out_isi)
+        assert len(self.isi) == len(self.in_row)
+        self.c = _SolveRequest(int(overhead), self.isi.ctypes.data_as(u32p), self.in_row.ctypes.data_as(u32p),
+                               1 if want_c else 0, len(self.out_isi), self.out_isi.ctypes.data_as(u32p))
+
+    @staticmethod
+    def for_encoder(K, want_c=True, out_isi=()):
+        p = block_params(K)
+        k = np.arange(p.Kprime, dtype=np.uint32)
+        return SolveRequest(k, np.where(k < K, k, NO_ROW), 0, want_c, out_isi)
+
+    @staticmethod
+    def for_decoder(K, esis, K_params=None):
+        """Row placement of nanorq_decoder_add_symbol / nanorq_repair_block
+        (reference lib/nanorq.c:478-509,527-565) for symbols that arrived in the
+        order `esis` and were staged in that order (staging row = arrival index).
+        Returns (request, missing_esis) or (None, missing) when too few symbols."""
+        p = block_params(K_params or K)
+        pad = p.Kprime - K
+        have, reps, seen = {}, [], set()
+        for k, e in enumerate(esis):
+            e = int(e)
+            if len(have) == K:
+                break
+            if e < K:
+                have.setdefault(e, k)
+            elif e not in seen:
+                seen.add(e)
+                reps.append((e, k))
+        missing = [e for e in range(K) if e not in have]
+        if len(reps) < len(missing):
+            return None, missing
+        oh = len(reps) - len(missing)
+        isi = np.arange(p.Kprime + oh, dtype=np.uint32)
+        in_row = np.full(p.Kprime + oh, NO_ROW, dtype=np.uint32)
+        for e, k in have.items():
+            in_row[e] = k
+        for g, (e, k) in zip(missing, reps):
+            isi[g] = e + pad
+            in_row[g] = k
+        for x, (e, k) in enumerate(reps[len(missing):]):
+            isi[p.Kprime + x] = e + pad
+            in_row[p.Kprime + x] = k
+        return SolveRequest(isi, in_row, oh, True, missing), missing
+
+
+def plan_blob(K_params, req):
+    """Host-only: build the device program and return (rc, dict) without a GPU."""
+    b = PlanBlob()
+    rc = lib().rqb_plan_blob_build(K_params, C.byref(req.c), C.byref(b))
+    if rc != 0:
+        return rc, None
+    out = {
+        "n_slots": b.n_slots, "n_pages": b.n_pages, "page_bytes": b.page_bytes,
+        "load_src": np.ctypeslib.as_array(b.load_src, (b.n_slots,)).copy(),
+        "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(),
+        "stats": b.stats.as_dict(),
+    }
+    lib().rqb_plan_blob_free(C.byref(b))
+    return 0, out
+
+
+class MemIO:
+    """ioctx_from_mem over a numpy uint8 array (reference lib/io.c:139-157)."""
+
+    ptr = None
+
+    def __init__(self, arr):
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        self.arr = arr
+        self.ptr = lib().ioctx_from_mem(arr.ctypes.data, arr.size)
+
+    def close(self):
+        if self.ptr:
+            destroy = C.cast(self.ptr, C.POINTER(_IoCtx)).contents.destroy
+            destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+class _IoCtx(C.Structure):
+    _fields_ = [("read", vp), ("write", vp), ("seek", vp), ("size", vp), ("tell", vp),
+                ("destroy", C.CFUNCTYPE(None, vp)), ("seekable", C.c_bool), ("writable", C.c_bool)]
+
+
+class _Codec:
+    h = None
+
+    def __init__(self, h):
+        if not h:
+            raise ValueError("nanorq constructor returned NULL")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().nanorq_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def oti_common(self):
+        return lib().nanorq_oti_common(self.h)
+
+    def oti_scheme_specific(self):
+        return lib().nanorq_oti_scheme_specific(self.h)
+
+    def transfer_length(self):
+        return lib().nanorq_transfer_length(self.h)
+
+    def symbol_size(self):
+        return lib().nanorq_symbol_size(self.h)
+
+    def blocks(self):
+        return lib().nanorq_blocks(self.h)
+
+    def block_symbols(self, sbn):
+        return lib().nanorq_block_symbols(self.h, sbn)
+
+    def encoder_cleanup(self, sbn):
+        lib().nanorq_encoder_cleanup(self.h, sbn)
+
+    def encoder_reset(self, sbn):
+        lib().nanorq_encoder_reset(self.h, sbn)
+
+
+class Encoder(_Codec):
+    def __init__(self, length, T, K=0, Z=0, Al=8):
+        super().__init__(lib().nanorq_encoder_new_ex(length, T, K, Z, Al))
+
+    def precalculate(self):
+        return lib().nanorq_precalculate(self.h)
+
+    def generate_symbols(self, sbn, io):
+        return lib().nanorq_generate_symbols(self.h, sbn, io.ptr)
+
+    def encode(self, esi, sbn, io, out=None):
+        T = self.symbol_size()
+        if out is None:
+            out = np.empty(T, dtype=np.uint8)
+        n = lib().nanorq_encode(self.h, out.ctypes.data, esi, sbn, io.ptr)
+        return out if n == T else None
+
+
+class Decoder(_Codec):
+    def __init__(self, common, specific):
+        super().__init__(lib().nanorq_decoder_new(common, specific))
+
+    def set_max_esi(self, v):
+        return lib().nanorq_set_max_esi(self.h, v)
+
+    def add_symbol(self, data, tag, io):
+        return lib().nanorq_decoder_add_symbol(self.h, data.ctypes.data, tag, io.ptr)
+
+    def num_missing(self, sbn):
+        return lib().nanorq_num_missing(self.h, sbn)
+
+    def num_repair(self, sbn):
+        return lib().nanorq_num_repair(self.h, sbn)
+
+    def repair_block(self, io, sbn):
+        return lib().nanorq_repair_block(self.h, io.ptr, sbn)
+
+
+def tag(sbn, esi):
+    return lib().nanorq_tag(sbn, esi)
+
+
+class Solver:
+    """rqb_solver: one source block resident on the GPU."""
+    h = None
+
+    def __init__(self, K, T, max_in=None, max_out=1, K_params=None):
+        self.K, self.T = K, T
+        self.max_in = int(max_in or K)
+        self.max_out = int(max_out)
+        h = vp()
+        _check(lib().rqb_solver_create_ex(C.byref(h), K, K_params or K, T, self.max_in, self.max_out),
+               "rqb_solver_create")
+        self.h = h
+        self.pitch = lib().rqb_solver_pitch(h)
+        buf = (C.c_uint8 * (self.max_in * self.pitch)).from_address(lib().rqb_solver_staging(h))
+        self.staging = np.frombuffer(buf, dtype=np.uint8).reshape(self.max_in, self.pitch)
+
+    def close(self):
+        if self.h:
+            self.staging = None
+            lib().rqb_solver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def upload(self, first, n):
+        _check(lib().rqb_solver_upload(self.h, first, n), "rqb_solver_upload")
+
+    def plan(self, req):
+        rc = lib().rqb_solver_plan(self.h, C.byref(req.c))
+        if rc not in (0, RQB_NEED_MORE):
+            _check(rc, "rqb_solver_plan")
+        return rc
+
+    def plan_encode(self, want_c=True, n_repair=0):
+        _check(lib().rqb_solver_plan_encode(self.h, 1 if want_c else 0, n_repair), "rqb_solver_plan_encode")
+
+    def run(self):
+        _check(lib().rqb_solver_run(self.h), "rqb_solver_run")
+
+    def emit(self, isi):
+        isi = _u32(isi)
+        _check(lib().rqb_solver_emit(self.h, isi.ctypes.data_as(u32p), len(isi)), "rqb_solver_emit")
+
+    def sync(self):
+        _check(lib().rqb_solver_sync(self.h), "rqb_solver_sync")
+
+    def fetch_syms(self, n, first=0):
+        out = np.empty((n, self.T), dtype=np.uint8)
+        _check(lib().rqb_solver_fetch_syms(self.h, first, n, out.ctypes.data, self.T), "rqb_solver_fetch_syms")
+        return out
+
+    def fetch_syms_mirror(self, n, first=0):
+        _check(lib().rqb_solver_fetch_syms(self.h, first, n, None, 0), "rqb_solver_fetch_syms")
+
+    def fetch_c(self, n=None, first=0):
+        n = n if n is not None else block_params(self.K).L
+        out = np.empty((n, self.T), dtype=np.uint8)
+        _check(lib().rqb_solver_fetch_c(self.h, first, n, out.ctypes.data, self.T), "rqb_solver_fetch_c")
+        return out
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().rqb_solver_last_kernel_ms(self.h, C.byref(ms)), "rqb_solver_last_kernel_ms")
+        return ms.value
+
+    def stats(self):
+        st = SolverStats()
+        _check(lib().rqb_solver_get_stats(self.h, C.byref(st)), "rqb_solver_get_stats")
+        return st.as_dict()
+
+    @staticmethod
+    def run_batch(solvers):
+        arr = (vp * len(solvers))(*[s.h for s in solvers])
+        _check(lib().rqb_solver_run_batch(arr, len(solvers)), "rqb_solver_run_batch")
+
+
+class Matrix:
+    """rqb_matrix: rows x T bytes in HBM, target of the batched row ops."""
+    h = None
+
+    def __init__(self, rows, T):
+        self.rows, self.T = rows, T
+        h = vp()
+        _check(lib().rqb_matrix_create(C.byref(h), rows, T), "rqb_matrix_create")
+        self.h = h
+        self.pitch = lib().rqb_matrix_pitch(h)
+
+    def close(self):
+        if self.h:
+            lib().rqb_matrix_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def upload(self, arr, first=0):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        _check(lib().rqb_matrix_upload(self.h, first, arr.shape[0], arr.ctypes.data, arr.strides[0]),
+               "rqb_matrix_upload")
+
+    def download(self, first=0, n=None):
+        n = self.rows - first if n is None else n
+        out = np.empty((n, self.T), dtype=np.uint8)
+        _check(lib().rqb_matrix_download(self.h, first, n, out.ctypes.data, self.T), "rqb_matrix_download")
+        return out
+
+    def fill_random(self, seed=1):
+        _check(lib().rqb_matrix_fill_random(self.h, seed), "rqb_matrix_fill_random")
+
+    @staticmethod
+    def make_ops(beta, i, j):
+        ops = np.zeros(len(beta), dtype=OP_DTYPE)
+        ops["beta"], ops["i"], ops["j"] = beta, i, j
+        return ops
+
+    def apply(self, ops):
+        assert ops.dtype == OP_DTYPE
+        _check(lib().rqb_rowops_apply(self.h, ops.ctypes.data, len(ops)), "rqb_rowops_apply")
+
+    def upload_ops(self, ops):
+        assert ops.dtype == OP_DTYPE
+        h = vp()
+        _check(lib().rqb_ops_upload(C.byref(h), ops.ctypes.data, len(ops)), "rqb_ops_upload")
+        return h
+
+    def apply_dev(self, oplist, repeats=1):
+        ms = C.c_float()
+        _check(lib().rqb_rowops_apply_dev(self.h, oplist, repeats, C.byref(ms)), "rqb_rowops_apply_dev")
+        return ms.value
+
+    def schedule_replay(self, ops, mark0, mark1, di, c):
+        assert ops.dtype == OP_DTYPE
+        di = np.ascontiguousarray(di, dtype=np.int32)
+        c = np.ascontiguousarray(c, dtype=np.int32)
+        ms = C.c_float()
+        _check(lib().rqb_schedule_replay(self.h, ops.ctypes.data, len(ops), mark0, mark1,
+                                         di.ctypes.data_as(C.POINTER(C.c_int)), len(di),
+                                         c.ctypes.data_as(C.POINTER(C.c_int)), len(c), C.byref(ms)),
+               "rqb_schedule_replay")
+        return ms.value

@@ -1,0 +1,395 @@
+/* nanorq_api.c -- the nanorq.h encoder/decoder object on top of the GPU block
+ * solver (rqb200.h).  Host glue only: OTI packing, source-block partitioning,
+ * symbol bookkeeping and ioctx traffic follow the reference's lib/nanorq.c
+ * (cited per function); all symbol arithmetic happens on the device.
+ */
+#include "nanorq.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include "rqb200.h"
+
+#define Z_MAX 256
+#define K_MAX 56403
+
+struct part {
+  size_t IL, IS, JL, JS; /* long size, short size, #long, #short */
+};
+
+struct block {
+  uint16_t K;
+  bool loaded, inverted;
+  rqb_solver *sv;
+  size_t pitch;
+  /* decoder bookkeeping (lib/nanorq.c:40-47: repair_bin, repair_mask) */
+  uint32_t *mask;
+  size_t mask_words;
+  size_t gaps;
+  uint32_t *rep_esi;
+  size_t nrep, rep_cap;
+  uint32_t in_cap;
+  /* encoder: window of repair symbols already produced on the device */
+  uint32_t win_first, win_n, win_cap;
+};
+
+struct nanorq {
+  size_t F, T, Al, Z, N, Kt;
+  struct part src_part, sub_part;
+  rqb_block_params P;
+  uint32_t max_esi;
+  struct block *blocks[Z_MAX];
+};
+
+static size_t div_ceil(size_t a, size_t b) { return a / b + (a % b ? 1 : 0); }
+
+static struct part make_part(size_t I, size_t J) { /* lib/nanorq.c:83-95 */
+  struct part p = {0, 0, 0, 0};
+  if (J == 0) return p;
+  p.IL = div_ceil(I, J);
+  p.IS = I / J;
+  p.JL = I - p.IS * J;
+  p.JS = J - p.JL;
+  if (p.JL == 0) p.IL = 0;
+  return p;
+}
+
+size_t nanorq_block_symbols(nanorq *rq, uint8_t sbn) { /* :379-385 */
+  if (sbn < rq->src_part.JL) return rq->src_part.IL;
+  if (sbn - rq->src_part.JL < rq->src_part.JS) return rq->src_part.IS;
+  return 0;
+}
+
+size_t nanorq_max_blocks(nanorq *rq) {
+  (void)rq;
+  return Z_MAX;
+}
+size_t nanorq_blocks(nanorq *rq) { return rq->src_part.JL + rq->src_part.JS; }
+size_t nanorq_transfer_length(nanorq *rq) { return rq->F; }
+size_t nanorq_symbol_size(nanorq *rq) { return rq->T; }
+
+uint64_t nanorq_oti_common(nanorq *rq) { /* :309-315 */
+  return ((uint64_t)rq->F << 24) | ((rq->T - 1) & 0xffff);
+}
+
+uint32_t nanorq_oti_scheme_specific(nanorq *rq) { /* :317-324 */
+  return (uint32_t)((rq->Z - 1) << 24) | (uint32_t)((rq->N - 1) << 8) | (uint32_t)rq->Al;
+}
+
+uint32_t nanorq_tag(uint8_t sbn, uint32_t esi) { return ((uint32_t)sbn << 24) | (esi & 0x00ffffff); }
+
+nanorq *nanorq_encoder_new_ex(size_t len, uint16_t T16, uint16_t K, uint16_t Z16, uint8_t Al) {
+  /* lib/nanorq.c:241-292 and gen_scheme_specific :60-81 */
+  static const uint8_t aligns[] = {1, 2, 4, 8};
+  if (len == 0 || len > NANORQ_MAX_TRANSFER) return NULL;
+  uint8_t al = 1;
+  for (int a = 3; a >= 0; a--)
+    if (Al >= aligns[a]) {
+      al = aligns[a];
+      break;
+    }
+  size_t T = T16, Z = Z16;
+  if (T < al)
+    T = al;
+  else
+    T -= T % al;
+  while (div_ceil(len, T) > (size_t)Z_MAX * K_MAX) {
+    if (al == 1) return NULL; /* the reference would spin forever here */
+    T *= al;
+    if (T > 65535) return NULL;
+  }
+  size_t Kt = div_ceil(len, T), Kn = K;
+  if (K == 0) {
+    Kn = Kt;
+    if (Z == 0) {
+      Z = 16;
+      while (div_ceil(Kt, Z) > K_MAX) Z++;
+    }
+    Kn = div_ceil(Kt, Z);
+  }
+  if (Kn == 0) return NULL;
+  size_t Zf = div_ceil(Kt, Kn);
+  if (Zf == 0 || Zf > Z_MAX || div_ceil(Kt, Zf) > K_MAX) return NULL;
+  nanorq *rq = calloc(1, sizeof(*rq));
+  rq->F = len;
+  rq->T = T;
+  rq->Al = al;
+  rq->Kt = Kt;
+  rq->Z = Zf;
+  rq->N = 1; /* sub-block interleaving is disabled in the reference as well (:78) */
+  rq->src_part = make_part(Kt, Zf);
+  rq->sub_part = make_part(T / al, 1);
+  if (rqb_block_params_init((int)nanorq_block_symbols(rq, 0), &rq->P)) {
+    free(rq);
+    return NULL;
+  }
+  return rq;
+}
+
+nanorq *nanorq_encoder_new(size_t len, uint16_t T, uint8_t Al) { return nanorq_encoder_new_ex(len, T, 0, 0, Al); }
+
+nanorq *nanorq_decoder_new(uint64_t common, uint32_t scheme) { /* :336-376 */
+  uint64_t F = common >> 24;
+  size_t T = (size_t)(common & 0xffff) + 1;
+  if (F == 0 || F > NANORQ_MAX_TRANSFER) return NULL;
+  size_t Z = ((scheme >> 24) & 0xff) + 1, N = ((scheme >> 8) & 0xffff) + 1, Al = scheme & 0xff;
+  if (Al == 0 || T < Al || T % Al != 0) return NULL;
+  size_t Kt = div_ceil(F, T);
+  if (div_ceil(Kt, Z) > K_MAX) return NULL;
+  nanorq *rq = calloc(1, sizeof(*rq));
+  rq->F = F;
+  rq->T = T;
+  rq->Al = Al;
+  rq->Z = Z;
+  rq->N = N;
+  rq->Kt = Kt;
+  rq->src_part = make_part(Kt, Z);
+  rq->sub_part = make_part(T / Al, N);
+  if (nanorq_block_symbols(rq, 0) == 0 || rqb_block_params_init((int)nanorq_block_symbols(rq, 0), &rq->P)) {
+    free(rq);
+    return NULL;
+  }
+  rq->max_esi = 2u * (uint32_t)rq->P.Kprime;
+  return rq;
+}
+
+bool nanorq_set_max_esi(nanorq *rq, uint32_t max_esi) { /* :471-476 */
+  if (!rq || max_esi >= (1u << 24) || max_esi < (uint32_t)rq->P.Kprime) return false;
+  rq->max_esi = max_esi;
+  return true;
+}
+
+/* byte offset of symbol esi of block sbn in the object (N = 1: one contiguous
+ * span, get_source_block / get_symbol_offset :97-128) */
+static size_t symbol_offset(nanorq *rq, uint8_t sbn, uint32_t esi) {
+  size_t first;
+  if (sbn < rq->src_part.JL)
+    first = (size_t)sbn * rq->src_part.IL;
+  else
+    first = rq->src_part.IL * rq->src_part.JL + ((size_t)sbn - rq->src_part.JL) * rq->src_part.IS;
+  return (first + esi) * rq->T;
+}
+
+/* transfer_esi :148-173 for N = 1 */
+static size_t transfer_symbol(nanorq *rq, uint8_t sbn, uint32_t esi, uint8_t *ptr, struct ioctx *io, int out) {
+  size_t off = symbol_offset(rq, sbn, esi), n = rq->T;
+  if (off >= rq->F) return 0;
+  if (!io->seek(io, off)) return 0;
+  if (off + n >= rq->F) n = rq->F - off;
+  return out ? io->write(io, ptr, n) : io->read(io, ptr, n);
+}
+
+static void block_free(struct block *b) {
+  if (!b) return;
+  rqb_solver_destroy(b->sv);
+  free(b->mask);
+  free(b->rep_esi);
+  free(b);
+}
+
+static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :130-146 */
+  if (rq->blocks[sbn]) return rq->blocks[sbn];
+  size_t K = nanorq_block_symbols(rq, sbn);
+  if (K == 0) return NULL;
+  struct block *b = calloc(1, sizeof(*b));
+  b->K = (uint16_t)K;
+  uint32_t max_in, max_out;
+  if (rq->max_esi) { /* decoder: source slots + every repair ESI that may arrive */
+    uint32_t spare = rq->max_esi >= K ? rq->max_esi - (uint32_t)K + 1 : 1;
+    max_in = (uint32_t)rq->P.Kprime + spare;
+    max_out = (uint32_t)K;
+    b->mask_words = rq->max_esi / 32 + 2;
+    b->mask = calloc(b->mask_words, sizeof(uint32_t));
+    b->gaps = K;
+  } else {
+    max_in = (uint32_t)K;
+    b->win_cap = (uint32_t)(K / 4 < 32 ? 32 : (K / 4 > 8192 ? 8192 : K / 4));
+    max_out = b->win_cap;
+  }
+  b->in_cap = max_in;
+  if (rqb_solver_create_ex(&b->sv, (int)K, rq->P.Kprime, rq->T, max_in, max_out) != 0) {
+    block_free(b);
+    return NULL;
+  }
+  b->pitch = rqb_solver_pitch(b->sv);
+  rq->blocks[sbn] = b;
+  return b;
+}
+
+static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
+  /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging rows */
+  uint8_t *st = rqb_solver_staging(b->sv);
+  for (uint32_t esi = 0; esi < b->K; esi++) {
+    uint8_t *row = st + (size_t)esi * b->pitch;
+    size_t got = transfer_symbol(rq, sbn, esi, row, io, 0);
+    if (got < rq->T) memset(row + got, 0, rq->T - got);
+  }
+  return true;
+}
+
+bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :206-232 */
+  struct block *b = get_block(rq, sbn);
+  if (!b) return false;
+  if (b->inverted) return true;
+  if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
+  if (!b->loaded) return false;
+  if (rqb_solver_upload(b->sv, 0, b->K)) return false;
+  if (rqb_solver_plan_encode(b->sv, 1, 0)) return false; /* cached per K: cf. rq->S :219-221 */
+  if (rqb_solver_run(b->sv) || rqb_solver_sync(b->sv)) return false;
+  b->inverted = true;
+  b->win_n = 0;
+  return true;
+}
+
+bool nanorq_precalculate(nanorq *rq) { /* :393-401 */
+  struct block *b = get_block(rq, 0);
+  if (!b) return false;
+  return rqb_solver_plan_encode(b->sv, 1, 0) == 0;
+}
+
+size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct ioctx *io) { /* :403-435 */
+  struct block *b = get_block(rq, sbn);
+  if (!b) return 0;
+  if (esi < b->K) {
+    /* source symbol: the bytes the block was loaded with (the reference re-derives
+     * them from the intermediate symbols once inverted; same bytes) */
+    if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
+    if (!b->loaded) return 0;
+    memcpy(data, rqb_solver_staging(b->sv) + (size_t)esi * b->pitch, rq->T);
+    return rq->T;
+  }
+  if (esi > ((1u << 24) - 1)) return 0;
+  if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  if (!(b->win_n && esi >= b->win_first && esi < b->win_first + b->win_n)) {
+    /* produce the next window of repair symbols on the device in one LT launch */
+    uint32_t n = b->win_cap, pad = (uint32_t)rq->P.Kprime - b->K;
+    if ((uint64_t)esi + n > (1u << 24)) n = (1u << 24) - esi;
+    uint32_t *isi = malloc(sizeof(uint32_t) * n);
+    for (uint32_t k = 0; k < n; k++) isi[k] = esi + k + pad; /* ISI = ESI + (K'-K) :429 */
+    int rc = rqb_solver_emit(b->sv, isi, n);
+    free(isi);
+    if (rc || rqb_solver_fetch_syms(b->sv, 0, n, NULL, 0)) return 0;
+    b->win_first = esi;
+    b->win_n = n;
+  }
+  memcpy(data, rqb_solver_sym_mirror(b->sv) + (size_t)(esi - b->win_first) * b->pitch, rq->T);
+  return rq->T;
+}
+
+void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn) { /* :437-451 */
+  if (!rq->blocks[sbn]) return;
+  block_free(rq->blocks[sbn]);
+  rq->blocks[sbn] = NULL;
+}
+
+void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
+  struct block *b = rq->blocks[sbn];
+  if (!b) return;
+  b->loaded = b->inverted = false;
+  b->win_n = 0;
+  b->nrep = 0;
+  if (b->mask) {
+    memset(b->mask, 0, b->mask_words * sizeof(uint32_t));
+    b->gaps = b->K;
+  }
+}
+
+void nanorq_free(nanorq *rq) { /* :298-307 (NULL-safe here) */
+  if (!rq) return;
+  for (int sbn = 0; sbn < Z_MAX; sbn++) nanorq_encoder_cleanup(rq, (uint8_t)sbn);
+  free(rq);
+}
+
+static inline bool mask_get(const struct block *b, uint32_t id) { return (b->mask[id / 32] >> (id % 32)) & 1; }
+static inline void mask_set(struct block *b, uint32_t id) { b->mask[id / 32] |= 1u << (id % 32); }
+
+int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx *io) { /* :478-509 */
+  uint8_t sbn = (tag >> 24) & 0xff;
+  uint32_t esi = tag & 0x00ffffff;
+  struct block *b = get_block(rq, sbn);
+  if (!b || !b->mask || esi > rq->max_esi || esi / 32 >= b->mask_words) return NANORQ_SYM_ERR;
+  if (b->gaps == 0) return NANORQ_SYM_IGN;
+  if (mask_get(b, esi)) return NANORQ_SYM_DUP;
+  uint8_t *st = rqb_solver_staging(b->sv);
+  if (esi < b->K) {
+    memcpy(st + (size_t)esi * b->pitch, data, rq->T);
+    transfer_symbol(rq, sbn, esi, data, io, 1); /* source symbols go straight to the output */
+    b->gaps--;
+  } else {
+    uint32_t row = (uint32_t)rq->P.Kprime + (uint32_t)b->nrep;
+    if (row >= b->in_cap) return NANORQ_SYM_ERR;
+    if (b->nrep == b->rep_cap) {
+      b->rep_cap = b->rep_cap ? b->rep_cap * 2 : 256;
+      b->rep_esi = realloc(b->rep_esi, b->rep_cap * sizeof(uint32_t));
+    }
+    memcpy(st + (size_t)row * b->pitch, data, rq->T); /* arrival order, like repair_bin */
+    b->rep_esi[b->nrep++] = esi;
+  }
+  mask_set(b, esi);
+  return NANORQ_SYM_ADDED;
+}
+
+size_t nanorq_num_missing(nanorq *rq, uint8_t sbn) { /* :511-517 */
+  struct block *b = get_block(rq, sbn);
+  return b && b->mask ? b->gaps : 0;
+}
+
+size_t nanorq_num_repair(nanorq *rq, uint8_t sbn) { /* :519-525 */
+  struct block *b = get_block(rq, sbn);
+  return b ? b->nrep : 0;
+}
+
+bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-631 */
+  struct block *b = get_block(rq, sbn);
+  if (!b || !b->mask) return false;
+  if (b->gaps == 0) return true;
+  if (b->nrep < b->gaps) return false;
+  const int Kp = rq->P.Kprime;
+  const size_t gaps = b->gaps, overhead = b->nrep - gaps;
+  const uint32_t pad = (uint32_t)Kp - b->K;
+  /* the symbol bytes start moving to the GPU while the host analyses the matrix */
+  if (rqb_solver_upload(b->sv, 0, (uint32_t)Kp + (uint32_t)b->nrep)) return false;
+  size_t nlt = (size_t)Kp + overhead;
+  uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);
+  uint32_t *missing = malloc(sizeof(uint32_t) * gaps);
+  size_t rep = 0, nm = 0;
+  /* fill_symbol_matrix_gaps + patch_precode_matrix (:527-565): missing source rows take
+   * the repair symbols in arrival order, the rest become overhead rows */
+  for (uint32_t e = 0; e < (uint32_t)Kp; e++) {
+    if (e >= b->K) { /* padding symbol: known zero */
+      isi[e] = e;
+      in_row[e] = RQB_NO_ROW;
+    } else if (mask_get(b, e)) {
+      isi[e] = e;
+      in_row[e] = e;
+    } else {
+      isi[e] = b->rep_esi[rep] + pad;
+      in_row[e] = (uint32_t)Kp + (uint32_t)rep;
+      rep++;
+      missing[nm++] = e;
+    }
+  }
+  for (size_t x = 0; x < overhead; x++, rep++) {
+    isi[Kp + x] = b->rep_esi[rep] + pad;
+    in_row[Kp + x] = (uint32_t)Kp + (uint32_t)rep;
+  }
+  rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing};
+  int rc = rqb_solver_plan(b->sv, &req);
+  free(isi);
+  free(in_row);
+  bool ok = false;
+  if (rc == 0 && rqb_solver_run(b->sv) == 0 && rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0) == 0) {
+    /* decode_repair_rows + write_repair_rows (:567-589) */
+    const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
+    for (size_t k = 0; k < nm; k++) {
+      transfer_symbol(rq, sbn, missing[k], (uint8_t *)sy + k * b->pitch, io, 1);
+      mask_set(b, missing[k]);
+    }
+    b->gaps = 0;
+    ok = true;
+  } else {
+    rqb_solver_sync(b->sv);
+  }
+  free(missing);
+  return ok;
+}

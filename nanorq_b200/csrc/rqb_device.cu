@@ -1,0 +1,518 @@
+// rqb_device.cu -- sm_100a kernels for the nanorq hot path + the extern "C" shim.
+//
+// Kernels (reference function each one replaces):
+//   rqb_solve_kernel   precode_matrix_apply_sched + precode_matrix_permute
+//                      (lib/precode.c:3-32,379-389) and decode_row for the symbols
+//                      requested with the solve (lib/nanorq.c:184-204).
+//                      Column-sliced: one CTA owns a VB-byte slice of every row of
+//                      the block in shared memory and interprets the host-built
+//                      program (rqb_program.h); pages of the program are staged by
+//                      TMA bulk copies (cp.async.bulk + mbarrier) into a ring.
+//   rqb_lt_kernel      decode_row / gen_tuple on demand (lib/nanorq.c:184-204,
+//                      lib/tuple.c:21-43), tuples computed on the device.
+//   rqb_rowops_kernel  oaxpy / oaddrow / oscal (deps/oblas/oblas_avx.c:43-114) as a
+//                      batch of independent row ops streaming out of HBM with
+//                      128-bit accesses.
+//   rqb_gather_rows_kernel  precode_matrix_permute as an out-of-place gather.
+//
+// All arithmetic is GF(2)/GF(256) integer work (poly 0x11D); no tensor cores.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "rfc6330_tables.h"
+#include "rqb_device.h"
+#include "rqb_program.h"
+
+// ---------------------------------------------------------------- constants
+__constant__ uint32_t c_rand_v[4][256];
+__constant__ uint32_t c_degree_cdf[31];
+
+static constexpr int kSolveThreads = 256;
+static constexpr int kRingStages = 4;
+static constexpr uint32_t kRingBytes = kRingStages * RQB_PAGE_BYTES;
+static constexpr uint32_t kSolveSmemFixed = kRingBytes + 128; // ring + mbarriers
+static constexpr uint32_t kMaxSmem = 232448;                  // 227 KB opt-in limit
+
+// ------------------------------------------------------------- GF(256) SWAR
+// 4 packed field elements per 32-bit word.
+__device__ __forceinline__ uint32_t xtime4(uint32_t x) {
+  return ((x & 0x7f7f7f7fu) << 1) ^ (((x >> 7) & 0x01010101u) * 0x1du);
+}
+__device__ __forceinline__ uint32_t xtime1(uint32_t c) { // one element in the low byte
+  return ((c << 1) ^ ((c & 0x80u) ? 0x11du : 0u)) & 0xffu;
+}
+// the eight products beta*2^k, k=0..7
+struct BetaPlanes {
+  uint32_t c[8];
+};
+__device__ __forceinline__ BetaPlanes beta_planes(uint32_t beta) {
+  BetaPlanes p;
+  p.c[0] = beta;
+#pragma unroll
+  for (int k = 1; k < 8; k++) p.c[k] = xtime1(p.c[k - 1]);
+  return p;
+}
+// beta * x for 4 packed elements: sum over the bit planes of x
+__device__ __forceinline__ uint32_t gfmul4(uint32_t x, const BetaPlanes &p) {
+  uint32_t y = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) y ^= ((x >> k) & 0x01010101u) * p.c[k];
+  return y;
+}
+
+// ------------------------------------------------- VB-byte vectors in words
+template <int VB>
+struct Vec {
+  static constexpr int NW = VB >= 4 ? VB / 4 : 1;
+  uint32_t w[NW];
+};
+template <int VB>
+__device__ __forceinline__ Vec<VB> vzero() {
+  Vec<VB> v;
+#pragma unroll
+  for (int k = 0; k < Vec<VB>::NW; k++) v.w[k] = 0;
+  return v;
+}
+template <int VB>
+__device__ __forceinline__ Vec<VB> vload(const void *p) {
+  Vec<VB> v;
+  if constexpr (VB == 16) {
+    uint4 t = *reinterpret_cast<const uint4 *>(p);
+    v.w[0] = t.x; v.w[1] = t.y; v.w[2] = t.z; v.w[3] = t.w;
+  } else if constexpr (VB == 8) {
+    uint2 t = *reinterpret_cast<const uint2 *>(p);
+    v.w[0] = t.x; v.w[1] = t.y;
+  } else if constexpr (VB == 4) {
+    v.w[0] = *reinterpret_cast<const uint32_t *>(p);
+  } else {
+    v.w[0] = *reinterpret_cast<const uint16_t *>(p);
+  }
+  return v;
+}
+template <int VB>
+__device__ __forceinline__ void vstore(void *p, const Vec<VB> &v) {
+  if constexpr (VB == 16) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+  } else if constexpr (VB == 8) {
+    *reinterpret_cast<uint2 *>(p) = make_uint2(v.w[0], v.w[1]);
+  } else if constexpr (VB == 4) {
+    *reinterpret_cast<uint32_t *>(p) = v.w[0];
+  } else {
+    *reinterpret_cast<uint16_t *>(p) = (uint16_t)v.w[0];
+  }
+}
+template <int VB>
+__device__ __forceinline__ void vxor(Vec<VB> &a, const Vec<VB> &b) {
+#pragma unroll
+  for (int k = 0; k < Vec<VB>::NW; k++) a.w[k] ^= b.w[k];
+}
+
+// --------------------------------------------------- mbarrier / TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit, completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------- solve kernel
+// grid = (width / VB, nblocks); block = kSolveThreads; dynamic smem =
+// kSolveSmemFixed + max_slots * VB.  One lane executes one task on its CTA's slice.
+template <int VB>
+__global__ void __launch_bounds__(kSolveThreads)
+rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const rqb_solve_args a = args_list[blockIdx.y];
+  const uint32_t col0 = blockIdx.x * VB;
+  if (col0 >= a.width) return; // whole CTA leaves: no barrier is skipped by a subset
+  uint8_t *ring = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);
+  uint8_t *ws = smem + kSolveSmemFixed;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < kRingStages; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t first = a.n_pages < (uint32_t)kRingStages ? a.n_pages : (uint32_t)kRingStages;
+    for (uint32_t s = 0; s < first; s++) {
+      mbar_expect_tx(&bars[s], RQB_PAGE_BYTES);
+      tma_bulk_g2s(ring + s * RQB_PAGE_BYTES, a.pages + (size_t)s * RQB_PAGE_BYTES, RQB_PAGE_BYTES, &bars[s]);
+    }
+  }
+  // load this CTA's column slice of every row (zero rows where no input exists)
+  for (uint32_t slot = tid; slot < a.n_slots; slot += kSolveThreads) {
+    const uint32_t r = __ldg(&a.load_src[slot]);
+    Vec<VB> v = vzero<VB>();
+    if (r != RQB_ROW_NONE) v = vload<VB>(a.in + (size_t)r * a.in_pitch + col0);
+    vstore<VB>(ws + (size_t)slot * VB, v);
+  }
+  __syncthreads();
+
+  for (uint32_t pg = 0; pg < a.n_pages; pg++) {
+    const uint32_t st = pg % kRingStages;
+    mbar_wait(&bars[st], (pg / kRingStages) & 1u);
+    const uint8_t *page = ring + st * RQB_PAGE_BYTES;
+    const uint32_t n_levels = reinterpret_cast<const rqb_page_hdr *>(page)->n_levels;
+    uint32_t off = sizeof(rqb_page_hdr);
+    for (uint32_t lv = 0; lv < n_levels; lv++) {
+      const uint4 lh = *reinterpret_cast<const uint4 *>(page + off); // n_tasks, next_off
+      const uint4 *tasks = reinterpret_cast<const uint4 *>(page + off + sizeof(rqb_level_hdr));
+      for (uint32_t t = tid; t < lh.x; t += kSolveThreads) {
+        const uint4 th = tasks[t]; // {src_off, arg, nsrc | dst<<16, kind}
+        const uint32_t nsrc = th.z & 0xffffu, dst = th.z >> 16, kind = th.w & 0xffu;
+        const uint8_t *sp = page + th.x;
+        if (kind == RQB_T_GF_SET || kind == RQB_T_GF_ACC) {
+          Vec<VB> acc = vzero<VB>();
+          if (kind == RQB_T_GF_ACC) acc = vload<VB>(ws + (size_t)dst * VB);
+          const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp);
+          for (uint32_t k = 0; k < nsrc; k++) {
+            const uint32_t e = s32[k];
+            const Vec<VB> x = vload<VB>(ws + (size_t)(e & 0xffffu) * VB);
+            const BetaPlanes bp = beta_planes((e >> 16) & 0xffu);
+#pragma unroll
+            for (int q = 0; q < Vec<VB>::NW; q++) acc.w[q] ^= gfmul4(x.w[q], bp);
+          }
+          vstore<VB>(ws + (size_t)dst * VB, acc);
+        } else if (kind == RQB_T_HORNER) {
+          const uint32_t H = th.y;
+          const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp);
+          for (uint32_t h = 0; h < H; h++) vstore<VB>(ws + (size_t)(dst + h) * VB, vzero<VB>());
+          Vec<VB> y = vzero<VB>();
+          for (uint32_t k = 0; k < nsrc; k++) {
+            const uint32_t e = s32[k], slot = e & 0xffffu;
+#pragma unroll
+            for (int q = 0; q < Vec<VB>::NW; q++) y.w[q] = xtime4(y.w[q]);
+            if (slot != RQB_SLOT_NONE) vxor<VB>(y, vload<VB>(ws + (size_t)slot * VB));
+            if (e & (1u << 24)) {
+              uint8_t *p1 = ws + (size_t)(dst + ((e >> 16) & 15u)) * VB;
+              uint8_t *p2 = ws + (size_t)(dst + ((e >> 20) & 15u)) * VB;
+              Vec<VB> a1 = vload<VB>(p1), a2 = vload<VB>(p2);
+              vxor<VB>(a1, y);
+              vxor<VB>(a2, y);
+              vstore<VB>(p1, a1);
+              vstore<VB>(p2, a2);
+            }
+          }
+          vstore<VB>(ws + (size_t)(dst + H) * VB, y);
+        } else {
+          Vec<VB> acc = vzero<VB>();
+          if (kind == RQB_T_XOR_ACC)
+            acc = vload<VB>(ws + (size_t)dst * VB);
+          else if (kind == RQB_T_LOAD_XOR && th.y != RQB_ROW_NONE)
+            acc = vload<VB>(a.in + (size_t)th.y * a.in_pitch + col0);
+          const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sp);
+          uint32_t k = 0;
+          for (; k + 4 <= nsrc; k += 4) { // lists are 8-byte aligned and padded
+            const uint2 q = *reinterpret_cast<const uint2 *>(s16 + k);
+            const Vec<VB> x0 = vload<VB>(ws + (size_t)(q.x & 0xffffu) * VB);
+            const Vec<VB> x1 = vload<VB>(ws + (size_t)(q.x >> 16) * VB);
+            const Vec<VB> x2 = vload<VB>(ws + (size_t)(q.y & 0xffffu) * VB);
+            const Vec<VB> x3 = vload<VB>(ws + (size_t)(q.y >> 16) * VB);
+#pragma unroll
+            for (int w = 0; w < Vec<VB>::NW; w++) acc.w[w] ^= x0.w[w] ^ x1.w[w] ^ x2.w[w] ^ x3.w[w];
+          }
+          for (; k < nsrc; k++) vxor<VB>(acc, vload<VB>(ws + (size_t)s16[k] * VB));
+          if (kind == RQB_T_OUT_C)
+            vstore<VB>(a.c_out + (size_t)th.y * a.c_pitch + col0, acc);
+          else if (kind == RQB_T_OUT_SYM)
+            vstore<VB>(a.sym_out + (size_t)th.y * a.sym_pitch + col0, acc);
+          else
+            vstore<VB>(ws + (size_t)dst * VB, acc);
+        }
+      }
+      __syncthreads();
+      off = lh.y;
+    }
+    if (n_levels == 0) __syncthreads();
+    // every thread is past its last read of this stage: refill it
+    if (tid == 0 && pg + kRingStages < a.n_pages) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[st], RQB_PAGE_BYTES);
+      tma_bulk_g2s(ring + st * RQB_PAGE_BYTES, a.pages + (size_t)(pg + kRingStages) * RQB_PAGE_BYTES,
+                   RQB_PAGE_BYTES, &bars[st]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LT kernel
+// one CTA per output symbol; lane 0 expands Tuple[K', isi] into row indices.
+__global__ void __launch_bounds__(128)
+rqb_lt_kernel(rqb_params P, const uint8_t *__restrict__ c, uint32_t c_pitch,
+              const uint32_t *__restrict__ isi, uint8_t *__restrict__ out, uint32_t out_pitch,
+              uint32_t width) {
+  __shared__ uint32_t idx[RQB_MAX_LT_DEGREE];
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = rqb_lt_indices(&P, c_rand_v, c_degree_cdf, isi[blockIdx.x], idx);
+  __syncthreads();
+  const int n = cnt;
+  for (uint32_t v = threadIdx.x * 16; v < width; v += blockDim.x * 16) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < n; k++) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4 *>(c + (size_t)idx[k] * c_pitch + v));
+      acc.x ^= x.x; acc.y ^= x.y; acc.z ^= x.z; acc.w ^= x.w;
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)blockIdx.x * out_pitch + v) = acc;
+  }
+}
+
+// ------------------------------------------------------------ row-op kernel
+// flat index over (op, 16-byte chunk); reads src+dst, writes dst: 3*T bytes per axpy.
+__global__ void __launch_bounds__(256)
+rqb_rowops_kernel(uint8_t *__restrict__ D, size_t pitch, uint32_t vpr /* uint4 per row */,
+                  const rqb_rowop *__restrict__ ops, uint32_t n) {
+  const uint64_t total = (uint64_t)n * vpr;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = (uint32_t)(g / vpr), v = (uint32_t)(g - (uint64_t)o * vpr);
+    const uint32_t beta = ops[o].beta, i = ops[o].i, j = ops[o].j;
+    uint4 *dp = reinterpret_cast<uint4 *>(D + (size_t)i * pitch) + v;
+    if (beta == 0) { // oscal: multiplier in j; u < 2 is a no-op (oblas_avx.c:94-95)
+      const uint32_t u = j & 0xffu;
+      if (u < 2) continue;
+      const BetaPlanes bp = beta_planes(u);
+      uint4 d = *dp;
+      d.x = gfmul4(d.x, bp); d.y = gfmul4(d.y, bp); d.z = gfmul4(d.z, bp); d.w = gfmul4(d.w, bp);
+      *dp = d;
+    } else {
+      const uint4 s = *(reinterpret_cast<const uint4 *>(D + (size_t)j * pitch) + v);
+      uint4 d = *dp;
+      if (beta == 1) {
+        d.x ^= s.x; d.y ^= s.y; d.z ^= s.z; d.w ^= s.w;
+      } else {
+        const BetaPlanes bp = beta_planes(beta);
+        d.x ^= gfmul4(s.x, bp); d.y ^= gfmul4(s.y, bp); d.z ^= gfmul4(s.z, bp); d.w ^= gfmul4(s.w, bp);
+      }
+      *dp = d;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rqb_gather_rows_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *__restrict__ src,
+                       size_t spitch, const uint32_t *__restrict__ map, uint32_t n, uint32_t vpr) {
+  const uint64_t total = (uint64_t)n * vpr;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(g / vpr), v = (uint32_t)(g - (uint64_t)r * vpr);
+    reinterpret_cast<uint4 *>(dst + (size_t)r * dpitch)[v] =
+        __ldg(reinterpret_cast<const uint4 *>(src + (size_t)map[r] * spitch) + v);
+  }
+}
+
+// ------------------------------------------------------------------- shim
+static thread_local char g_err[256] = "";
+static unsigned long long g_launches = 0;
+static int g_consts_dev[64];
+
+static int fail(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+#define CK(x)                          \
+  do {                                 \
+    int _e = fail((x), #x);            \
+    if (_e) return _e;                 \
+  } while (0)
+
+static int ensure_consts() {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 64 && g_consts_dev[dev]) return 0;
+  CK(cudaMemcpyToSymbol(c_rand_v, rqb_rand_v, sizeof(rqb_rand_v)));
+  CK(cudaMemcpyToSymbol(c_degree_cdf, rqb_degree_cdf, sizeof(rqb_degree_cdf)));
+  if (dev < 64) g_consts_dev[dev] = 1;
+  return 0;
+}
+
+template <int VB>
+static int launch_solve_t(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots, uint32_t max_width,
+                          cudaStream_t st) {
+  const uint32_t smem = kSolveSmemFixed + max_slots * VB;
+  static uint32_t configured[64];
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 64 || configured[dev] < smem) {
+    CK(cudaFuncSetAttribute(rqb_solve_kernel<VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    if (dev < 64) configured[dev] = kMaxSmem;
+  }
+  dim3 grid((max_width + VB - 1) / VB, (unsigned)nblocks);
+  rqb_solve_kernel<VB><<<grid, kSolveThreads, smem, st>>>(args_dev);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+const char *rqb_dev_last_error(void) { return g_err; }
+unsigned long long rqb_dev_launch_count(void) { return g_launches; }
+
+int rqb_dev_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int rqb_dev_set(int dev) { CK(cudaSetDevice(dev)); return 0; }
+int rqb_dev_get(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+int rqb_dev_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+int rqb_dev_malloc(void **p, size_t bytes) { CK(cudaMalloc(p, bytes ? bytes : 16)); return 0; }
+int rqb_dev_free(void *p) { CK(cudaFree(p)); return 0; }
+int rqb_host_malloc(void **p, size_t bytes) { CK(cudaMallocHost(p, bytes ? bytes : 16)); return 0; }
+int rqb_host_free(void *p) { CK(cudaFreeHost(p)); return 0; }
+int rqb_stream_create(void **s) {
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = (void *)st;
+  return 0;
+}
+int rqb_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
+int rqb_stream_sync(void *s) { CK(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
+int rqb_dev_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
+int rqb_copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_copy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_copy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_copy2d_h2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                   void *stream) {
+  CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_copy2d_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                   void *stream) {
+  CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_dev_memset(void *p, int v, size_t bytes, void *stream) {
+  CK(cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream));
+  return 0;
+}
+int rqb_event_create(void **e) {
+  cudaEvent_t ev;
+  CK(cudaEventCreate(&ev));
+  *e = (void *)ev;
+  return 0;
+}
+int rqb_event_destroy(void *e) { CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
+int rqb_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream)); return 0; }
+int rqb_event_sync(void *e) { CK(cudaEventSynchronize((cudaEvent_t)e)); return 0; }
+int rqb_event_elapsed_ms(void *start, void *stop, float *ms) {
+  CK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+
+int rqb_solve_pick_vec(uint32_t n_slots) {
+  for (int vb = 16; vb >= 2; vb >>= 1)
+    if ((uint64_t)kSolveSmemFixed + (uint64_t)n_slots * vb <= kMaxSmem) return vb;
+  return 0;
+}
+
+int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots, uint32_t max_width,
+                     int vec_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((uint64_t)kSolveSmemFixed + (uint64_t)max_slots * (uint32_t)vec_bytes > kMaxSmem) {
+    snprintf(g_err, sizeof(g_err), "solve: %u slots x %d bytes exceed shared memory", max_slots, vec_bytes);
+    return (int)cudaErrorInvalidValue;
+  }
+  switch (vec_bytes) {
+    case 16: return launch_solve_t<16>(args_dev, nblocks, max_slots, max_width, st);
+    case 8: return launch_solve_t<8>(args_dev, nblocks, max_slots, max_width, st);
+    case 4: return launch_solve_t<4>(args_dev, nblocks, max_slots, max_width, st);
+    case 2: return launch_solve_t<2>(args_dev, nblocks, max_slots, max_width, st);
+  }
+  snprintf(g_err, sizeof(g_err), "solve: bad vec_bytes %d", vec_bytes);
+  return (int)cudaErrorInvalidValue;
+}
+
+int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const uint32_t *isi_dev, uint32_t n,
+                  uint8_t *out, uint32_t out_pitch, uint32_t width, void *stream) {
+  if (n == 0) return 0;
+  int e = ensure_consts();
+  if (e) return e;
+  rqb_lt_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(*P, c, c_pitch, isi_dev, out, out_pitch, width);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static unsigned stream_grid(uint64_t total, int threads) {
+  int sms = rqb_dev_sm_count();
+  if (sms <= 0) sms = 148;
+  uint64_t want = (total + threads - 1) / threads, cap = (uint64_t)sms * 16;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+int rqb_launch_rowops(uint8_t *D, size_t pitch, uint32_t width, const rqb_rowop *ops_dev, uint32_t n,
+                      void *stream) {
+  if (n == 0) return 0;
+  const uint32_t vpr = width / 16;
+  rqb_rowops_kernel<<<stream_grid((uint64_t)n * vpr, 256), 256, 0, (cudaStream_t)stream>>>(D, pitch, vpr, ops_dev, n);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rqb_launch_gather_rows(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch,
+                           const uint32_t *map_dev, uint32_t n, uint32_t width, void *stream) {
+  if (n == 0) return 0;
+  const uint32_t vpr = width / 16;
+  rqb_gather_rows_kernel<<<stream_grid((uint64_t)n * vpr, 256), 256, 0, (cudaStream_t)stream>>>(
+      dst, dpitch, src, spitch, map_dev, n, vpr);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,96 @@
+/* rqb_device.h -- the thin extern "C" shim between the C host code and the
+ * sm_100a kernels in rqb_device.cu.  Plain pointers and sizes only.
+ * Every function returns 0 on success or a cudaError_t value; the text of the
+ * last failure is available from rqb_dev_last_error(). */
+#ifndef RQB_DEVICE_H
+#define RQB_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rqb_rfc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* one row operation, binary-compatible with the reference's sched_op
+ * (include/sched.h:6-10): beta>=1: D[i] ^= beta*D[j] ; beta==0: D[i] *= (uint8_t)j */
+typedef struct {
+  uint8_t beta;
+  uint32_t i;
+  uint32_t j;
+} rqb_rowop;
+
+/* arguments of one source block for the column-sliced solve kernel
+ * (all pointers are DEVICE pointers) */
+typedef struct {
+  const uint8_t *in;        /* input symbol rows                         */
+  uint8_t *c_out;           /* intermediate symbols, row = index (or 0)  */
+  uint8_t *sym_out;         /* requested encoding symbols (or 0)         */
+  const uint32_t *load_src; /* [n_slots] input row per slot / ROW_NONE   */
+  const uint8_t *pages;     /* program pages                             */
+  uint32_t in_pitch, c_pitch, sym_pitch; /* bytes, multiples of 64       */
+  uint32_t n_slots, n_pages;
+  uint32_t width;           /* bytes per row to process (multiple of 16) */
+} rqb_solve_args;
+
+int rqb_dev_count(void);
+int rqb_dev_set(int dev);
+int rqb_dev_get(void);
+int rqb_dev_sm_count(void);
+const char *rqb_dev_last_error(void);
+
+int rqb_dev_malloc(void **p, size_t bytes);
+int rqb_dev_free(void *p);
+int rqb_host_malloc(void **p, size_t bytes); /* pinned */
+int rqb_host_free(void *p);
+int rqb_stream_create(void **s);
+int rqb_stream_destroy(void *s);
+int rqb_stream_sync(void *s);
+int rqb_dev_sync(void);
+int rqb_copy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int rqb_copy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int rqb_copy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int rqb_copy2d_h2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                   size_t rows, void *stream);
+int rqb_copy2d_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                   size_t rows, void *stream);
+int rqb_dev_memset(void *p, int v, size_t bytes, void *stream);
+int rqb_event_create(void **e);
+int rqb_event_destroy(void *e);
+int rqb_event_record(void *e, void *stream);
+int rqb_event_sync(void *e);
+int rqb_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* bytes of shared memory the solve kernel needs for n_slots rows of vec bytes;
+ * picks the widest slice (16, 8, 4, 2 bytes) that fits; 0 = does not fit */
+int rqb_solve_pick_vec(uint32_t n_slots);
+/* launches ONE kernel over nblocks source blocks (gridDim.y); args_dev is a
+ * device array of rqb_solve_args; max_* are maxima over the batch */
+int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots,
+                     uint32_t max_width, int vec_bytes, void *stream);
+
+/* LT combine (decode_row, lib/nanorq.c:184-204): out[k] = XOR of the
+ * intermediate symbols selected by Tuple[K', isi[k]]; tuples are generated on
+ * the device.  isi_dev: device array. */
+int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const uint32_t *isi_dev,
+                  uint32_t n, uint8_t *out, uint32_t out_pitch, uint32_t width, void *stream);
+
+/* batched row operations out of HBM (oaxpy/oaddrow/oscal, oblas_avx.c:43-114).
+ * The ops of one call must be independent of each other (no op reads or writes a
+ * row another op writes).  ops_dev: device array. */
+int rqb_launch_rowops(uint8_t *D, size_t pitch, uint32_t width, const rqb_rowop *ops_dev,
+                      uint32_t n, void *stream);
+/* out-of-place row gather (precode_matrix_permute, lib/precode.c:3-13):
+ * dst[k] = src[map[k]] */
+int rqb_launch_gather_rows(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch,
+                           const uint32_t *map_dev, uint32_t n, uint32_t width, void *stream);
+
+/* kernels launched by this process so far (bench.py's gpu_launches) */
+unsigned long long rqb_dev_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,683 @@
+/* rqb_solver.c -- host side of the rqb200.h C ABI: per-block device contexts,
+ * buffer pool, process-wide cache of encoder plans, batched row ops and the
+ * reference-format schedule replay.  Plain C; the device work is done by the
+ * kernels behind rqb_device.h.  There is no CPU fallback anywhere in this
+ * file: symbol bytes are only ever combined on the GPU. */
+#define _POSIX_C_SOURCE 200809L
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rqb200.h"
+#include "rqb_device.h"
+#include "rqb_planner.h"
+#include "rqb_program.h"
+
+static __thread char g_err[320];
+
+const char *rqb_last_error(void) { return g_err; }
+
+static int dev_fail(int e, const char *what) {
+  snprintf(g_err, sizeof(g_err), "%s failed: %s", what, rqb_dev_last_error());
+  (void)e;
+  return RQB_E_NODEVICE;
+}
+#define DEV(x)                               \
+  do {                                       \
+    int _e = (x);                            \
+    if (_e) return dev_fail(_e, #x);         \
+  } while (0)
+
+int rqb_device_count(void) { return rqb_dev_count(); }
+int rqb_set_device(int dev) {
+  DEV(rqb_dev_set(dev));
+  return 0;
+}
+unsigned long long rqb_kernel_launches(void) { return rqb_dev_launch_count(); }
+
+int rqb_block_params_init(int K, rqb_block_params *out) {
+  rqb_params P;
+  if (rqb_params_init(K, &P)) return RQB_E_ARG;
+  memcpy(out, &P, sizeof(P));
+  return 0;
+}
+
+int rqb_lt_row_indices(int K, uint32_t isi, uint32_t *out) {
+  rqb_params P;
+  if (rqb_params_init(K, &P)) return RQB_E_ARG;
+  return rqb_host_lt_indices(&P, isi, out);
+}
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+/* ------------------------------------------------------------ buffer pool
+ * cudaMalloc / cudaMallocHost cost milliseconds; blocks come and go at wire
+ * rate, so freed buffers are kept and handed out again (per device). */
+typedef struct pool_ent {
+  void *p;
+  size_t bytes;
+  int dev, pinned;
+  struct pool_ent *next;
+} pool_ent;
+static pool_ent *g_pool;
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static size_t pool_class(size_t bytes) {
+  size_t c = 4096;
+  while (c < bytes && c < ((size_t)1 << 20)) c <<= 1;
+  if (c >= bytes) return c;
+  return round_up(bytes, (size_t)1 << 20);
+}
+
+static int pool_get(void **out, size_t bytes, int pinned) {
+  size_t cls = pool_class(bytes);
+  int dev = pinned ? -1 : rqb_dev_get();
+  pthread_mutex_lock(&g_pool_mu);
+  for (pool_ent **pp = &g_pool; *pp; pp = &(*pp)->next) {
+    pool_ent *e = *pp;
+    if (e->pinned == pinned && e->dev == dev && e->bytes == cls) {
+      *pp = e->next;
+      pthread_mutex_unlock(&g_pool_mu);
+      *out = e->p;
+      free(e);
+      return 0;
+    }
+  }
+  pthread_mutex_unlock(&g_pool_mu);
+  return pinned ? rqb_host_malloc(out, cls) : rqb_dev_malloc(out, cls);
+}
+
+static void pool_put(void *p, size_t bytes, int pinned) {
+  if (!p) return;
+  pool_ent *e = malloc(sizeof(*e));
+  e->p = p;
+  e->bytes = pool_class(bytes);
+  e->pinned = pinned;
+  e->dev = pinned ? -1 : rqb_dev_get();
+  pthread_mutex_lock(&g_pool_mu);
+  e->next = g_pool;
+  g_pool = e;
+  pthread_mutex_unlock(&g_pool_mu);
+}
+
+/* --------------------------------------------------- encoder plan cache
+ * The constraint matrix of an encoder depends only on K (isi = identity), like
+ * the schedule nanorq_precalculate keeps in rq->S (lib/nanorq.c:393-401); here
+ * it is cached process-wide together with its device copy. */
+typedef struct enc_plan {
+  int K, Kparams, want_c, dev;
+  uint32_t n_out;
+  rqb_plan *plan;
+  uint8_t *d_pages;
+  uint32_t *d_load;
+  struct enc_plan *next;
+} enc_plan;
+static enc_plan *g_enc_plans;
+static pthread_mutex_t g_plan_mu = PTHREAD_MUTEX_INITIALIZER;
+
+/* ------------------------------------------------------------- solver */
+struct rqb_solver {
+  int K, Kparams, dev;
+  size_t T, pitch;
+  rqb_params P;
+  uint32_t max_in, max_out;
+  void *stream, *ev0, *ev1;
+  uint8_t *h_in, *d_in, *d_c, *d_sym, *h_sym;
+  uint32_t *d_isi, *h_isi;
+  /* current program */
+  rqb_plan *plan; /* owned unless shared */
+  int plan_shared, has_c, vec_bytes, timed;
+  uint8_t *d_pages;
+  size_t d_pages_cap;
+  uint32_t *d_load;
+  size_t d_load_cap;
+  const uint8_t *cur_pages; /* device pointers actually used (own or cached) */
+  const uint32_t *cur_load;
+  rqb_solve_args *h_args, *d_args; /* pinned / device, one entry (batch uses [n]) */
+  uint32_t n_out_last;
+};
+
+size_t rqb_solver_pitch(const rqb_solver *s) { return s->pitch; }
+uint8_t *rqb_solver_staging(rqb_solver *s) { return s->h_in; }
+const uint8_t *rqb_solver_sym_mirror(rqb_solver *s) { return s->h_sym; }
+
+void rqb_solver_destroy(rqb_solver *s) {
+  if (!s) return;
+  if (s->stream) rqb_stream_sync(s->stream);
+  int cur = rqb_dev_get();
+  if (cur != s->dev) rqb_dev_set(s->dev);
+  pool_put(s->h_in, (size_t)s->max_in * s->pitch, 1);
+  pool_put(s->d_in, (size_t)s->max_in * s->pitch, 0);
+  pool_put(s->d_c, (size_t)s->P.L * s->pitch, 0);
+  pool_put(s->d_sym, (size_t)s->max_out * s->pitch, 0);
+  pool_put(s->h_sym, (size_t)s->max_out * s->pitch, 1);
+  pool_put(s->d_isi, (size_t)s->max_out * 4, 0);
+  pool_put(s->h_isi, (size_t)s->max_out * 4, 1);
+  pool_put(s->d_pages, s->d_pages_cap, 0);
+  pool_put(s->d_load, s->d_load_cap, 0);
+  pool_put(s->h_args, 4096, 1);
+  pool_put(s->d_args, 4096, 0);
+  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  if (s->ev0) rqb_event_destroy(s->ev0);
+  if (s->ev1) rqb_event_destroy(s->ev1);
+  if (s->stream) rqb_stream_destroy(s->stream);
+  if (cur != s->dev && cur >= 0) rqb_dev_set(cur);
+  free(s);
+}
+
+int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32_t max_out) {
+  return rqb_solver_create_ex(out, K, K, T, max_in, max_out);
+}
+
+int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_t max_in, uint32_t max_out) {
+  *out = NULL;
+  rqb_params P;
+  if (K < 1 || rqb_params_init(Kparams, &P) || K > P.Kprime || T == 0 || T > 65535 || max_in < (uint32_t)K) {
+    snprintf(g_err, sizeof(g_err), "rqb_solver_create: bad arguments");
+    return RQB_E_ARG;
+  }
+  if (rqb_dev_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device visible: the nanorq_b200 hot path has no CPU fallback");
+    return RQB_E_NODEVICE;
+  }
+  rqb_solver *s = calloc(1, sizeof(*s));
+  s->K = K;
+  s->Kparams = Kparams;
+  s->T = T;
+  s->pitch = round_up(T, 64);
+  s->P = P;
+  s->max_in = max_in;
+  s->max_out = max_out ? max_out : 1;
+  s->dev = rqb_dev_get();
+  int e = 0;
+  e = e ? e : rqb_stream_create(&s->stream);
+  e = e ? e : rqb_event_create(&s->ev0);
+  e = e ? e : rqb_event_create(&s->ev1);
+  e = e ? e : pool_get((void **)&s->h_in, (size_t)s->max_in * s->pitch, 1);
+  e = e ? e : pool_get((void **)&s->d_in, (size_t)s->max_in * s->pitch, 0);
+  e = e ? e : pool_get((void **)&s->d_c, (size_t)P.L * s->pitch, 0);
+  e = e ? e : pool_get((void **)&s->d_sym, (size_t)s->max_out * s->pitch, 0);
+  e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->max_out * s->pitch, 1);
+  e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->max_out * 4, 0);
+  e = e ? e : pool_get((void **)&s->h_isi, (size_t)s->max_out * 4, 1);
+  e = e ? e : pool_get((void **)&s->h_args, 4096, 1);
+  e = e ? e : pool_get((void **)&s->d_args, 4096, 0);
+  if (e) {
+    dev_fail(e, "rqb_solver_create allocation");
+    rqb_solver_destroy(s);
+    return RQB_E_NODEVICE;
+  }
+  /* pad bytes of the staging rows must be zero: they are transformed too (pool
+   * buffers are recycled, symbol bytes are always overwritten before use) */
+  if (s->pitch > T)
+    for (uint32_t r = 0; r < s->max_in; r++) memset(s->h_in + (size_t)r * s->pitch + T, 0, s->pitch - T);
+  *out = s;
+  return 0;
+}
+
+int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
+  if ((uint64_t)first + n > s->max_in) return RQB_E_ARG;
+  if (!n) return 0;
+  DEV(rqb_copy_h2d(s->d_in + (size_t)first * s->pitch, s->h_in + (size_t)first * s->pitch,
+                   (size_t)n * s->pitch, s->stream));
+  return 0;
+}
+
+static void fill_stats(const rqb_plan *p, int vec, rqb_solver_stats *o) {
+  memset(o, 0, sizeof(*o));
+  o->i = p->st.i; o->u = p->st.u; o->nb = p->st.nb; o->rho = p->st.rho; o->nfree = p->st.nfree;
+  o->levels_fwd = p->st.levels_fwd; o->n_levels = p->st.n_levels; o->n_tasks = p->st.n_tasks;
+  o->n_pages = p->st.n_pages; o->n_srcs = p->st.n_srcs; o->n_gf_srcs = p->st.n_gf_srcs;
+  o->n_horner = p->st.n_horner; o->nnz = p->st.nnz; o->t_matrix = p->st.t_matrix;
+  o->t_peel = p->st.t_peel; o->t_dense = p->st.t_dense; o->t_emit = p->st.t_emit;
+  o->n_slots = p->n_slots;
+  o->vec_bytes = vec;
+}
+
+int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out) {
+  if (!s->plan) return RQB_E_ARG;
+  fill_stats(s->plan, s->vec_bytes, out);
+  return 0;
+}
+
+static int solver_set_args(rqb_solver *s) {
+  const rqb_plan *p = s->plan;
+  s->vec_bytes = rqb_solve_pick_vec(p->n_slots);
+  if (!s->vec_bytes) {
+    snprintf(g_err, sizeof(g_err), "block needs %u shared-memory rows: too large for the column-sliced solver",
+             p->n_slots);
+    return RQB_E_TOOBIG;
+  }
+  rqb_solve_args *a = s->h_args;
+  memset(a, 0, sizeof(*a));
+  a->in = s->d_in;
+  a->c_out = s->d_c;
+  a->sym_out = s->d_sym;
+  a->load_src = s->cur_load;
+  a->pages = s->cur_pages;
+  a->in_pitch = a->c_pitch = a->sym_pitch = (uint32_t)s->pitch;
+  a->n_slots = p->n_slots;
+  a->n_pages = p->n_pages;
+  a->width = (uint32_t)round_up(s->T, 16);
+  DEV(rqb_copy_h2d(s->d_args, s->h_args, sizeof(*a), s->stream));
+  s->has_c = p->n_c_rows != 0;
+  s->n_out_last = p->n_out;
+  return 0;
+}
+
+int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
+  if (req->n_out > s->max_out) return RQB_E_ARG;
+  rqb_plan_request pr;
+  pr.K = s->Kparams;
+  pr.overhead = req->overhead;
+  pr.isi = req->isi;
+  pr.in_row = req->in_row;
+  pr.want_c = req->want_c;
+  pr.n_out = (int)req->n_out;
+  pr.out_isi = req->out_isi;
+  rqb_plan *p = NULL;
+  int rc = rqb_plan_build(&pr, &p);
+  if (rc == 1) return RQB_NEED_MORE;
+  if (rc) {
+    snprintf(g_err, sizeof(g_err), "rqb_plan_build failed (%d)", rc);
+    return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
+  }
+  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  s->plan = p;
+  s->plan_shared = 0;
+  size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES, lb = (size_t)p->n_slots * 4;
+  if (pb > s->d_pages_cap) {
+    pool_put(s->d_pages, s->d_pages_cap, 0);
+    s->d_pages = NULL;
+    s->d_pages_cap = 0;
+    DEV(pool_get((void **)&s->d_pages, pb, 0));
+    s->d_pages_cap = pb;
+  }
+  if (lb > s->d_load_cap) {
+    pool_put(s->d_load, s->d_load_cap, 0);
+    s->d_load = NULL;
+    s->d_load_cap = 0;
+    DEV(pool_get((void **)&s->d_load, lb, 0));
+    s->d_load_cap = lb;
+  }
+  /* the plan's host arrays are pageable; the copies are small and stream-ordered */
+  DEV(rqb_copy_h2d(s->d_pages, p->pages, pb, s->stream));
+  DEV(rqb_copy_h2d(s->d_load, p->load_src, lb, s->stream));
+  s->cur_pages = s->d_pages;
+  s->cur_load = s->d_load;
+  return solver_set_args(s);
+}
+
+int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
+  if (n_rep > s->max_out) return RQB_E_ARG;
+  pthread_mutex_lock(&g_plan_mu);
+  enc_plan *e = g_enc_plans;
+  for (; e; e = e->next)
+    if (e->K == s->K && e->Kparams == s->Kparams && e->want_c == want_c && e->n_out == n_rep && e->dev == s->dev) break;
+  if (!e) {
+    const int Kp = s->P.Kprime;
+    uint32_t *isi = malloc(sizeof(uint32_t) * (size_t)Kp), *in_row = malloc(sizeof(uint32_t) * (size_t)Kp);
+    uint32_t *oi = malloc(sizeof(uint32_t) * (size_t)(n_rep ? n_rep : 1));
+    for (int k = 0; k < Kp; k++) {
+      isi[k] = (uint32_t)k;
+      in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
+    }
+    for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
+    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi};
+    rqb_plan *p = NULL;
+    int rc = rqb_plan_build(&pr, &p);
+    free(isi);
+    free(in_row);
+    free(oi);
+    if (rc) {
+      pthread_mutex_unlock(&g_plan_mu);
+      snprintf(g_err, sizeof(g_err), "encoder plan for K=%d failed (%d)", s->K, rc);
+      return rc == 1 ? RQB_NEED_MORE : (rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG);
+    }
+    e = calloc(1, sizeof(*e));
+    e->K = s->K;
+    e->Kparams = s->Kparams;
+    e->want_c = want_c;
+    e->n_out = n_rep;
+    e->dev = s->dev;
+    e->plan = p;
+    size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES, lb = (size_t)p->n_slots * 4;
+    int de = rqb_dev_malloc((void **)&e->d_pages, pb);
+    de = de ? de : rqb_dev_malloc((void **)&e->d_load, lb);
+    de = de ? de : rqb_copy_h2d(e->d_pages, p->pages, pb, s->stream);
+    de = de ? de : rqb_copy_h2d(e->d_load, p->load_src, lb, s->stream);
+    de = de ? de : rqb_stream_sync(s->stream);
+    if (de) {
+      pthread_mutex_unlock(&g_plan_mu);
+      return dev_fail(de, "encoder plan upload");
+    }
+    e->next = g_enc_plans;
+    g_enc_plans = e;
+  }
+  pthread_mutex_unlock(&g_plan_mu);
+  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  s->plan = e->plan;
+  s->plan_shared = 1;
+  s->cur_pages = e->d_pages;
+  s->cur_load = e->d_load;
+  return solver_set_args(s);
+}
+
+int rqb_solver_run(rqb_solver *s) {
+  if (!s->plan) return RQB_E_ARG;
+  DEV(rqb_event_record(s->ev0, s->stream));
+  DEV(rqb_launch_solve(s->d_args, 1, s->plan->n_slots, s->h_args->width, s->vec_bytes, s->stream));
+  DEV(rqb_event_record(s->ev1, s->stream));
+  s->timed = 1;
+  return 0;
+}
+
+int rqb_solver_run_batch(rqb_solver **sv, int n) {
+  if (n <= 0) return RQB_E_ARG;
+  if (n == 1) return rqb_solver_run(sv[0]);
+  rqb_solver *s0 = sv[0];
+  if ((size_t)n * sizeof(rqb_solve_args) > 4096) return RQB_E_ARG;
+  uint32_t max_slots = 0;
+  int vec = 16;
+  for (int k = 0; k < n; k++) {
+    if (!sv[k]->plan || sv[k]->T != s0->T || sv[k]->dev != s0->dev) return RQB_E_ARG;
+    if (k) DEV(rqb_stream_sync(sv[k]->stream)); /* its uploads must have landed */
+    if (sv[k]->plan->n_slots > max_slots) max_slots = sv[k]->plan->n_slots;
+    if (sv[k]->vec_bytes < vec) vec = sv[k]->vec_bytes;
+    s0->h_args[k] = *sv[k]->h_args;
+  }
+  DEV(rqb_copy_h2d(s0->d_args, s0->h_args, (size_t)n * sizeof(rqb_solve_args), s0->stream));
+  DEV(rqb_event_record(s0->ev0, s0->stream));
+  DEV(rqb_launch_solve(s0->d_args, n, max_slots, s0->h_args->width, vec, s0->stream));
+  DEV(rqb_event_record(s0->ev1, s0->stream));
+  s0->timed = 1;
+  return 0;
+}
+
+int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n) {
+  if (!s->has_c || n > s->max_out) return RQB_E_ARG;
+  memcpy(s->h_isi, isi, (size_t)n * 4);
+  DEV(rqb_copy_h2d(s->d_isi, s->h_isi, (size_t)n * 4, s->stream));
+  DEV(rqb_launch_lt(&s->P, s->d_c, (uint32_t)s->pitch, s->d_isi, n, s->d_sym, (uint32_t)s->pitch,
+                    (uint32_t)round_up(s->T, 16), s->stream));
+  s->n_out_last = n;
+  return 0;
+}
+
+int rqb_solver_sync(rqb_solver *s) {
+  DEV(rqb_stream_sync(s->stream));
+  return 0;
+}
+
+int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms) {
+  if (!s->timed) return RQB_E_ARG;
+  DEV(rqb_event_sync(s->ev1));
+  DEV(rqb_event_elapsed_ms(s->ev0, s->ev1, ms));
+  return 0;
+}
+
+int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch) {
+  if ((uint64_t)first + n > s->max_out) return RQB_E_ARG;
+  if (!n) return 0;
+  DEV(rqb_copy_d2h(s->h_sym + (size_t)first * s->pitch, s->d_sym + (size_t)first * s->pitch,
+                   (size_t)n * s->pitch, s->stream));
+  DEV(rqb_stream_sync(s->stream));
+  if (dst)
+    for (uint32_t k = 0; k < n; k++)
+      memcpy(dst + (size_t)k * dst_pitch, s->h_sym + (size_t)(first + k) * s->pitch, s->T);
+  return 0;
+}
+
+int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch) {
+  if (!s->has_c || (uint64_t)first + n > (uint32_t)s->P.L) return RQB_E_ARG;
+  DEV(rqb_copy2d_d2h(dst, dst_pitch, s->d_c + (size_t)first * s->pitch, s->pitch, s->T, n, s->stream));
+  DEV(rqb_stream_sync(s->stream));
+  return 0;
+}
+
+/* ------------------------------------------------ host-only plan access */
+int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out) {
+  rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi};
+  rqb_plan *p = NULL;
+  int rc = rqb_plan_build(&pr, &p);
+  memset(out, 0, sizeof(*out));
+  if (rc == 1) return RQB_NEED_MORE;
+  if (rc) return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
+  out->n_slots = p->n_slots;
+  out->n_pages = p->n_pages;
+  out->page_bytes = RQB_PAGE_BYTES;
+  out->load_src = p->load_src;
+  out->pages = p->pages;
+  out->opaque = p;
+  int vec = 16;
+  while (vec >= 2 && (size_t)p->n_slots * (size_t)vec + 4 * RQB_PAGE_BYTES + 128 > 232448) vec >>= 1;
+  fill_stats(p, vec >= 2 ? vec : 0, &out->stats);
+  return 0;
+}
+
+void rqb_plan_blob_free(rqb_plan_blob *b) {
+  if (b && b->opaque) rqb_plan_free((rqb_plan *)b->opaque);
+  if (b) memset(b, 0, sizeof(*b));
+}
+
+/* ------------------------------------------------------ HBM row matrix */
+struct rqb_matrix {
+  size_t rows, T, pitch;
+  uint8_t *d;
+  void *stream, *ev0, *ev1;
+  int dev;
+};
+struct rqb_oplist {
+  rqb_rowop *d;
+  size_t n;
+};
+
+size_t rqb_matrix_pitch(const rqb_matrix *m) { return m->pitch; }
+
+int rqb_matrix_create(rqb_matrix **out, size_t rows, size_t T) {
+  *out = NULL;
+  if (!rows || !T) return RQB_E_ARG;
+  if (rqb_dev_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device visible: the nanorq_b200 hot path has no CPU fallback");
+    return RQB_E_NODEVICE;
+  }
+  rqb_matrix *m = calloc(1, sizeof(*m));
+  m->rows = rows;
+  m->T = T;
+  m->pitch = round_up(T, 64);
+  m->dev = rqb_dev_get();
+  int e = rqb_stream_create(&m->stream);
+  e = e ? e : rqb_event_create(&m->ev0);
+  e = e ? e : rqb_event_create(&m->ev1);
+  e = e ? e : rqb_dev_malloc((void **)&m->d, rows * m->pitch);
+  e = e ? e : rqb_dev_memset(m->d, 0, rows * m->pitch, m->stream);
+  if (e) {
+    dev_fail(e, "rqb_matrix_create");
+    rqb_matrix_destroy(m);
+    return RQB_E_NODEVICE;
+  }
+  *out = m;
+  return 0;
+}
+
+void rqb_matrix_destroy(rqb_matrix *m) {
+  if (!m) return;
+  if (m->stream) rqb_stream_sync(m->stream);
+  if (m->d) rqb_dev_free(m->d);
+  if (m->ev0) rqb_event_destroy(m->ev0);
+  if (m->ev1) rqb_event_destroy(m->ev1);
+  if (m->stream) rqb_stream_destroy(m->stream);
+  free(m);
+}
+
+int rqb_matrix_upload(rqb_matrix *m, size_t first, size_t n, const uint8_t *src, size_t src_pitch) {
+  if (first + n > m->rows) return RQB_E_ARG;
+  DEV(rqb_copy2d_h2d(m->d + first * m->pitch, m->pitch, src, src_pitch, m->T, n, m->stream));
+  DEV(rqb_stream_sync(m->stream));
+  return 0;
+}
+
+int rqb_matrix_download(rqb_matrix *m, size_t first, size_t n, uint8_t *dst, size_t dst_pitch) {
+  if (first + n > m->rows) return RQB_E_ARG;
+  DEV(rqb_copy2d_d2h(dst, dst_pitch, m->d + first * m->pitch, m->pitch, m->T, n, m->stream));
+  DEV(rqb_stream_sync(m->stream));
+  return 0;
+}
+
+int rqb_matrix_fill_random(rqb_matrix *m, uint64_t seed) {
+  /* benchmark filler: a host xorshift tile repeated over the matrix by device copies */
+  size_t tile = (size_t)1 << 22, total = m->rows * m->pitch;
+  if (tile > total) tile = total;
+  uint8_t *h = malloc(tile);
+  uint64_t x = seed ? seed : 88172645463325252ULL;
+  for (size_t k = 0; k + 8 <= tile; k += 8) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    memcpy(h + k, &x, 8);
+  }
+  int e = rqb_copy_h2d(m->d, h, tile, m->stream);
+  e = e ? e : rqb_stream_sync(m->stream);
+  free(h);
+  if (e) return dev_fail(e, "fill_random");
+  for (size_t done = tile; done < total; done *= 2) {
+    size_t n = done < total - done ? done : total - done;
+    DEV(rqb_copy_d2d(m->d + done, m->d, n, m->stream));
+  }
+  DEV(rqb_stream_sync(m->stream));
+  return 0;
+}
+
+int rqb_ops_upload(rqb_oplist **out, const rqb_op *ops, size_t n) {
+  *out = NULL;
+  rqb_oplist *l = calloc(1, sizeof(*l));
+  l->n = n;
+  int e = rqb_dev_malloc((void **)&l->d, n * sizeof(rqb_rowop));
+  e = e ? e : rqb_copy_h2d(l->d, ops, n * sizeof(rqb_rowop), NULL);
+  e = e ? e : rqb_dev_sync();
+  if (e) {
+    free(l);
+    return dev_fail(e, "rqb_ops_upload");
+  }
+  *out = l;
+  return 0;
+}
+
+void rqb_ops_free(rqb_oplist *l) {
+  if (!l) return;
+  rqb_dev_free(l->d);
+  free(l);
+}
+
+int rqb_rowops_apply_dev(rqb_matrix *m, const rqb_oplist *l, int repeats, float *ms_total) {
+  if (repeats < 1) repeats = 1;
+  DEV(rqb_event_record(m->ev0, m->stream));
+  for (int r = 0; r < repeats; r++)
+    DEV(rqb_launch_rowops(m->d, m->pitch, (uint32_t)round_up(m->T, 16), l->d, (uint32_t)l->n, m->stream));
+  DEV(rqb_event_record(m->ev1, m->stream));
+  DEV(rqb_event_sync(m->ev1));
+  if (ms_total) DEV(rqb_event_elapsed_ms(m->ev0, m->ev1, ms_total));
+  return 0;
+}
+
+int rqb_rowops_apply(rqb_matrix *m, const rqb_op *ops, size_t n) {
+  if (!n) return 0;
+  for (size_t k = 0; k < n; k++)
+    if (ops[k].i >= m->rows || (ops[k].beta && ops[k].j >= m->rows)) return RQB_E_ARG;
+  rqb_oplist *l = NULL;
+  int rc = rqb_ops_upload(&l, ops, n);
+  if (rc) return rc;
+  rc = rqb_rowops_apply_dev(m, l, 1, NULL);
+  rqb_ops_free(l);
+  return rc;
+}
+
+/* ------------------------------------------- reference-schedule replay */
+int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, long m1, const int *di,
+                        size_t rows, const int *c, size_t cols, float *ms_device) {
+  if (rows > m->rows || cols > m->rows || m0 < -1 || m1 < 0 || (size_t)m1 > nops || m0 >= (long)nops)
+    return RQB_E_ARG;
+  /* 1. the applied sequence of precode_matrix_apply_sched (lib/precode.c:23-32) */
+  size_t napp = nops + 2 * (size_t)(m0 + 1), k = 0;
+  rqb_rowop *seq = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
+  for (long q = 0; q < m1; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
+  for (long q = m0; q >= 0; q--) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
+  for (long q = m1; q < (long)nops; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
+  for (long q = 0; q <= m0; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
+  /* 2. levelise: an op runs after every earlier op that wrote one of its rows or
+   *    read its destination; ops of one level are then mutually independent */
+  uint32_t *lw = calloc(m->rows, 4), *lr = calloc(m->rows, 4), *lev = malloc(4 * (napp ? napp : 1));
+  uint32_t nlev = 0;
+  for (size_t q = 0; q < napp; q++) {
+    uint32_t i = seq[q].i, l = lw[i] > lr[i] ? lw[i] : lr[i];
+    if (i >= m->rows || (seq[q].beta && seq[q].j >= m->rows)) {
+      free(seq); free(lw); free(lr); free(lev);
+      return RQB_E_ARG;
+    }
+    if (seq[q].beta) {
+      uint32_t j = seq[q].j;
+      if (lw[j] > l) l = lw[j];
+      l++;
+      if (lr[j] < l) lr[j] = l;
+    } else {
+      l++;
+    }
+    lw[i] = l;
+    lev[q] = l;
+    if (l > nlev) nlev = l;
+  }
+  uint32_t *start = calloc((size_t)nlev + 2, 4);
+  for (size_t q = 0; q < napp; q++) start[lev[q] + 1]++;
+  for (uint32_t l = 0; l <= nlev; l++) start[l + 1] += start[l];
+  rqb_rowop *sorted = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
+  {
+    uint32_t *cur = malloc(4 * ((size_t)nlev + 2));
+    memcpy(cur, start, 4 * ((size_t)nlev + 2));
+    for (size_t q = 0; q < napp; q++) sorted[cur[lev[q]]++] = seq[q];
+    free(cur);
+  }
+  /* 3. the two cycle-walk permutations (lib/precode.c:3-13,381-386) composed into one gather map */
+  size_t nr = m->rows;
+  uint32_t *map = malloc(4 * nr);
+  for (size_t r = 0; r < nr; r++) map[r] = (uint32_t)r;
+  for (int pass = 0; pass < 2; pass++) {
+    size_t n = pass ? cols : rows;
+    int *P = malloc(sizeof(int) * (n ? n : 1));
+    memcpy(P, pass ? c : di, sizeof(int) * n);
+    for (size_t i = 0; i < n; i++) {
+      size_t at = i;
+      while (P[at] >= 0) {
+        uint32_t t = map[i];
+        map[i] = map[(size_t)P[at]];
+        map[(size_t)P[at]] = t;
+        int nx = P[at];
+        P[at] = -1;
+        at = (size_t)nx;
+      }
+    }
+    free(P);
+  }
+  /* 4. device: one launch per level, then the gather */
+  rqb_rowop *d_ops = NULL;
+  uint32_t *d_map = NULL;
+  uint8_t *d_tmp = NULL;
+  int e = rqb_dev_malloc((void **)&d_ops, sizeof(rqb_rowop) * (napp ? napp : 1));
+  e = e ? e : rqb_dev_malloc((void **)&d_map, 4 * nr);
+  e = e ? e : rqb_dev_malloc((void **)&d_tmp, nr * m->pitch);
+  e = e ? e : rqb_copy_h2d(d_ops, sorted, sizeof(rqb_rowop) * napp, m->stream);
+  e = e ? e : rqb_copy_h2d(d_map, map, 4 * nr, m->stream);
+  e = e ? e : rqb_event_record(m->ev0, m->stream);
+  uint32_t width = (uint32_t)round_up(m->T, 16);
+  for (uint32_t l = 1; l <= nlev && !e; l++)
+    e = rqb_launch_rowops(m->d, m->pitch, width, d_ops + start[l], start[l + 1] - start[l], m->stream);
+  e = e ? e : rqb_launch_gather_rows(d_tmp, m->pitch, m->d, m->pitch, d_map, (uint32_t)nr, width, m->stream);
+  e = e ? e : rqb_copy_d2d(m->d, d_tmp, nr * m->pitch, m->stream);
+  e = e ? e : rqb_event_record(m->ev1, m->stream);
+  e = e ? e : rqb_stream_sync(m->stream);
+  if (!e && ms_device) e = rqb_event_elapsed_ms(m->ev0, m->ev1, ms_device);
+  if (d_ops) rqb_dev_free(d_ops);
+  if (d_map) rqb_dev_free(d_map);
+  if (d_tmp) rqb_dev_free(d_tmp);
+  free(seq); free(lw); free(lr); free(lev); free(start); free(sorted); free(map);
+  if (e) return dev_fail(e, "rqb_schedule_replay");
+  return 0;
+}

@@ -11,7 +11,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "rqb_planner.h"
 #include "rqb_program.h"
 
 static uint8_t gmul(uint8_t a, uint8_t b) { /* shift-and-add, poly 0x11D */
@@ -25,9 +24,10 @@ static uint8_t gmul(uint8_t a, uint8_t b) { /* shift-and-add, poly 0x11D */
 }
 
 /* returns 0 ok, 10 = intra-level hazard, 11 = malformed */
-int rqb_interp_run(const rqb_plan *plan, const uint8_t *in, size_t in_pitch, size_t T,
-                   uint8_t *c_out, size_t c_pitch, uint8_t *sym_out, size_t sym_pitch) {
-  size_t ns = plan->n_slots;
+int rqb_interp_run(uint32_t n_slots, const uint32_t *load_src, uint32_t n_pages, const uint8_t *pages,
+                   const uint8_t *in, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_pitch,
+                   uint8_t *sym_out, size_t sym_pitch) {
+  size_t ns = n_slots;
   uint8_t *ws = calloc(ns * T + 1, 1);
   uint32_t *wstamp = calloc(ns, sizeof(uint32_t)); /* level id that last wrote the slot */
   uint32_t *wowner = calloc(ns, sizeof(uint32_t));
@@ -35,9 +35,9 @@ int rqb_interp_run(const rqb_plan *plan, const uint8_t *in, size_t in_pitch, siz
   int rc = 0;
   uint32_t level_id = 0;
   for (size_t s = 0; s < ns; s++)
-    if (plan->load_src[s] != RQB_ROW_NONE) memcpy(ws + s * T, in + (size_t)plan->load_src[s] * in_pitch, T);
-  for (uint32_t pg = 0; pg < plan->n_pages && !rc; pg++) {
-    const uint8_t *page = plan->pages + (size_t)pg * RQB_PAGE_BYTES;
+    if (load_src[s] != RQB_ROW_NONE) memcpy(ws + s * T, in + (size_t)load_src[s] * in_pitch, T);
+  for (uint32_t pg = 0; pg < n_pages && !rc; pg++) {
+    const uint8_t *page = pages + (size_t)pg * RQB_PAGE_BYTES;
     const rqb_page_hdr *ph = (const rqb_page_hdr *)page;
     uint32_t off = sizeof(rqb_page_hdr);
     for (uint32_t lv = 0; lv < ph->n_levels && !rc; lv++) {

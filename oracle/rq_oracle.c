@@ -693,6 +693,12 @@ void orc_intermediate(const orc_sched *S, uint8_t *D, size_t pitch, size_t T) {
   free(cm);
 }
 
+uint64_t orc_fnv1a64(const uint8_t *p, size_t n) { /* hash used by the KAT fixtures */
+  uint64_t h = 14695981039346656037ULL;
+  for (size_t k = 0; k < n; k++) h = (h ^ p[k]) * 1099511628211ULL;
+  return h;
+}
+
 /* ------------------------------------------------------ whole-block paths */
 int orc_encode_block(int K, size_t T, const uint8_t *src, uint8_t *C_out,
                      size_t pitch, size_t *nops, size_t *n_applied) {

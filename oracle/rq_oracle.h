@@ -86,6 +86,8 @@ void orc_intermediate(const orc_sched *S, uint8_t *D, size_t pitch, size_t T);
 void orc_lt_row(const orc_params *P, const uint8_t *C, size_t pitch,
                 uint32_t isi, uint8_t *out, size_t T);
 
+uint64_t orc_fnv1a64(const uint8_t *p, size_t n);
+
 /* Whole-block helpers mirroring nanorq_generate_symbols / nanorq_repair_block
  * (lib/nanorq.c:206-232, 591-631).
  *  - encode: src = K*T bytes (row-major), C_out = L rows of pitch bytes.

@@ -31,9 +31,7 @@ class Sched(C.Structure):
 
 
 def build_oracle():
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
-            os.path.join(ROOT, "oracle", "rq_oracle.c")):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
 
 
 _oracle = None
@@ -50,6 +48,8 @@ def oracle():
         build_oracle()
         L = C.CDLL(ORACLE_SO)
         L.orc_params_init.argtypes = [C.c_int, C.POINTER(Params)]
+        L.orc_fnv1a64.restype = C.c_uint64
+        L.orc_fnv1a64.argtypes = [u8p, C.c_size_t]
         L.orc_rand.restype = C.c_uint32
         L.orc_rand.argtypes = [C.c_uint32] * 3
         L.orc_lt_indices.argtypes = [C.POINTER(Params), C.c_uint32, u32p]
@@ -111,13 +111,29 @@ def kat_payload(n):
 
 
 def fnv1a64(a):
-    """FNV-1a 64 over a byte array (vectorised over nothing: plain loop in numpy chunks)."""
-    h = 14695981039346656037
-    prime = 1099511628211
-    mask = (1 << 64) - 1
-    for b in a.tobytes():
-        h = ((h ^ b) * prime) & mask
-    return h
+    """FNV-1a 64 over a byte array (the hash of the KAT fixtures)."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return int(oracle().orc_fnv1a64(ptr(a), a.size))
+
+
+INTERP_SO = os.path.join(ROOT, "oracle", "libplan_interp.so")
+_interp = None
+
+
+def interp_run(blob, inp, T, n_c, n_out):
+    """Run a plan blob (nanorq_b200.plan_blob) on the CPU interpreter.
+    -> (rc, C[n_c,T], syms[n_out,T])"""
+    global _interp
+    if _interp is None:
+        _interp = C.CDLL(INTERP_SO)
+        _interp.rqb_interp_run.argtypes = [C.c_uint32, u32p, C.c_uint32, u8p, u8p, C.c_size_t, C.c_size_t,
+                                           u8p, C.c_size_t, u8p, C.c_size_t]
+    inp = np.ascontiguousarray(inp, dtype=np.uint8)
+    cout = np.zeros((max(n_c, 1), T), np.uint8)
+    sout = np.zeros((max(n_out, 1), T), np.uint8)
+    rc = _interp.rqb_interp_run(blob["n_slots"], ptr(blob["load_src"], u32p), blob["n_pages"], ptr(blob["pages"]),
+                                ptr(inp), inp.strides[0], T, ptr(cout), T, ptr(sout), T)
+    return rc, cout[:n_c], sout[:n_out]
 
 
 def orc_params(K):
