@@ -194,6 +194,7 @@ static void pb_level_end(progbuf *pb) {
       pb_close_page(pb);
       continue;
     }
+    need = (need + 15) & ~(size_t)15; /* levels start 16-byte aligned (uint4 loads); avail is a multiple of 16 */
     uint8_t *page = pb->pages + (pb->npages - 1) * RQB_PAGE_BYTES;
     rqb_level_hdr *lh = (rqb_level_hdr *)(page + pb->cur);
     size_t n = j - idx;

@@ -23,7 +23,9 @@ static uint8_t gmul(uint8_t a, uint8_t b) { /* shift-and-add, poly 0x11D */
   return r;
 }
 
-/* returns 0 ok, 10 = intra-level hazard, 11 = malformed */
+/* returns 0 ok, 10 = intra-level hazard, 11 = malformed, 12 = misaligned (the kernel
+ * reads level headers and tasks as 16-byte vectors, u16 source lists as 8-byte
+ * vectors and u32 lists as words) */
 int rqb_interp_run(uint32_t n_slots, const uint32_t *load_src, uint32_t n_pages, const uint8_t *pages,
                    const uint8_t *in, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_pitch,
                    uint8_t *sym_out, size_t sym_pitch) {
@@ -41,6 +43,7 @@ int rqb_interp_run(uint32_t n_slots, const uint32_t *load_src, uint32_t n_pages,
     const rqb_page_hdr *ph = (const rqb_page_hdr *)page;
     uint32_t off = sizeof(rqb_page_hdr);
     for (uint32_t lv = 0; lv < ph->n_levels && !rc; lv++) {
+      if (off % 16 || off + sizeof(rqb_level_hdr) > RQB_PAGE_BYTES) { rc = off % 16 ? 12 : 11; break; }
       const rqb_level_hdr *lh = (const rqb_level_hdr *)(page + off);
       const rqb_task *tasks = (const rqb_task *)(page + off + sizeof(rqb_level_hdr));
       level_id++;
@@ -62,6 +65,7 @@ int rqb_interp_run(uint32_t n_slots, const uint32_t *load_src, uint32_t n_pages,
         const uint16_t *s16 = (const uint16_t *)(page + t->src_off);
         const uint32_t *s32 = (const uint32_t *)(page + t->src_off);
         if (t->src_off + (size_t)t->nsrc * 2 > RQB_PAGE_BYTES) { rc = 11; break; }
+        if (t->src_off % 8) { rc = 12; break; }
         switch (t->kind) {
           case RQB_T_XOR_SET: case RQB_T_XOR_ACC: case RQB_T_LOAD_XOR:
           case RQB_T_OUT_C: case RQB_T_OUT_SYM: {
