@@ -37,8 +37,12 @@ extern "C" {
 
 const char *rqb_last_error(void);
 int rqb_device_count(void);
+/* selects the device new solvers/matrices are created on (process-wide: CUDA's
+ * current device is per thread, the library binds calling threads itself) */
 int rqb_set_device(int dev);
 unsigned long long rqb_kernel_launches(void);
+/* bytes copied host->device / device->host by this library so far */
+void rqb_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
 
 /* ---- RFC 6330 construction helpers (host, integer only) */
 typedef struct {
@@ -104,6 +108,12 @@ int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 /* run several solvers' pending programs as ONE kernel launch (gridDim.y = n);
  * all must share T and device.  Asynchronous on solvers[0]'s stream. */
 int rqb_solver_run_batch(rqb_solver **solvers, int n);
+/* same, on the stream of `owner` (so that several batches queue behind each other) */
+int rqb_solver_run_batch_on(rqb_solver **solvers, int n, rqb_solver *owner);
+/* CUDA-event timing of whatever is queued on this solver's stream between
+ * mark(s,0) and mark(s,1) */
+int rqb_solver_mark(rqb_solver *s, int end);
+int rqb_solver_marked_ms(rqb_solver *s, float *ms);
 
 /* host-only: build the plan and hand back the raw program (tests / tooling);
  * free with rqb_plan_blob_free. */

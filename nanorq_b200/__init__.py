@@ -19,6 +19,7 @@ from .api import (  # noqa: F401
     lt_row_indices,
     plan_blob,
     set_device,
+    transfer_bytes,
     SYM_ADDED,
     SYM_DUP,
     SYM_ERR,

@@ -106,6 +106,9 @@ def lib():
     sig("rqb_device_count", C.c_int)
     sig("rqb_set_device", C.c_int, C.c_int)
     sig("rqb_kernel_launches", C.c_ulonglong)
+    sig("rqb_transfer_bytes", None, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
+    sig("rqb_solver_mark", C.c_int, vp, C.c_int)
+    sig("rqb_solver_marked_ms", C.c_int, vp, C.POINTER(C.c_float))
     sig("rqb_block_params_init", C.c_int, C.c_int, C.POINTER(BlockParams))
     sig("rqb_lt_row_indices", C.c_int, C.c_int, C.c_uint32, u32p)
     sig("rqb_solver_create", C.c_int, C.POINTER(vp), C.c_int, sz, C.c_uint32, C.c_uint32)
@@ -125,6 +128,7 @@ def lib():
     sig("rqb_solver_last_kernel_ms", C.c_int, vp, C.POINTER(C.c_float))
     sig("rqb_solver_get_stats", C.c_int, vp, C.POINTER(SolverStats))
     sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
+    sig("rqb_solver_run_batch_on", C.c_int, C.POINTER(vp), C.c_int, vp)
     sig("rqb_plan_blob_build", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.POINTER(PlanBlob))
     sig("rqb_plan_blob_free", None, C.POINTER(PlanBlob))
     sig("rqb_matrix_create", C.c_int, C.POINTER(vp), sz, sz)
@@ -151,7 +155,8 @@ EXPORTED_SYMBOLS = [
     "nanorq_encode", "nanorq_encoder_cleanup", "nanorq_encoder_reset", "nanorq_decoder_new",
     "nanorq_set_max_esi", "nanorq_decoder_add_symbol", "nanorq_num_missing", "nanorq_num_repair",
     "nanorq_repair_block", "ioctx_from_file", "ioctx_mmap_file", "ioctx_from_mem",
-    "rqb_last_error", "rqb_device_count", "rqb_set_device", "rqb_kernel_launches",
+    "rqb_last_error", "rqb_device_count", "rqb_set_device", "rqb_kernel_launches", "rqb_transfer_bytes",
+    "rqb_solver_mark", "rqb_solver_marked_ms", "rqb_solver_run_batch_on",
     "rqb_block_params_init", "rqb_lt_row_indices", "rqb_solver_create", "rqb_solver_create_ex",
     "rqb_solver_destroy", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
     "rqb_solver_plan", "rqb_solver_plan_encode", "rqb_solver_run", "rqb_solver_emit",
@@ -177,6 +182,12 @@ def set_device(dev):
 
 def kernel_launches():
     return int(lib().rqb_kernel_launches())
+
+
+def transfer_bytes():
+    h, d = C.c_ulonglong(), C.c_ulonglong()
+    lib().rqb_transfer_bytes(C.byref(h), C.byref(d))
+    return int(h.value), int(d.value)
 
 
 def _check(rc, what):
@@ -443,15 +454,26 @@ class Solver:
         _check(lib().rqb_solver_last_kernel_ms(self.h, C.byref(ms)), "rqb_solver_last_kernel_ms")
         return ms.value
 
+    def mark(self, end=False):
+        _check(lib().rqb_solver_mark(self.h, 1 if end else 0), "rqb_solver_mark")
+
+    def marked_ms(self):
+        ms = C.c_float()
+        _check(lib().rqb_solver_marked_ms(self.h, C.byref(ms)), "rqb_solver_marked_ms")
+        return ms.value
+
     def stats(self):
         st = SolverStats()
         _check(lib().rqb_solver_get_stats(self.h, C.byref(st)), "rqb_solver_get_stats")
         return st.as_dict()
 
     @staticmethod
-    def run_batch(solvers):
+    def run_batch(solvers, owner=None):
         arr = (vp * len(solvers))(*[s.h for s in solvers])
-        _check(lib().rqb_solver_run_batch(arr, len(solvers)), "rqb_solver_run_batch")
+        if owner is None:
+            _check(lib().rqb_solver_run_batch(arr, len(solvers)), "rqb_solver_run_batch")
+        else:
+            _check(lib().rqb_solver_run_batch_on(arr, len(solvers), owner.h), "rqb_solver_run_batch_on")
 
 
 class Matrix:

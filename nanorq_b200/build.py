@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnanorq_b200.so")
+RT_OUT = os.path.join(HERE, "librq_roundtrip.so")
 C_SOURCES = ["rqb_planner.c", "rqb_solver.c", "nanorq_api.c", "rqb_io.c"]
 CU_SOURCES = ["rqb_device.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -51,6 +52,14 @@ def build(force=False, verbose=False):
             subprocess.check_call(cmd)
     if force or _stale(OUT, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lpthread"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    # the nanorq.h-only round-trip harness (bench/rq_roundtrip.c), linked against the library
+    rt_src = os.path.join(ROOT, "bench", "rq_roundtrip.c")
+    if os.path.exists(rt_src) and (force or _stale(RT_OUT, [rt_src, OUT] + hdrs)):
+        cmd = [CC, "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-pthread", "-o", RT_OUT, rt_src,
+               "-I" + os.path.join(ROOT, "include"), "-L" + HERE, "-lnanorq_b200", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -18,7 +18,9 @@
 // All arithmetic is GF(2)/GF(256) integer work (poly 0x11D); no tensor cores.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 
@@ -332,8 +334,11 @@ rqb_gather_rows_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *
 
 // ------------------------------------------------------------------- shim
 static thread_local char g_err[256] = "";
-static unsigned long long g_launches = 0;
-static int g_consts_dev[64];
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+static std::atomic<int> g_consts_dev[64];
+static std::atomic<int> g_default_dev{0};
+static std::mutex g_cfg_mu;
 
 static int fail(cudaError_t e, const char *what) {
   if (e == cudaSuccess) return 0;
@@ -349,10 +354,11 @@ static int fail(cudaError_t e, const char *what) {
 static int ensure_consts() {
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  if (dev < 64 && g_consts_dev[dev]) return 0;
+  if (dev < 64 && g_consts_dev[dev].load(std::memory_order_acquire)) return 0;
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
   CK(cudaMemcpyToSymbol(c_rand_v, rqb_rand_v, sizeof(rqb_rand_v)));
   CK(cudaMemcpyToSymbol(c_degree_cdf, rqb_degree_cdf, sizeof(rqb_degree_cdf)));
-  if (dev < 64) g_consts_dev[dev] = 1;
+  if (dev < 64) g_consts_dev[dev].store(1, std::memory_order_release);
   return 0;
 }
 
@@ -360,12 +366,13 @@ template <int VB>
 static int launch_solve_t(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots, uint32_t max_width,
                           cudaStream_t st) {
   const uint32_t smem = kSolveSmemFixed + max_slots * VB;
-  static uint32_t configured[64];
+  static std::atomic<uint32_t> configured[64];
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  if (dev >= 64 || configured[dev] < smem) {
+  if (dev >= 64 || configured[dev].load(std::memory_order_acquire) < smem) {
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
     CK(cudaFuncSetAttribute(rqb_solve_kernel<VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    if (dev < 64) configured[dev] = kMaxSmem;
+    if (dev < 64) configured[dev].store(kMaxSmem, std::memory_order_release);
   }
   dim3 grid((max_width + VB - 1) / VB, (unsigned)nblocks);
   rqb_solve_kernel<VB><<<grid, kSolveThreads, smem, st>>>(args_dev);
@@ -377,7 +384,15 @@ static int launch_solve_t(const rqb_solve_args *args_dev, int nblocks, uint32_t 
 extern "C" {
 
 const char *rqb_dev_last_error(void) { return g_err; }
-unsigned long long rqb_dev_launch_count(void) { return g_launches; }
+unsigned long long rqb_dev_launch_count(void) { return g_launches.load(); }
+void rqb_dev_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h) {
+  if (h2d) *h2d = g_h2d_bytes.load();
+  if (d2h) *d2h = g_d2h_bytes.load();
+}
+/* CUDA's current device is per thread (new threads start on device 0): the
+ * library keeps a process-wide default that contexts are created on */
+void rqb_dev_set_default(int dev) { g_default_dev.store(dev); }
+int rqb_dev_default(void) { return g_default_dev.load(); }
 
 int rqb_dev_count(void) {
   int n = 0;
@@ -414,10 +429,12 @@ int rqb_stream_sync(void *s) { CK(cudaStreamSynchronize((cudaStream_t)s)); retur
 int rqb_dev_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int rqb_copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  g_h2d_bytes += bytes;
   return 0;
 }
 int rqb_copy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  g_d2h_bytes += bytes;
   return 0;
 }
 int rqb_copy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
@@ -427,11 +444,13 @@ int rqb_copy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
 int rqb_copy2d_h2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
                    void *stream) {
   CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  g_h2d_bytes += width * rows;
   return 0;
 }
 int rqb_copy2d_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
                    void *stream) {
   CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  g_d2h_bytes += width * rows;
   return 0;
 }
 int rqb_dev_memset(void *p, int v, size_t bytes, void *stream) {

@@ -89,6 +89,11 @@ int rqb_launch_gather_rows(uint8_t *dst, size_t dpitch, const uint8_t *src, size
 
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 unsigned long long rqb_dev_launch_count(void);
+/* bytes moved by rqb_copy* so far */
+void rqb_dev_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
+/* process-wide default device for new contexts (CUDA's current device is per thread) */
+void rqb_dev_set_default(int dev);
+int rqb_dev_default(void);
 
 #ifdef __cplusplus
 }

@@ -32,9 +32,19 @@ static int dev_fail(int e, const char *what) {
 int rqb_device_count(void) { return rqb_dev_count(); }
 int rqb_set_device(int dev) {
   DEV(rqb_dev_set(dev));
+  rqb_dev_set_default(dev);
   return 0;
 }
 unsigned long long rqb_kernel_launches(void) { return rqb_dev_launch_count(); }
+void rqb_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h) { rqb_dev_transfer_bytes(h2d, d2h); }
+
+/* CUDA's current device is per thread; contexts remember theirs and every entry
+ * point binds the calling thread to it (worker threads start on device 0) */
+static int bind_dev(int dev) {
+  if (rqb_dev_get() == dev) return 0;
+  return rqb_dev_set(dev);
+}
+#define BIND(dev) DEV(bind_dev(dev))
 
 int rqb_block_params_init(int K, rqb_block_params *out) {
   rqb_params P;
@@ -49,6 +59,7 @@ int rqb_lt_row_indices(int K, uint32_t isi, uint32_t *out) {
   return rqb_host_lt_indices(&P, isi, out);
 }
 
+#define RQB_ARGS_BYTES 16384 /* room for 256 blocks in one batched launch */
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 /* ------------------------------------------------------------ buffer pool
@@ -122,7 +133,7 @@ struct rqb_solver {
   size_t T, pitch;
   rqb_params P;
   uint32_t max_in, max_out;
-  void *stream, *ev0, *ev1;
+  void *stream, *ev0, *ev1, *ev2, *ev3;
   uint8_t *h_in, *d_in, *d_c, *d_sym, *h_sym;
   uint32_t *d_isi, *h_isi;
   /* current program */
@@ -156,11 +167,13 @@ void rqb_solver_destroy(rqb_solver *s) {
   pool_put(s->h_isi, (size_t)s->max_out * 4, 1);
   pool_put(s->d_pages, s->d_pages_cap, 0);
   pool_put(s->d_load, s->d_load_cap, 0);
-  pool_put(s->h_args, 4096, 1);
-  pool_put(s->d_args, 4096, 0);
+  pool_put(s->h_args, RQB_ARGS_BYTES, 1);
+  pool_put(s->d_args, RQB_ARGS_BYTES, 0);
   if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
   if (s->ev0) rqb_event_destroy(s->ev0);
   if (s->ev1) rqb_event_destroy(s->ev1);
+  if (s->ev2) rqb_event_destroy(s->ev2);
+  if (s->ev3) rqb_event_destroy(s->ev3);
   if (s->stream) rqb_stream_destroy(s->stream);
   if (cur != s->dev && cur >= 0) rqb_dev_set(cur);
   free(s);
@@ -189,9 +202,11 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   s->P = P;
   s->max_in = max_in;
   s->max_out = max_out ? max_out : 1;
-  s->dev = rqb_dev_get();
-  int e = 0;
+  s->dev = rqb_dev_default();
+  int e = bind_dev(s->dev);
   e = e ? e : rqb_stream_create(&s->stream);
+  e = e ? e : rqb_event_create(&s->ev2);
+  e = e ? e : rqb_event_create(&s->ev3);
   e = e ? e : rqb_event_create(&s->ev0);
   e = e ? e : rqb_event_create(&s->ev1);
   e = e ? e : pool_get((void **)&s->h_in, (size_t)s->max_in * s->pitch, 1);
@@ -201,8 +216,8 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->max_out * s->pitch, 1);
   e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->max_out * 4, 0);
   e = e ? e : pool_get((void **)&s->h_isi, (size_t)s->max_out * 4, 1);
-  e = e ? e : pool_get((void **)&s->h_args, 4096, 1);
-  e = e ? e : pool_get((void **)&s->d_args, 4096, 0);
+  e = e ? e : pool_get((void **)&s->h_args, RQB_ARGS_BYTES, 1);
+  e = e ? e : pool_get((void **)&s->d_args, RQB_ARGS_BYTES, 0);
   if (e) {
     dev_fail(e, "rqb_solver_create allocation");
     rqb_solver_destroy(s);
@@ -217,6 +232,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
 }
 
 int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
+  BIND(s->dev);
   if ((uint64_t)first + n > s->max_in) return RQB_E_ARG;
   if (!n) return 0;
   DEV(rqb_copy_h2d(s->d_in + (size_t)first * s->pitch, s->h_in + (size_t)first * s->pitch,
@@ -267,6 +283,7 @@ static int solver_set_args(rqb_solver *s) {
 }
 
 int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
+  BIND(s->dev);
   if (req->n_out > s->max_out) return RQB_E_ARG;
   rqb_plan_request pr;
   pr.K = s->Kparams;
@@ -310,6 +327,7 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
 }
 
 int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
+  BIND(s->dev);
   if (n_rep > s->max_out) return RQB_E_ARG;
   pthread_mutex_lock(&g_plan_mu);
   enc_plan *e = g_enc_plans;
@@ -366,6 +384,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
 
 int rqb_solver_run(rqb_solver *s) {
   if (!s->plan) return RQB_E_ARG;
+  BIND(s->dev);
   DEV(rqb_event_record(s->ev0, s->stream));
   DEV(rqb_launch_solve(s->d_args, 1, s->plan->n_slots, s->h_args->width, s->vec_bytes, s->stream));
   DEV(rqb_event_record(s->ev1, s->stream));
@@ -373,29 +392,52 @@ int rqb_solver_run(rqb_solver *s) {
   return 0;
 }
 
-int rqb_solver_run_batch(rqb_solver **sv, int n) {
-  if (n <= 0) return RQB_E_ARG;
-  if (n == 1) return rqb_solver_run(sv[0]);
-  rqb_solver *s0 = sv[0];
-  if ((size_t)n * sizeof(rqb_solve_args) > 4096) return RQB_E_ARG;
-  uint32_t max_slots = 0;
-  int vec = 16;
-  for (int k = 0; k < n; k++) {
-    if (!sv[k]->plan || sv[k]->T != s0->T || sv[k]->dev != s0->dev) return RQB_E_ARG;
-    if (k) DEV(rqb_stream_sync(sv[k]->stream)); /* its uploads must have landed */
-    if (sv[k]->plan->n_slots > max_slots) max_slots = sv[k]->plan->n_slots;
-    if (sv[k]->vec_bytes < vec) vec = sv[k]->vec_bytes;
-    s0->h_args[k] = *sv[k]->h_args;
-  }
-  DEV(rqb_copy_h2d(s0->d_args, s0->h_args, (size_t)n * sizeof(rqb_solve_args), s0->stream));
-  DEV(rqb_event_record(s0->ev0, s0->stream));
-  DEV(rqb_launch_solve(s0->d_args, n, max_slots, s0->h_args->width, vec, s0->stream));
-  DEV(rqb_event_record(s0->ev1, s0->stream));
-  s0->timed = 1;
+/* time a region of work queued on this solver's stream with CUDA events */
+int rqb_solver_mark(rqb_solver *s, int end) {
+  BIND(s->dev);
+  DEV(rqb_event_record(end ? s->ev3 : s->ev2, s->stream));
+  return 0;
+}
+int rqb_solver_marked_ms(rqb_solver *s, float *ms) {
+  BIND(s->dev);
+  DEV(rqb_event_sync(s->ev3));
+  DEV(rqb_event_elapsed_ms(s->ev2, s->ev3, ms));
   return 0;
 }
 
+/* one launch for n blocks on the stream of `own` (which also lends its argument
+ * buffers and timing events) */
+int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
+  if (n <= 0 || !own) return RQB_E_ARG;
+  BIND(own->dev);
+  if ((size_t)(n + 1) * sizeof(rqb_solve_args) > RQB_ARGS_BYTES) return RQB_E_ARG;
+  uint32_t max_slots = 0;
+  int vec = 16;
+  /* entry 0 of the owner's buffer stays its own single-run argument block */
+  rqb_solve_args *h = own->h_args + 1, *d = own->d_args + 1;
+  for (int k = 0; k < n; k++) {
+    if (!sv[k]->plan || sv[k]->T != own->T || sv[k]->dev != own->dev) return RQB_E_ARG;
+    if (sv[k] != own) DEV(rqb_stream_sync(sv[k]->stream)); /* its uploads must have landed */
+    if (sv[k]->plan->n_slots > max_slots) max_slots = sv[k]->plan->n_slots;
+    if (sv[k]->vec_bytes < vec) vec = sv[k]->vec_bytes;
+    h[k] = *sv[k]->h_args;
+  }
+  DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
+  DEV(rqb_event_record(own->ev0, own->stream));
+  DEV(rqb_launch_solve(d, n, max_slots, h[0].width, vec, own->stream));
+  DEV(rqb_event_record(own->ev1, own->stream));
+  own->timed = 1;
+  return 0;
+}
+
+int rqb_solver_run_batch(rqb_solver **sv, int n) {
+  if (n <= 0) return RQB_E_ARG;
+  if (n == 1) return rqb_solver_run(sv[0]);
+  return rqb_solver_run_batch_on(sv, n, sv[0]);
+}
+
 int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n) {
+  BIND(s->dev);
   if (!s->has_c || n > s->max_out) return RQB_E_ARG;
   memcpy(s->h_isi, isi, (size_t)n * 4);
   DEV(rqb_copy_h2d(s->d_isi, s->h_isi, (size_t)n * 4, s->stream));
@@ -406,11 +448,13 @@ int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n) {
 }
 
 int rqb_solver_sync(rqb_solver *s) {
+  BIND(s->dev);
   DEV(rqb_stream_sync(s->stream));
   return 0;
 }
 
 int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms) {
+  BIND(s->dev);
   if (!s->timed) return RQB_E_ARG;
   DEV(rqb_event_sync(s->ev1));
   DEV(rqb_event_elapsed_ms(s->ev0, s->ev1, ms));
@@ -418,6 +462,7 @@ int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms) {
 }
 
 int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch) {
+  BIND(s->dev);
   if ((uint64_t)first + n > s->max_out) return RQB_E_ARG;
   if (!n) return 0;
   DEV(rqb_copy_d2h(s->h_sym + (size_t)first * s->pitch, s->d_sym + (size_t)first * s->pitch,
@@ -430,6 +475,7 @@ int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *ds
 }
 
 int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch) {
+  BIND(s->dev);
   if (!s->has_c || (uint64_t)first + n > (uint32_t)s->P.L) return RQB_E_ARG;
   DEV(rqb_copy2d_d2h(dst, dst_pitch, s->d_c + (size_t)first * s->pitch, s->pitch, s->T, n, s->stream));
   DEV(rqb_stream_sync(s->stream));
@@ -486,8 +532,9 @@ int rqb_matrix_create(rqb_matrix **out, size_t rows, size_t T) {
   m->rows = rows;
   m->T = T;
   m->pitch = round_up(T, 64);
-  m->dev = rqb_dev_get();
-  int e = rqb_stream_create(&m->stream);
+  m->dev = rqb_dev_default();
+  int e = bind_dev(m->dev);
+  e = e ? e : rqb_stream_create(&m->stream);
   e = e ? e : rqb_event_create(&m->ev0);
   e = e ? e : rqb_event_create(&m->ev1);
   e = e ? e : rqb_dev_malloc((void **)&m->d, rows * m->pitch);
@@ -512,6 +559,7 @@ void rqb_matrix_destroy(rqb_matrix *m) {
 }
 
 int rqb_matrix_upload(rqb_matrix *m, size_t first, size_t n, const uint8_t *src, size_t src_pitch) {
+  BIND(m->dev);
   if (first + n > m->rows) return RQB_E_ARG;
   DEV(rqb_copy2d_h2d(m->d + first * m->pitch, m->pitch, src, src_pitch, m->T, n, m->stream));
   DEV(rqb_stream_sync(m->stream));
@@ -519,6 +567,7 @@ int rqb_matrix_upload(rqb_matrix *m, size_t first, size_t n, const uint8_t *src,
 }
 
 int rqb_matrix_download(rqb_matrix *m, size_t first, size_t n, uint8_t *dst, size_t dst_pitch) {
+  BIND(m->dev);
   if (first + n > m->rows) return RQB_E_ARG;
   DEV(rqb_copy2d_d2h(dst, dst_pitch, m->d + first * m->pitch, m->pitch, m->T, n, m->stream));
   DEV(rqb_stream_sync(m->stream));
@@ -526,6 +575,7 @@ int rqb_matrix_download(rqb_matrix *m, size_t first, size_t n, uint8_t *dst, siz
 }
 
 int rqb_matrix_fill_random(rqb_matrix *m, uint64_t seed) {
+  BIND(m->dev);
   /* benchmark filler: a host xorshift tile repeated over the matrix by device copies */
   size_t tile = (size_t)1 << 22, total = m->rows * m->pitch;
   if (tile > total) tile = total;
@@ -569,6 +619,7 @@ void rqb_ops_free(rqb_oplist *l) {
 }
 
 int rqb_rowops_apply_dev(rqb_matrix *m, const rqb_oplist *l, int repeats, float *ms_total) {
+  BIND(m->dev);
   if (repeats < 1) repeats = 1;
   DEV(rqb_event_record(m->ev0, m->stream));
   for (int r = 0; r < repeats; r++)
