@@ -31,7 +31,7 @@ extern "C" {
 #define RQB_NEED_MORE 1      /* matrix rank < L: add symbols and retry     */
 #define RQB_E_ARG (-1)
 #define RQB_E_NODEVICE (-100) /* no CUDA device / CUDA error (see rqb_last_error) */
-#define RQB_E_TOOBIG (-101)  /* block does not fit the shared-memory solver */
+#define RQB_E_TOOBIG (-101)  /* program needs more rows than a row reference can address */
 
 #define RQB_NO_ROW 0xFFFFFFFFu
 
@@ -98,10 +98,11 @@ int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms);
 
 typedef struct {
   int i, u, nb, rho, nfree, levels_fwd, n_levels, n_tasks, n_pages;
-  size_t n_srcs, n_gf_srcs, n_horner, nnz;
-  double t_matrix, t_peel, t_dense, t_emit;
-  uint32_t n_slots;
-  int vec_bytes;
+  size_t n_srcs, n_gf_srcs, n_horner, nnz; /* XOR sources, GF(256) sources, scan entries, matrix non-zeros */
+  double t_matrix, t_peel, t_dense, t_emit; /* host seconds per planning phase */
+  uint32_t n_ws_rows; /* working rows the program uses in HBM */
+  int n_parts;        /* partial sums scheduled off the critical path */
+  int slice_bytes;    /* column slice one CTA owns */
 } rqb_solver_stats;
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 
@@ -118,8 +119,7 @@ int rqb_solver_marked_ms(rqb_solver *s, float *ms);
 /* host-only: build the plan and hand back the raw program (tests / tooling);
  * free with rqb_plan_blob_free. */
 typedef struct {
-  uint32_t n_slots, n_pages, page_bytes;
-  const uint32_t *load_src;
+  uint32_t n_ws_rows, n_pages, page_bytes;
   const uint8_t *pages;
   rqb_solver_stats stats;
   void *opaque;

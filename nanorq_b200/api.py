@@ -36,15 +36,15 @@ class SolverStats(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("i", "u", "nb", "rho", "nfree", "levels_fwd", "n_levels", "n_tasks", "n_pages")] + \
                [(n, C.c_size_t) for n in ("n_srcs", "n_gf_srcs", "n_horner", "nnz")] + \
                [(n, C.c_double) for n in ("t_matrix", "t_peel", "t_dense", "t_emit")] + \
-               [("n_slots", C.c_uint32), ("vec_bytes", C.c_int)]
+               [("n_ws_rows", C.c_uint32), ("n_parts", C.c_int), ("slice_bytes", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class PlanBlob(C.Structure):
-    _fields_ = [("n_slots", C.c_uint32), ("n_pages", C.c_uint32), ("page_bytes", C.c_uint32),
-                ("load_src", u32p), ("pages", u8p), ("stats", SolverStats), ("opaque", vp)]
+    _fields_ = [("n_ws_rows", C.c_uint32), ("n_pages", C.c_uint32), ("page_bytes", C.c_uint32),
+                ("pages", u8p), ("stats", SolverStats), ("opaque", vp)]
 
 
 class Op(C.Structure):
@@ -271,8 +271,7 @@ def plan_blob(K_params, req):
     if rc != 0:
         return rc, None
     out = {
-        "n_slots": b.n_slots, "n_pages": b.n_pages, "page_bytes": b.page_bytes,
-        "load_src": np.ctypeslib.as_array(b.load_src, (b.n_slots,)).copy(),
+        "n_ws_rows": b.n_ws_rows, "n_pages": b.n_pages, "page_bytes": b.page_bytes,
         "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(),
         "stats": b.stats.as_dict(),
     }

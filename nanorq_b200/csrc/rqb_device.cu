@@ -4,10 +4,13 @@
 //   rqb_solve_kernel   precode_matrix_apply_sched + precode_matrix_permute
 //                      (lib/precode.c:3-32,379-389) and decode_row for the symbols
 //                      requested with the solve (lib/nanorq.c:184-204).
-//                      Column-sliced: one CTA owns a VB-byte slice of every row of
-//                      the block in shared memory and interprets the host-built
-//                      program (rqb_program.h); pages of the program are staged by
-//                      TMA bulk copies (cp.async.bulk + mbarrier) into a ring.
+//                      Column-sliced: one CTA owns a 128-byte column slice of every
+//                      row of a source block and interprets the host-built program
+//                      (rqb_program.h).  Rows stay in HBM/L2; a task is a gather of
+//                      <= 8 row segments done by 8 lanes x 16 bytes (one 128-byte
+//                      line per source, all loads in flight together).  Pages of
+//                      the program are staged by TMA bulk copies (cp.async.bulk +
+//                      mbarrier) into a shared-memory ring.
 //   rqb_lt_kernel      decode_row / gen_tuple on demand (lib/nanorq.c:184-204,
 //                      lib/tuple.c:21-43), tuples computed on the device.
 //   rqb_rowops_kernel  oaxpy / oaddrow / oscal (deps/oblas/oblas_avx.c:43-114) as a
@@ -33,10 +36,12 @@ __constant__ uint32_t c_rand_v[4][256];
 __constant__ uint32_t c_degree_cdf[31];
 
 static constexpr int kSolveThreads = 256;
+static constexpr int kSolveMinCtas = 4;                        // CTAs per SM the register budget allows
+static constexpr int kLanesPerTask = RQB_SLICE_BYTES / 16;     // 8 lanes x 16 bytes
+static constexpr int kTaskGroups = kSolveThreads / kLanesPerTask;
 static constexpr int kRingStages = 4;
 static constexpr uint32_t kRingBytes = kRingStages * RQB_PAGE_BYTES;
-static constexpr uint32_t kSolveSmemFixed = kRingBytes + 128; // ring + mbarriers
-static constexpr uint32_t kMaxSmem = 232448;                  // 227 KB opt-in limit
+static constexpr uint32_t kSolveSmem = kRingBytes + 128;       // ring + mbarriers
 
 // ------------------------------------------------------------- GF(256) SWAR
 // 4 packed field elements per 32-bit word.
@@ -64,52 +69,8 @@ __device__ __forceinline__ uint32_t gfmul4(uint32_t x, const BetaPlanes &p) {
   for (int k = 0; k < 8; k++) y ^= ((x >> k) & 0x01010101u) * p.c[k];
   return y;
 }
-
-// ------------------------------------------------- VB-byte vectors in words
-template <int VB>
-struct Vec {
-  static constexpr int NW = VB >= 4 ? VB / 4 : 1;
-  uint32_t w[NW];
-};
-template <int VB>
-__device__ __forceinline__ Vec<VB> vzero() {
-  Vec<VB> v;
-#pragma unroll
-  for (int k = 0; k < Vec<VB>::NW; k++) v.w[k] = 0;
-  return v;
-}
-template <int VB>
-__device__ __forceinline__ Vec<VB> vload(const void *p) {
-  Vec<VB> v;
-  if constexpr (VB == 16) {
-    uint4 t = *reinterpret_cast<const uint4 *>(p);
-    v.w[0] = t.x; v.w[1] = t.y; v.w[2] = t.z; v.w[3] = t.w;
-  } else if constexpr (VB == 8) {
-    uint2 t = *reinterpret_cast<const uint2 *>(p);
-    v.w[0] = t.x; v.w[1] = t.y;
-  } else if constexpr (VB == 4) {
-    v.w[0] = *reinterpret_cast<const uint32_t *>(p);
-  } else {
-    v.w[0] = *reinterpret_cast<const uint16_t *>(p);
-  }
-  return v;
-}
-template <int VB>
-__device__ __forceinline__ void vstore(void *p, const Vec<VB> &v) {
-  if constexpr (VB == 16) {
-    *reinterpret_cast<uint4 *>(p) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
-  } else if constexpr (VB == 8) {
-    *reinterpret_cast<uint2 *>(p) = make_uint2(v.w[0], v.w[1]);
-  } else if constexpr (VB == 4) {
-    *reinterpret_cast<uint32_t *>(p) = v.w[0];
-  } else {
-    *reinterpret_cast<uint16_t *>(p) = (uint16_t)v.w[0];
-  }
-}
-template <int VB>
-__device__ __forceinline__ void vxor(Vec<VB> &a, const Vec<VB> &b) {
-#pragma unroll
-  for (int k = 0; k < Vec<VB>::NW; k++) a.w[k] ^= b.w[k];
+__device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
+  a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
 }
 
 // --------------------------------------------------- mbarrier / TMA bulk copy
@@ -146,19 +107,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 }
 
 // ------------------------------------------------------------- solve kernel
-// grid = (width / VB, nblocks); block = kSolveThreads; dynamic smem =
-// kSolveSmemFixed + max_slots * VB.  One lane executes one task on its CTA's slice.
-template <int VB>
-__global__ void __launch_bounds__(kSolveThreads)
+// grid = (ceil(width / 128), nblocks); block = kSolveThreads; dynamic smem = kSolveSmem.
+// Thread t: lane q = t % 8 of task group t / 8; it owns bytes [col0 + 16q, +16) of
+// every row its group touches.  Rows written in one level are read in later
+// levels by other threads of the SAME CTA only (slices are disjoint), so the CTA
+// barrier between levels is all the ordering the program needs.
+struct RowSpaces {
+  uint8_t *b0, *b1, *b2, *b3; // space bases, already offset to this thread's column
+  uint32_t pitch;
+  __device__ __forceinline__ uint8_t *at(uint32_t ref) const {
+    const uint32_t sp = (ref >> RQB_IDX_BITS) & 3u;
+    uint8_t *lo = (sp & 1u) ? b1 : b0, *hi = (sp & 1u) ? b3 : b2;
+    return ((sp & 2u) ? hi : lo) + (size_t)(ref & (RQB_MAX_ROWS - 1u)) * pitch;
+  }
+};
+
+__global__ void __launch_bounds__(kSolveThreads, kSolveMinCtas)
 rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const rqb_solve_args a = args_list[blockIdx.y];
-  const uint32_t col0 = blockIdx.x * VB;
-  if (col0 >= a.width) return; // whole CTA leaves: no barrier is skipped by a subset
+  const rqb_solve_args &a = args_list[blockIdx.y];
+  const uint32_t width = a.width;
+  const uint32_t col0 = blockIdx.x * RQB_SLICE_BYTES;
+  if (col0 >= width) return; // whole CTA leaves: no barrier is skipped by a subset
   uint8_t *ring = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);
-  uint8_t *ws = smem + kSolveSmemFixed;
   const int tid = threadIdx.x;
+  const uint32_t n_pages = a.n_pages;
+  const uint8_t *pages = a.pages;
 
   if (tid == 0) {
     for (int s = 0; s < kRingStages; s++) mbar_init(&bars[s], 1);
@@ -166,22 +141,20 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   }
   __syncthreads();
   if (tid == 0) {
-    const uint32_t first = a.n_pages < (uint32_t)kRingStages ? a.n_pages : (uint32_t)kRingStages;
+    const uint32_t first = n_pages < (uint32_t)kRingStages ? n_pages : (uint32_t)kRingStages;
     for (uint32_t s = 0; s < first; s++) {
       mbar_expect_tx(&bars[s], RQB_PAGE_BYTES);
-      tma_bulk_g2s(ring + s * RQB_PAGE_BYTES, a.pages + (size_t)s * RQB_PAGE_BYTES, RQB_PAGE_BYTES, &bars[s]);
+      tma_bulk_g2s(ring + s * RQB_PAGE_BYTES, pages + (size_t)s * RQB_PAGE_BYTES, RQB_PAGE_BYTES, &bars[s]);
     }
   }
-  // load this CTA's column slice of every row (zero rows where no input exists)
-  for (uint32_t slot = tid; slot < a.n_slots; slot += kSolveThreads) {
-    const uint32_t r = __ldg(&a.load_src[slot]);
-    Vec<VB> v = vzero<VB>();
-    if (r != RQB_ROW_NONE) v = vload<VB>(a.in + (size_t)r * a.in_pitch + col0);
-    vstore<VB>(ws + (size_t)slot * VB, v);
-  }
-  __syncthreads();
+  const uint32_t col = col0 + (uint32_t)(tid % kLanesPerTask) * 16u;
+  const bool active = col < width; // the last slice of a row may be narrower than 128 bytes
+  const uint32_t grp = (uint32_t)tid / kLanesPerTask;
+  RowSpaces R;
+  R.b0 = a.base[0] + col; R.b1 = a.base[1] + col; R.b2 = a.base[2] + col; R.b3 = a.base[3] + col;
+  R.pitch = a.pitch;
 
-  for (uint32_t pg = 0; pg < a.n_pages; pg++) {
+  for (uint32_t pg = 0; pg < n_pages; pg++) {
     const uint32_t st = pg % kRingStages;
     mbar_wait(&bars[st], (pg / kRingStages) & 1u);
     const uint8_t *page = ring + st * RQB_PAGE_BYTES;
@@ -190,67 +163,66 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
     for (uint32_t lv = 0; lv < n_levels; lv++) {
       const uint4 lh = *reinterpret_cast<const uint4 *>(page + off); // n_tasks, next_off
       const uint4 *tasks = reinterpret_cast<const uint4 *>(page + off + sizeof(rqb_level_hdr));
-      for (uint32_t t = tid; t < lh.x; t += kSolveThreads) {
-        const uint4 th = tasks[t]; // {src_off, arg, nsrc | dst<<16, kind}
-        const uint32_t nsrc = th.z & 0xffffu, dst = th.z >> 16, kind = th.w & 0xffu;
-        const uint8_t *sp = page + th.x;
-        if (kind == RQB_T_GF_SET || kind == RQB_T_GF_ACC) {
-          Vec<VB> acc = vzero<VB>();
-          if (kind == RQB_T_GF_ACC) acc = vload<VB>(ws + (size_t)dst * VB);
-          const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp);
-          for (uint32_t k = 0; k < nsrc; k++) {
-            const uint32_t e = s32[k];
-            const Vec<VB> x = vload<VB>(ws + (size_t)(e & 0xffffu) * VB);
-            const BetaPlanes bp = beta_planes((e >> 16) & 0xffu);
+      if (active) {
+        for (uint32_t t = grp; t < lh.x; t += kTaskGroups) {
+          const uint4 th = tasks[t]; // {src_off, dst, nsrc | kind<<16 | aux<<24, pad}
+          const uint32_t nsrc = th.z & 0xffffu, kind = (th.z >> 16) & 0xffu;
+          const uint32_t *sp = reinterpret_cast<const uint32_t *>(page + th.x);
+          if (kind == RQB_T_SCAN) {
+            // y = alpha*y ^ row[e_k]; row[dst+k] = y.  Loads run four entries ahead of the chain.
+            uint4 y = make_uint4(0, 0, 0, 0);
+            uint8_t *dp = R.at(th.y);
+            for (uint32_t k0 = 0; k0 < nsrc; k0 += 4) {
+              const uint4 e = *reinterpret_cast<const uint4 *>(sp + k0);
+              const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+              uint4 x[4];
 #pragma unroll
-            for (int q = 0; q < Vec<VB>::NW; q++) acc.w[q] ^= gfmul4(x.w[q], bp);
-          }
-          vstore<VB>(ws + (size_t)dst * VB, acc);
-        } else if (kind == RQB_T_HORNER) {
-          const uint32_t H = th.y;
-          const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp);
-          for (uint32_t h = 0; h < H; h++) vstore<VB>(ws + (size_t)(dst + h) * VB, vzero<VB>());
-          Vec<VB> y = vzero<VB>();
-          for (uint32_t k = 0; k < nsrc; k++) {
-            const uint32_t e = s32[k], slot = e & 0xffffu;
+              for (int u = 0; u < 4; u++) {
+                x[u] = make_uint4(0, 0, 0, 0);
+                if (k0 + u < nsrc && (ev[u] & RQB_REF_MASK) != RQB_REF_NONE)
+                  x[u] = *reinterpret_cast<const uint4 *>(R.at(ev[u]));
+              }
 #pragma unroll
-            for (int q = 0; q < Vec<VB>::NW; q++) y.w[q] = xtime4(y.w[q]);
-            if (slot != RQB_SLOT_NONE) vxor<VB>(y, vload<VB>(ws + (size_t)slot * VB));
-            if (e & (1u << 24)) {
-              uint8_t *p1 = ws + (size_t)(dst + ((e >> 16) & 15u)) * VB;
-              uint8_t *p2 = ws + (size_t)(dst + ((e >> 20) & 15u)) * VB;
-              Vec<VB> a1 = vload<VB>(p1), a2 = vload<VB>(p2);
-              vxor<VB>(a1, y);
-              vxor<VB>(a2, y);
-              vstore<VB>(p1, a1);
-              vstore<VB>(p2, a2);
+              for (int u = 0; u < 4; u++) {
+                if (k0 + u < nsrc) {
+                  y.x = xtime4(y.x) ^ x[u].x; y.y = xtime4(y.y) ^ x[u].y;
+                  y.z = xtime4(y.z) ^ x[u].z; y.w = xtime4(y.w) ^ x[u].w;
+                  *reinterpret_cast<uint4 *>(dp) = y;
+                  dp += R.pitch;
+                }
+              }
             }
-          }
-          vstore<VB>(ws + (size_t)(dst + H) * VB, y);
-        } else {
-          Vec<VB> acc = vzero<VB>();
-          if (kind == RQB_T_XOR_ACC)
-            acc = vload<VB>(ws + (size_t)dst * VB);
-          else if (kind == RQB_T_LOAD_XOR && th.y != RQB_ROW_NONE)
-            acc = vload<VB>(a.in + (size_t)th.y * a.in_pitch + col0);
-          const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sp);
-          uint32_t k = 0;
-          for (; k + 4 <= nsrc; k += 4) { // lists are 8-byte aligned and padded
-            const uint2 q = *reinterpret_cast<const uint2 *>(s16 + k);
-            const Vec<VB> x0 = vload<VB>(ws + (size_t)(q.x & 0xffffu) * VB);
-            const Vec<VB> x1 = vload<VB>(ws + (size_t)(q.x >> 16) * VB);
-            const Vec<VB> x2 = vload<VB>(ws + (size_t)(q.y & 0xffffu) * VB);
-            const Vec<VB> x3 = vload<VB>(ws + (size_t)(q.y >> 16) * VB);
+          } else {
+            // up to RQB_MAX_SRCS row segments, all requested before the first is consumed
+            const uint4 i0 = *reinterpret_cast<const uint4 *>(sp);
+            uint4 i1 = make_uint4(0, 0, 0, 0);
+            if (nsrc > 4) i1 = *reinterpret_cast<const uint4 *>(sp + 4);
+            const uint32_t id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            uint4 v[8];
 #pragma unroll
-            for (int w = 0; w < Vec<VB>::NW; w++) acc.w[w] ^= x0.w[w] ^ x1.w[w] ^ x2.w[w] ^ x3.w[w];
+            for (int u = 0; u < 8; u++) {
+              v[u] = make_uint4(0, 0, 0, 0);
+              if ((uint32_t)u < nsrc) v[u] = *reinterpret_cast<const uint4 *>(R.at(id[u]));
+            }
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            if (kind == RQB_T_XOR) {
+#pragma unroll
+              for (int u = 0; u < 8; u++) xor4(acc, v[u]);
+            } else {
+#pragma unroll 1
+              for (uint32_t u = 0; u < nsrc; u++) {
+                const BetaPlanes bp = beta_planes(sp[u] >> 24); // beta re-read from shared memory: no dynamic register index
+                // v[] is indexed dynamically here only through this select chain (keeps it in registers)
+                uint4 x = v[0];
+#pragma unroll
+                for (int w = 1; w < 8; w++)
+                  if (u == (uint32_t)w) x = v[w];
+                acc.x ^= gfmul4(x.x, bp); acc.y ^= gfmul4(x.y, bp);
+                acc.z ^= gfmul4(x.z, bp); acc.w ^= gfmul4(x.w, bp);
+              }
+            }
+            *reinterpret_cast<uint4 *>(R.at(th.y)) = acc;
           }
-          for (; k < nsrc; k++) vxor<VB>(acc, vload<VB>(ws + (size_t)s16[k] * VB));
-          if (kind == RQB_T_OUT_C)
-            vstore<VB>(a.c_out + (size_t)th.y * a.c_pitch + col0, acc);
-          else if (kind == RQB_T_OUT_SYM)
-            vstore<VB>(a.sym_out + (size_t)th.y * a.sym_pitch + col0, acc);
-          else
-            vstore<VB>(ws + (size_t)dst * VB, acc);
         }
       }
       __syncthreads();
@@ -258,10 +230,10 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
     }
     if (n_levels == 0) __syncthreads();
     // every thread is past its last read of this stage: refill it
-    if (tid == 0 && pg + kRingStages < a.n_pages) {
+    if (tid == 0 && pg + kRingStages < n_pages) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bars[st], RQB_PAGE_BYTES);
-      tma_bulk_g2s(ring + st * RQB_PAGE_BYTES, a.pages + (size_t)(pg + kRingStages) * RQB_PAGE_BYTES,
+      tma_bulk_g2s(ring + st * RQB_PAGE_BYTES, pages + (size_t)(pg + kRingStages) * RQB_PAGE_BYTES,
                    RQB_PAGE_BYTES, &bars[st]);
     }
   }
@@ -362,25 +334,6 @@ static int ensure_consts() {
   return 0;
 }
 
-template <int VB>
-static int launch_solve_t(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots, uint32_t max_width,
-                          cudaStream_t st) {
-  const uint32_t smem = kSolveSmemFixed + max_slots * VB;
-  static std::atomic<uint32_t> configured[64];
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (dev >= 64 || configured[dev].load(std::memory_order_acquire) < smem) {
-    std::lock_guard<std::mutex> lk(g_cfg_mu);
-    CK(cudaFuncSetAttribute(rqb_solve_kernel<VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    if (dev < 64) configured[dev].store(kMaxSmem, std::memory_order_release);
-  }
-  dim3 grid((max_width + VB - 1) / VB, (unsigned)nblocks);
-  rqb_solve_kernel<VB><<<grid, kSolveThreads, smem, st>>>(args_dev);
-  g_launches++;
-  CK(cudaGetLastError());
-  return 0;
-}
-
 extern "C" {
 
 const char *rqb_dev_last_error(void) { return g_err; }
@@ -471,27 +424,13 @@ int rqb_event_elapsed_ms(void *start, void *stop, float *ms) {
   return 0;
 }
 
-int rqb_solve_pick_vec(uint32_t n_slots) {
-  for (int vb = 16; vb >= 2; vb >>= 1)
-    if ((uint64_t)kSolveSmemFixed + (uint64_t)n_slots * vb <= kMaxSmem) return vb;
+int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, void *stream) {
+  if (nblocks <= 0 || max_width == 0) return 0;
+  dim3 grid((max_width + RQB_SLICE_BYTES - 1) / RQB_SLICE_BYTES, (unsigned)nblocks);
+  rqb_solve_kernel<<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
+  g_launches++;
+  CK(cudaGetLastError());
   return 0;
-}
-
-int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots, uint32_t max_width,
-                     int vec_bytes, void *stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if ((uint64_t)kSolveSmemFixed + (uint64_t)max_slots * (uint32_t)vec_bytes > kMaxSmem) {
-    snprintf(g_err, sizeof(g_err), "solve: %u slots x %d bytes exceed shared memory", max_slots, vec_bytes);
-    return (int)cudaErrorInvalidValue;
-  }
-  switch (vec_bytes) {
-    case 16: return launch_solve_t<16>(args_dev, nblocks, max_slots, max_width, st);
-    case 8: return launch_solve_t<8>(args_dev, nblocks, max_slots, max_width, st);
-    case 4: return launch_solve_t<4>(args_dev, nblocks, max_slots, max_width, st);
-    case 2: return launch_solve_t<2>(args_dev, nblocks, max_slots, max_width, st);
-  }
-  snprintf(g_err, sizeof(g_err), "solve: bad vec_bytes %d", vec_bytes);
-  return (int)cudaErrorInvalidValue;
 }
 
 int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const uint32_t *isi_dev, uint32_t n,

@@ -25,14 +25,12 @@ typedef struct {
 /* arguments of one source block for the column-sliced solve kernel
  * (all pointers are DEVICE pointers) */
 typedef struct {
-  const uint8_t *in;        /* input symbol rows                         */
-  uint8_t *c_out;           /* intermediate symbols, row = index (or 0)  */
-  uint8_t *sym_out;         /* requested encoding symbols (or 0)         */
-  const uint32_t *load_src; /* [n_slots] input row per slot / ROW_NONE   */
-  const uint8_t *pages;     /* program pages                             */
-  uint32_t in_pitch, c_pitch, sym_pitch; /* bytes, multiples of 64       */
-  uint32_t n_slots, n_pages;
-  uint32_t width;           /* bytes per row to process (multiple of 16) */
+  uint8_t *base[4];     /* row spaces of rqb_program.h: in, working rows, C, emitted symbols */
+  const uint8_t *pages; /* program pages                                                     */
+  uint32_t pitch;       /* bytes between rows (all spaces), multiple of 64                   */
+  uint32_t n_pages;
+  uint32_t width;       /* bytes per row to process (multiple of 16)                         */
+  uint32_t pad;
 } rqb_solve_args;
 
 int rqb_dev_count(void);
@@ -63,13 +61,9 @@ int rqb_event_record(void *e, void *stream);
 int rqb_event_sync(void *e);
 int rqb_event_elapsed_ms(void *start, void *stop, float *ms);
 
-/* bytes of shared memory the solve kernel needs for n_slots rows of vec bytes;
- * picks the widest slice (16, 8, 4, 2 bytes) that fits; 0 = does not fit */
-int rqb_solve_pick_vec(uint32_t n_slots);
 /* launches ONE kernel over nblocks source blocks (gridDim.y); args_dev is a
- * device array of rqb_solve_args; max_* are maxima over the batch */
-int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_slots,
-                     uint32_t max_width, int vec_bytes, void *stream);
+ * device array of rqb_solve_args; max_width is the maximum over the batch */
+int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, void *stream);
 
 /* LT combine (decode_row, lib/nanorq.c:184-204): out[k] = XOR of the
  * intermediate symbols selected by Tuple[K', isi[k]]; tuples are generated on

@@ -3,7 +3,8 @@
  * What the reference does in precode_matrix_gen + precode_matrix_invert
  * (lib/precode.c:90-377) -- generate the sparse constraint matrix A, peel it,
  * eliminate the dense remainder, record row operations -- is re-designed here
- * for a device that holds a column slice of every row in shared memory:
+ * for a device that replays a levelled gather program on column slices of the
+ * block (rqb_program.h):
  *
  *   1. build A (LDPC + LT rows; HDPC rows are handled in closed form);
  *   2. peel: order i (row, column) pairs so the peeled part X is unit lower
@@ -16,10 +17,13 @@
  *                                          lib/precode.c:60-83, in O((K'+S)*u))
  *      then a Gauss-Jordan of the small Schur system, binary rows first, so the
  *      inactive symbols z become explicit linear combinations of residual rows;
- *   4. emit gather tasks (rqb_program.h):
- *        A  Y      = X^-1 b_top           sparse forward substitution, by levels
- *        B  r_low  = b_low ^ X_low*Y      + HDPC rows through HORNER chunk scans
- *        C  z      = (Schur)^-1 r_low     3-4 dense levels
+ *   4. emit gather tasks of at most RQB_MAX_SRCS sources:
+ *        A  Y      = X^-1 b_top           sparse forward substitution, by levels;
+ *                                         rows with many terms are pre-reduced by
+ *                                         partial sums scheduled as early as their
+ *                                         inputs exist, off the critical path
+ *        B  r_low  = b_low ^ X_low*Y      + alpha-scans of Y in chunks (SCAN tasks)
+ *        C  z      = (Schur)^-1 r_low     a few dense levels (reduction trees)
  *        D  b_top' = b_top ^ U_top*z      (b_top re-read from the input rows)
  *        E  x      = X^-1 b_top'          same levels as A
  *        O  outputs: C[] in RFC order and/or LT combinations of it.
@@ -27,10 +31,16 @@
  * The intermediate symbols are the unique solution of A*C = D when rank(A) = L,
  * so this factorisation yields the same bytes as the reference's op sequence;
  * rank < L is reported exactly when the reference's elimination would fail.
+ *
+ * Allocation: every temporary lives in a per-thread scratch arena that is kept
+ * between calls, so that decoder threads planning different blocks at wire rate
+ * never meet in the allocator (malloc/mmap/page-fault contention made the
+ * planner scale negatively with threads).
  */
 #define _POSIX_C_SOURCE 200809L
 #include "rqb_planner.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -42,10 +52,9 @@
 /* ------------------------------------------------------------------ utils */
 static rqb_gf_tables GF;
 static uint64_t SPREAD[256]; /* byte -> 8 bytes holding its bits as 0/1 */
-static volatile int tables_ready;
+static pthread_once_t tables_once = PTHREAD_ONCE_INIT;
 
-static void tables_init(void) {
-  if (tables_ready) return;
+static void tables_build(void) {
   rqb_gf_build(&GF);
   for (int b = 0; b < 256; b++) {
     uint64_t v = 0;
@@ -53,8 +62,6 @@ static void tables_init(void) {
       if (b >> k & 1) v |= (uint64_t)1 << (8 * k);
     SPREAD[b] = v;
   }
-  __sync_synchronize();
-  tables_ready = 1;
 }
 
 static double now_s(void) {
@@ -97,128 +104,237 @@ int rqb_host_lt_indices(const rqb_params *P, uint32_t X, uint32_t *out) {
   return rqb_lt_indices(P, rqb_rand_v, rqb_degree_cdf, X, out);
 }
 
+/* ------------------------------------------------- per-thread scratch arena */
+enum {
+  SC_RPTR, SC_CIDX, SC_CPTR, SC_RIDX, SC_CUR, SC_DEG, SC_COLSTATE, SC_COLPOS, SC_COLT, SC_ROWPOS, SC_PROW,
+  SC_PCOL, SC_UCOL, SC_STK1, SC_STK2, SC_LEVEL, SC_G, SC_LOWROWS, SC_SB, SC_TB, SC_XPTR, SC_XIDX, SC_SH,
+  SC_HB1, SC_HB2, SC_YBUF, SC_ACCBUF, SC_PIVROW, SC_PIVCOL, SC_FREECOLS, SC_Q, SC_TQ, SC_TMP, SC_CSLOT,
+  SC_FPTR, SC_FITEMS, SC_PFIRST, SC_PLEVEL, SC_PPTR, SC_PITEMS, SC_CURLOC, SC_TASKS, SC_SRCS, SC_ORDER,
+  SC_LVLCNT, SC_CS, SC_COEF, SC_COUNT
+};
+typedef struct {
+  void *p[SC_COUNT];
+  size_t cap[SC_COUNT];
+} scratch_t;
+
+static pthread_key_t sc_key;
+static pthread_once_t sc_once = PTHREAD_ONCE_INIT;
+static void sc_destroy(void *v) {
+  scratch_t *sc = v;
+  if (!sc) return;
+  for (int k = 0; k < SC_COUNT; k++) free(sc->p[k]);
+  free(sc);
+}
+static void sc_make_key(void) { pthread_key_create(&sc_key, sc_destroy); }
+static scratch_t *sc_get(void) {
+  pthread_once(&sc_once, sc_make_key);
+  scratch_t *sc = pthread_getspecific(sc_key);
+  if (!sc) {
+    sc = calloc(1, sizeof(*sc));
+    pthread_setspecific(sc_key, sc);
+  }
+  return sc;
+}
+/* a buffer of at least `bytes` (contents undefined unless zero != 0) */
+static void *sc_buf(scratch_t *sc, int id, size_t bytes, int zero) {
+  if (bytes < 64) bytes = 64;
+  if (sc->cap[id] < bytes) {
+    free(sc->p[id]);
+    size_t cap = bytes + bytes / 2;
+    sc->p[id] = malloc(cap);
+    sc->cap[id] = cap;
+  }
+  if (zero) memset(sc->p[id], 0, bytes);
+  return sc->p[id];
+}
+/* grow keeping the contents */
+static void *sc_grow(scratch_t *sc, int id, size_t bytes) {
+  if (sc->cap[id] < bytes) {
+    size_t cap = bytes * 2;
+    sc->p[id] = realloc(sc->p[id], cap);
+    sc->cap[id] = cap;
+  }
+  return sc->p[id];
+}
+
 /* ------------------------------------------------------ program builder */
 typedef struct {
-  rqb_task *tasks;
-  size_t nt, ct;
-  uint8_t *src;
-  size_t ns, cs;
-  uint8_t *pages;
-  size_t npages, cpages;
-  uint32_t cur; /* write offset inside the open page, 0 = none open */
-  uint32_t levels_in_page;
-  size_t tot_levels, tot_tasks, tot_srcs, tot_gf, tot_horner;
-  int error;
-} progbuf;
+  uint32_t dst, src_at, level;
+  uint16_t nsrc;
+  uint8_t kind, aux;
+} ptask;
 
-static void pb_task(progbuf *pb, int kind, uint32_t dst, uint32_t arg, uint32_t nsrc,
-                    const void *srcs, size_t esz) {
-  if (pb->nt == pb->ct) {
-    pb->ct = pb->ct ? pb->ct * 2 : 1024;
-    pb->tasks = realloc(pb->tasks, pb->ct * sizeof(rqb_task));
-  }
-  size_t bytes = ((size_t)nsrc * esz + 7) & ~(size_t)7;
-  if (pb->ns + bytes > pb->cs) {
-    pb->cs = (pb->cs ? pb->cs * 2 : 65536) + bytes;
-    pb->src = realloc(pb->src, pb->cs);
-  }
-  if (nsrc > 0xFFFF || dst > 0xFFFF) pb->error = 1;
-  rqb_task *t = &pb->tasks[pb->nt++];
-  memset(t, 0, sizeof(*t));
-  t->src_off = (uint32_t)pb->ns;
-  t->arg = arg;
-  t->nsrc = (uint16_t)nsrc;
-  t->dst = (uint16_t)dst;
+typedef struct {
+  scratch_t *sc;
+  ptask *tasks;
+  size_t nt;
+  uint32_t *srcs;
+  size_t ns;
+  uint32_t ws_next; /* next unused working row */
+  uint32_t max_level;
+  size_t tot_x, tot_gf, tot_h;
+} builder;
+
+static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, const uint32_t *srcs, uint32_t n) {
+  b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
+  b->srcs = sc_grow(b->sc, SC_SRCS, (b->ns + n + 1) * sizeof(uint32_t));
+  ptask *t = &b->tasks[b->nt++];
+  t->dst = dst;
+  t->src_at = (uint32_t)b->ns;
+  t->level = level;
+  t->nsrc = (uint16_t)n;
   t->kind = (uint8_t)kind;
-  if (nsrc) memcpy(pb->src + pb->ns, srcs, (size_t)nsrc * esz);
-  if (bytes > (size_t)nsrc * esz) memset(pb->src + pb->ns + (size_t)nsrc * esz, 0, bytes - (size_t)nsrc * esz);
-  pb->ns += bytes;
-  if (kind == RQB_T_GF_SET || kind == RQB_T_GF_ACC)
-    pb->tot_gf += nsrc;
-  else if (kind == RQB_T_HORNER)
-    pb->tot_horner += nsrc;
+  t->aux = (uint8_t)aux;
+  if (n) memcpy(b->srcs + b->ns, srcs, (size_t)n * sizeof(uint32_t));
+  b->ns += n;
+  if (level > b->max_level) b->max_level = level;
+  if (kind == RQB_T_GF)
+    b->tot_gf += n;
+  else if (kind == RQB_T_SCAN)
+    b->tot_h += n;
   else
-    pb->tot_srcs += nsrc;
+    b->tot_x += n;
 }
 
-static size_t task_src_bytes(const rqb_task *t) {
-  size_t esz = (t->kind == RQB_T_GF_SET || t->kind == RQB_T_GF_ACC || t->kind == RQB_T_HORNER) ? 4 : 2;
-  return ((size_t)t->nsrc * esz + 7) & ~(size_t)7;
-}
-
-static void pb_close_page(progbuf *pb) {
-  if (!pb->cur) return;
-  rqb_page_hdr *h = (rqb_page_hdr *)(pb->pages + (pb->npages - 1) * RQB_PAGE_BYTES);
-  h->n_levels = pb->levels_in_page;
-  pb->cur = 0;
-  pb->levels_in_page = 0;
-}
-
-static void pb_open_page(progbuf *pb) {
-  if (pb->npages == pb->cpages) {
-    pb->cpages = pb->cpages ? pb->cpages * 2 : 64;
-    pb->pages = realloc(pb->pages, pb->cpages * RQB_PAGE_BYTES);
+/* row[dst] = sum of n sources that all exist before `level`: one task, or a
+ * tree of partial sums into fresh working rows (leaves keep `kind`, inner nodes
+ * are plain XORs).  srcs is clobbered.  Returns the level that writes dst. */
+static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint32_t n, uint32_t level) {
+  while (n > RQB_MAX_SRCS) {
+    uint32_t m = 0;
+    for (uint32_t o = 0; o < n; o += RQB_MAX_SRCS) {
+      uint32_t cnt = n - o < RQB_MAX_SRCS ? n - o : RQB_MAX_SRCS;
+      uint32_t r = RQB_REF(RQB_SP_WS, b->ws_next++);
+      b_task(b, kind, r, 0, level, srcs + o, cnt);
+      srcs[m++] = RQB_SRC(r, 1);
+    }
+    n = m;
+    kind = RQB_T_XOR;
+    level++;
   }
-  memset(pb->pages + pb->npages * RQB_PAGE_BYTES, 0, RQB_PAGE_BYTES);
-  pb->npages++;
-  pb->cur = sizeof(rqb_page_hdr);
-  pb->levels_in_page = 0;
+  b_task(b, kind, dst, 0, level, srcs, n);
+  return level;
 }
 
-static int task_cmp(const void *a, const void *b) {
-  const rqb_task *x = a, *y = b;
+static int cmp_task_idx(const void *a, const void *b, void *ctx) {
+  const ptask *T = ctx;
+  const ptask *x = &T[*(const uint32_t *)a], *y = &T[*(const uint32_t *)b];
   if (x->kind != y->kind) return (int)x->kind - (int)y->kind;
-  return (int)y->nsrc - (int)x->nsrc;
+  if (x->nsrc != y->nsrc) return (int)y->nsrc - (int)x->nsrc;
+  return (int)(*(const uint32_t *)a > *(const uint32_t *)b) - (int)(*(const uint32_t *)a < *(const uint32_t *)b);
 }
 
-/* close the current level: pack its tasks into pages (splitting when a page
- * fills up; splitting a level is always legal, its tasks are independent) */
-static void pb_level_end(progbuf *pb) {
-  if (!pb->nt) return;
-  qsort(pb->tasks, pb->nt, sizeof(rqb_task), task_cmp);
-  size_t idx = 0;
-  while (idx < pb->nt) {
-    if (!pb->cur) pb_open_page(pb);
-    size_t avail = RQB_PAGE_BYTES - pb->cur, need = sizeof(rqb_level_hdr), j = idx;
-    while (j < pb->nt) {
-      size_t add = sizeof(rqb_task) + task_src_bytes(&pb->tasks[j]);
-      if (need + add > avail) break;
-      need += add;
-      j++;
-    }
-    if (j == idx) {
-      if (pb->cur == sizeof(rqb_page_hdr)) { /* a single task larger than a page */
-        pb->error = 1;
-        return;
+/* insertion sort is enough: levels are small, and qsort_r is not portable C11 */
+static void sort_level(uint32_t *idx, size_t n, const ptask *T) {
+  if (n > 64) { /* shell sort for the few wide levels */
+    for (size_t gap = n / 2; gap > 0; gap /= 2)
+      for (size_t i = gap; i < n; i++) {
+        uint32_t v = idx[i];
+        size_t j = i;
+        while (j >= gap && cmp_task_idx(&idx[j - gap], &v, (void *)T) > 0) {
+          idx[j] = idx[j - gap];
+          j -= gap;
+        }
+        idx[j] = v;
       }
-      pb_close_page(pb);
-      continue;
-    }
-    need = (need + 15) & ~(size_t)15; /* levels start 16-byte aligned (uint4 loads); avail is a multiple of 16 */
-    uint8_t *page = pb->pages + (pb->npages - 1) * RQB_PAGE_BYTES;
-    rqb_level_hdr *lh = (rqb_level_hdr *)(page + pb->cur);
-    size_t n = j - idx;
-    lh->n_tasks = (uint32_t)n;
-    lh->next_off = (uint32_t)(pb->cur + need);
-    rqb_task *dst = (rqb_task *)(page + pb->cur + sizeof(rqb_level_hdr));
-    uint32_t soff = (uint32_t)(pb->cur + sizeof(rqb_level_hdr) + n * sizeof(rqb_task));
-    for (size_t k = 0; k < n; k++) {
-      rqb_task t = pb->tasks[idx + k];
-      size_t sb = task_src_bytes(&t);
-      memcpy(page + soff, pb->src + t.src_off, sb);
-      t.src_off = soff;
-      soff += (uint32_t)sb;
-      dst[k] = t;
-    }
-    pb->cur += (uint32_t)need;
-    pb->levels_in_page++;
-    pb->tot_levels++;
-    pb->tot_tasks += n;
-    idx = j;
-    if (RQB_PAGE_BYTES - pb->cur < sizeof(rqb_level_hdr) + sizeof(rqb_task) + 8) pb_close_page(pb);
+    return;
   }
-  pb->nt = 0;
-  pb->ns = 0;
+  for (size_t i = 1; i < n; i++) {
+    uint32_t v = idx[i];
+    size_t j = i;
+    while (j > 0 && cmp_task_idx(&idx[j - 1], &v, (void *)T) > 0) {
+      idx[j] = idx[j - 1];
+      j--;
+    }
+    idx[j] = v;
+  }
+}
+
+static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + (((size_t)t->nsrc * 4 + 15) & ~(size_t)15); }
+
+/* pack the tasks, level by level, into pages (a level may be split over pages:
+ * its tasks are independent).  Returns 0 or a negative error. */
+static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
+  scratch_t *sc = b->sc;
+  const uint32_t nl = b->max_level + 1;
+  uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nl + 2) * 4, 1);
+  uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
+  for (size_t k = 0; k < b->nt; k++) cnt[b->tasks[k].level + 1]++;
+  for (uint32_t l = 0; l < nl; l++) cnt[l + 1] += cnt[l];
+  { /* stable counting sort by level; cnt[l] is consumed as the cursor, restore afterwards */
+    for (size_t k = 0; k < b->nt; k++) order[cnt[b->tasks[k].level]++] = (uint32_t)k;
+    for (uint32_t l = nl; l > 0; l--) cnt[l] = cnt[l - 1];
+    cnt[0] = 0;
+  }
+  size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
+  uint8_t *pages = plan->pages;
+#define OPEN_PAGE()                                                         \
+  do {                                                                      \
+    if ((npages + 1) * RQB_PAGE_BYTES > plan->pages_cap) {                  \
+      plan->pages_cap = (npages + 64) * 2 * RQB_PAGE_BYTES;                 \
+      pages = plan->pages = realloc(plan->pages, plan->pages_cap);          \
+    }                                                                       \
+    memset(pages + npages * RQB_PAGE_BYTES, 0, RQB_PAGE_BYTES);             \
+    npages++;                                                               \
+    cur = sizeof(rqb_page_hdr);                                             \
+    levels_in_page = 0;                                                     \
+  } while (0)
+#define CLOSE_PAGE()                                                                              \
+  do {                                                                                            \
+    if (cur) ((rqb_page_hdr *)(pages + (npages - 1) * RQB_PAGE_BYTES))->n_levels = (uint32_t)levels_in_page; \
+    cur = 0;                                                                                      \
+  } while (0)
+  for (uint32_t l = 0; l < nl; l++) {
+    size_t lo = cnt[l], hi = cnt[l + 1];
+    if (lo == hi) continue;
+    sort_level(order + lo, hi - lo, b->tasks);
+    size_t idx = lo;
+    while (idx < hi) {
+      if (!cur) OPEN_PAGE();
+      size_t avail = RQB_PAGE_BYTES - cur, need = sizeof(rqb_level_hdr), j = idx;
+      while (j < hi) {
+        size_t add = task_bytes(&b->tasks[order[j]]);
+        if (need + add > avail) break;
+        need += add;
+        j++;
+      }
+      if (j == idx) {
+        if (cur == sizeof(rqb_page_hdr)) return -5; /* a single task larger than a page */
+        CLOSE_PAGE();
+        continue;
+      }
+      uint8_t *page = pages + (npages - 1) * RQB_PAGE_BYTES;
+      rqb_level_hdr *lh = (rqb_level_hdr *)(page + cur);
+      size_t n = j - idx;
+      lh->n_tasks = (uint32_t)n;
+      lh->next_off = (uint32_t)(cur + need);
+      rqb_task *dst = (rqb_task *)(page + cur + sizeof(rqb_level_hdr));
+      uint32_t soff = (uint32_t)(cur + sizeof(rqb_level_hdr) + n * sizeof(rqb_task));
+      for (size_t k = 0; k < n; k++) {
+        const ptask *t = &b->tasks[order[idx + k]];
+        size_t sb = ((size_t)t->nsrc * 4 + 15) & ~(size_t)15;
+        memcpy(page + soff, b->srcs + t->src_at, (size_t)t->nsrc * 4);
+        dst[k].src_off = soff;
+        dst[k].dst = t->dst;
+        dst[k].nsrc = t->nsrc;
+        dst[k].kind = t->kind;
+        dst[k].aux = t->aux;
+        dst[k].pad = 0;
+        soff += (uint32_t)sb;
+      }
+      cur += need;
+      levels_in_page++;
+      levels++;
+      idx = j;
+      if (RQB_PAGE_BYTES - cur < sizeof(rqb_level_hdr) + sizeof(rqb_task) + 16) CLOSE_PAGE();
+    }
+  }
+  CLOSE_PAGE();
+#undef OPEN_PAGE
+#undef CLOSE_PAGE
+  plan->n_pages = (uint32_t)npages;
+  *tot_levels = levels;
+  return 0;
 }
 
 /* ------------------------------------------------------------ bit helpers */
@@ -233,45 +349,45 @@ static inline uint64_t xtime8(uint64_t x) {
   return ((x & 0x7f7f7f7f7f7f7f7fULL) << 1) ^ (((x >> 7) & 0x0101010101010101ULL) * 0x1d);
 }
 
+/* ------------------------------------------------------- plan object pool */
+static rqb_plan *g_free_plans;
+static pthread_mutex_t g_plans_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static rqb_plan *plan_acquire(void) {
+  pthread_mutex_lock(&g_plans_mu);
+  rqb_plan *p = g_free_plans;
+  if (p) g_free_plans = p->next_free;
+  pthread_mutex_unlock(&g_plans_mu);
+  if (!p) p = calloc(1, sizeof(*p));
+  return p;
+}
+
+void rqb_plan_free(rqb_plan *p) {
+  if (!p) return;
+  pthread_mutex_lock(&g_plans_mu); /* keeps its page buffer for the next block */
+  p->next_free = g_free_plans;
+  g_free_plans = p;
+  pthread_mutex_unlock(&g_plans_mu);
+}
+
 /* ---------------------------------------------------------------- planner */
-#define FREE_ALL()                                                                        \
-  do {                                                                                    \
-    free(rptr); free(cidx); free(cptr); free(ridx); free(deg); free(col_state);           \
-    free(col_pos); free(col_t); free(row_pos); free(prow); free(pcol); free(ucol);        \
-    free(stk1); free(stk2); free(dptr); free(didx); free(level); free(G); free(lowrows);  \
-    free(Sb); free(Tb); free(xptr); free(xidx); free(Sh); free(hb1); free(hb2);           \
-    free(pivrow); free(pivcol_of_row); free(freecols); free(Q); free(TQ); free(tmp16);    \
-    free(tmp32); free(lvl_cnt); free(lvl_ord); free(cslot); free(ybuf); free(accbuf);     \
-    free(pb.tasks); free(pb.src);                                                         \
-  } while (0)
+#define NONE_REF RQB_REF_NONE /* "this row is all zero / has no location" */
 
 int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
-  tables_init();
+  pthread_once(&tables_once, tables_build);
   *out = NULL;
   rqb_params P;
   if (rqb_params_init(req->K, &P) || req->overhead < 0) return -1;
   const int S = P.S, H = P.H, W = P.W, L = P.L, Kp = P.Kprime, B = P.B;
   const int oh = req->overhead, R = L + oh, n = Kp + S, nlt = Kp + oh;
+  if ((uint32_t)H > RQB_MAX_H) return -1;
   double t0 = now_s();
-
-  int *rptr = NULL, *cidx = NULL, *cptr = NULL, *ridx = NULL, *deg = NULL;
-  uint8_t *col_state = NULL;
-  int *col_pos = NULL, *col_t = NULL, *row_pos = NULL, *prow = NULL, *pcol = NULL, *ucol = NULL;
-  int *stk1 = NULL, *stk2 = NULL, *dptr = NULL, *didx = NULL, *level = NULL, *lowrows = NULL;
-  uint64_t *G = NULL, *Sb = NULL, *Tb = NULL, *ybuf = NULL, *accbuf = NULL;
-  int *xptr = NULL, *xidx = NULL;
-  uint8_t *Sh = NULL, *hb1 = NULL, *hb2 = NULL, *Q = NULL, *TQ = NULL;
-  int *pivrow = NULL, *pivcol_of_row = NULL, *freecols = NULL, *lvl_cnt = NULL, *lvl_ord = NULL;
-  uint16_t *tmp16 = NULL, *cslot = NULL;
-  uint32_t *tmp32 = NULL;
-  progbuf pb;
-  memset(&pb, 0, sizeof(pb));
-  rqb_plan *plan = NULL;
+  scratch_t *sc = sc_get();
   int rc = 0;
 
   /* ---- 1. sparse matrix A, rows: [0,S) LDPC, [S,S+H) HDPC (kept empty, closed form),
    *         [S+H, R) LT rows.  Same contents as precode_matrix_gen (+patching). */
-  rptr = calloc((size_t)R + 1, sizeof(int));
+  int *rptr = sc_buf(sc, SC_RPTR, ((size_t)R + 2) * sizeof(int), 1);
   {
     for (int col = 0; col < B; col++) {
       int sub = col / S;
@@ -282,7 +398,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     for (int r = 0; r < S; r++) rptr[1 + r] += 3;
   }
   size_t cap = (size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)nlt + 16;
-  cidx = malloc(cap * sizeof(int));
+  int *cidx = sc_buf(sc, SC_CIDX, cap * sizeof(int), 0);
   {
     int acc = 0;
     for (int r = 0; r < S; r++) {
@@ -291,7 +407,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       acc += c;
     }
     for (int r = S; r <= S + H; r++) rptr[r] = acc;
-    int *cur = malloc(sizeof(int) * (size_t)S);
+    int *cur = sc_buf(sc, SC_CUR, sizeof(int) * (size_t)(S > L ? S : L), 0);
     memcpy(cur, rptr, sizeof(int) * (size_t)S);
     for (int col = 0; col < B; col++) {
       int sub = col / S;
@@ -304,7 +420,6 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       cidx[cur[r]++] = W + r % P.P;
       cidx[cur[r]++] = W + (r + 1) % P.P;
     }
-    free(cur);
     uint32_t idx[RQB_MAX_LT_DEGREE];
     for (int k = 0; k < nlt; k++) {
       int cnt = rqb_host_lt_indices(&P, req->isi[k], idx);
@@ -315,30 +430,29 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   }
   const int nnz = rptr[R];
   /* column lists */
-  cptr = calloc((size_t)L + 1, sizeof(int));
-  ridx = malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+  int *cptr = sc_buf(sc, SC_CPTR, ((size_t)L + 1) * sizeof(int), 1);
+  int *ridx = sc_buf(sc, SC_RIDX, sizeof(int) * (size_t)(nnz ? nnz : 1), 0);
   for (int k = 0; k < nnz; k++) cptr[cidx[k] + 1]++;
   for (int c = 0; c < L; c++) cptr[c + 1] += cptr[c];
   {
-    int *cur = malloc(sizeof(int) * (size_t)L);
+    int *cur = sc_buf(sc, SC_CUR, sizeof(int) * (size_t)(S > L ? S : L), 0);
     memcpy(cur, cptr, sizeof(int) * (size_t)L);
     for (int r = 0; r < R; r++)
       for (int k = rptr[r]; k < rptr[r + 1]; k++) ridx[cur[cidx[k]]++] = r;
-    free(cur);
   }
   double t1 = now_s();
 
   /* ---- 2. peeling */
-  deg = calloc((size_t)R, sizeof(int));
-  col_state = calloc((size_t)L, 1); /* 0 active, 1 peeled, 2 inactive */
-  col_pos = malloc(sizeof(int) * (size_t)L);
-  col_t = malloc(sizeof(int) * (size_t)L);
-  row_pos = malloc(sizeof(int) * (size_t)R);
-  prow = malloc(sizeof(int) * (size_t)L);
-  pcol = malloc(sizeof(int) * (size_t)L);
-  ucol = malloc(sizeof(int) * (size_t)L);
-  stk1 = malloc(sizeof(int) * ((size_t)nnz + (size_t)R + 8));
-  stk2 = malloc(sizeof(int) * ((size_t)nnz + (size_t)R + 8));
+  int *deg = sc_buf(sc, SC_DEG, (size_t)R * sizeof(int), 1);
+  uint8_t *col_state = sc_buf(sc, SC_COLSTATE, (size_t)L, 1); /* 0 active, 1 peeled, 2 inactive */
+  int *col_pos = sc_buf(sc, SC_COLPOS, sizeof(int) * (size_t)L, 0);
+  int *col_t = sc_buf(sc, SC_COLT, sizeof(int) * (size_t)L, 0);
+  int *row_pos = sc_buf(sc, SC_ROWPOS, sizeof(int) * (size_t)R, 0);
+  int *prow = sc_buf(sc, SC_PROW, sizeof(int) * (size_t)L, 0);
+  int *pcol = sc_buf(sc, SC_PCOL, sizeof(int) * (size_t)L, 0);
+  int *ucol = sc_buf(sc, SC_UCOL, sizeof(int) * (size_t)L, 0);
+  int *stk1 = sc_buf(sc, SC_STK1, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
+  int *stk2 = sc_buf(sc, SC_STK2, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
   int n1 = 0, n2 = 0, ni = 0, nu = 0;
   for (int r = 0; r < R; r++) row_pos[r] = -1;
   for (int c = 0; c < L; c++) col_pos[c] = col_t[c] = -1;
@@ -420,47 +534,84 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
   const int I = ni, U = nu, uw = (U + 63) / 64;
   const int nb = R - H - I;
-  if (I + U != L || nb < 0) {
-    rc = -2;
-    goto fail;
-  }
+  if (I + U != L || nb < 0) return -2;
   double t2 = now_s();
 
-  /* ---- 3a. dependencies, levels and G = X^-1 U_top (bits) */
-  dptr = malloc(sizeof(int) * ((size_t)I + 1));
-  didx = malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
-  level = malloc(sizeof(int) * ((size_t)I + 1));
-  G = calloc((size_t)(I ? I : 1) * uw, sizeof(uint64_t));
-  int maxlevel = -1;
+  /* ---- 3a. dependencies of the triangular solve, G = X^-1 U_top (bits), and the
+   * schedule of each row: at most RQB_MAX_SRCS-1 terms besides the row itself;
+   * longer rows get partial sums ("parts") placed at the earliest level their
+   * terms exist.  Items: q >= 0 = peeled position q, -1-k = part k. */
+  const int CAPF = (int)RQB_MAX_SRCS - 1;
+  int *level = sc_buf(sc, SC_LEVEL, sizeof(int) * ((size_t)I + 1), 0);
+  uint64_t *G = sc_buf(sc, SC_G, (size_t)(I ? I : 1) * uw * sizeof(uint64_t), 1);
+  int *fptr = sc_buf(sc, SC_FPTR, sizeof(int) * ((size_t)I + 1), 0);
+  int *fitems = sc_buf(sc, SC_FITEMS, sizeof(int) * ((size_t)I * CAPF + 8), 0);
+  int *pfirst = sc_buf(sc, SC_PFIRST, sizeof(int) * ((size_t)I + 1), 0);
+  /* parts: at most nnz/2 of them, items: at most nnz + #parts */
+  int *plevel = sc_buf(sc, SC_PLEVEL, sizeof(int) * ((size_t)nnz / 2 + 8), 0);
+  int *pptr = sc_buf(sc, SC_PPTR, sizeof(int) * ((size_t)nnz / 2 + 9), 0);
+  int *pitems = sc_buf(sc, SC_PITEMS, sizeof(int) * ((size_t)nnz * 2 + 64), 0);
+  int nparts = 0, npitems = 0, maxlevel = 0;
   {
-    int nd = 0;
+    int nf = 0;
+    int *it = sc_buf(sc, SC_TMP, sizeof(int) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
+    int *rd = it + ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64);
+    pptr[0] = 0;
     for (int p = 0; p < I; p++) {
-      int r = prow[p], lv = 0;
+      int r = prow[p], cnt = 0;
       uint64_t *g = G + (size_t)p * uw;
-      dptr[p] = nd;
+      pfirst[p] = nparts;
       for (int k = rptr[r]; k < rptr[r + 1]; k++) {
         int c = cidx[k];
         if (col_state[c] == 2) {
           bit_flip(g, col_t[c]);
         } else if (c != pcol[p]) {
           int q = col_pos[c];
-          if (q >= p) { /* cannot happen: would contradict the peeling invariant */
-            rc = -3;
-            goto fail;
-          }
-          didx[nd++] = q;
-          if (level[q] + 1 > lv) lv = level[q] + 1;
+          if (q >= p) return -3; /* cannot happen: would contradict the peeling invariant */
           bits_xor(g, G + (size_t)q * uw, uw);
+          /* insert sorted by the level at which the term exists */
+          int lv = level[q], j = cnt++;
+          while (j > 0 && rd[j - 1] > lv) {
+            rd[j] = rd[j - 1];
+            it[j] = it[j - 1];
+            j--;
+          }
+          rd[j] = lv;
+          it[j] = q;
         }
       }
-      level[p] = lv;
-      if (lv > maxlevel) maxlevel = lv;
+      int head = 0; /* items [head, cnt) are live, sorted by readiness */
+      while (cnt - head > CAPF) {
+        int take = cnt - head - CAPF + 1;
+        if (take > (int)RQB_MAX_SRCS) take = (int)RQB_MAX_SRCS;
+        int lv = rd[head + take - 1] + 1;
+        for (int k = 0; k < take; k++) pitems[npitems++] = it[head + k];
+        plevel[nparts] = lv;
+        pptr[nparts + 1] = npitems;
+        head += take;
+        /* put the part back, keeping the order */
+        int j = head - 1;
+        while (j + 1 < cnt && rd[j + 1] <= lv) {
+          rd[j] = rd[j + 1];
+          it[j] = it[j + 1];
+          j++;
+        }
+        rd[j] = lv;
+        it[j] = -1 - nparts;
+        head--;
+        nparts++;
+      }
+      fptr[p] = nf;
+      for (int k = head; k < cnt; k++) fitems[nf++] = it[k];
+      level[p] = cnt > head ? rd[cnt - 1] + 1 : 0;
+      if (level[p] > maxlevel) maxlevel = level[p];
     }
-    dptr[I] = nd;
+    fptr[I] = nf;
+    pfirst[I] = nparts;
   }
 
   /* ---- 3b. residual binary rows: Schur bits and their X-part source lists */
-  lowrows = malloc(sizeof(int) * (size_t)(nb ? nb : 1));
+  int *lowrows = sc_buf(sc, SC_LOWROWS, sizeof(int) * (size_t)(nb ? nb : 1), 0);
   {
     int m = 0;
     for (int r = S + H; r < R; r++)
@@ -469,10 +620,10 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       if (row_pos[r] < 0) lowrows[m++] = r;
   }
   const int nbw = (nb + 63) / 64;
-  Sb = calloc((size_t)(nb ? nb : 1) * uw, sizeof(uint64_t));
-  Tb = calloc((size_t)(nb ? nb : 1) * (nbw ? nbw : 1), sizeof(uint64_t));
-  xptr = malloc(sizeof(int) * ((size_t)nb + 1));
-  xidx = malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+  uint64_t *Sb = sc_buf(sc, SC_SB, (size_t)(nb ? nb : 1) * uw * sizeof(uint64_t), 1);
+  uint64_t *Tb = sc_buf(sc, SC_TB, (size_t)(nb ? nb : 1) * (nbw ? nbw : 1) * sizeof(uint64_t), 1);
+  int *xptr = sc_buf(sc, SC_XPTR, sizeof(int) * ((size_t)nb + 1), 0);
+  int *xidx = sc_buf(sc, SC_XIDX, sizeof(int) * (size_t)(nnz ? nnz : 1), 0);
   {
     int nx = 0;
     for (int m = 0; m < nb; m++) {
@@ -499,18 +650,19 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * (lib/precode.c:60-83)  =>  sum_j HDPC[h][j] v_j = alpha^h y_{n-1} ^ sum_{j<=n-2, h in b(j)} y_j
    * with y_j = alpha*y_{j-1} ^ v_j.  Here v_j is the u-vector of column j: row q of G if the
    * column is peeled at q (its symbol is Y_q ^ G_q z), the unit vector if inactive. */
-  hb1 = malloc((size_t)n);
-  hb2 = malloc((size_t)n);
+  uint8_t *hb1 = sc_buf(sc, SC_HB1, (size_t)n, 0);
+  uint8_t *hb2 = sc_buf(sc, SC_HB2, (size_t)n, 0);
   for (int j = 0; j + 1 < n; j++) {
     uint32_t b1 = rqb_rand(rqb_rand_v, (uint32_t)j + 1, 6, (uint32_t)H);
     uint32_t b2 = (b1 + rqb_rand(rqb_rand_v, (uint32_t)j + 1, 7, (uint32_t)H - 1) + 1) % (uint32_t)H;
     hb1[j] = (uint8_t)b1;
     hb2[j] = (uint8_t)b2;
   }
+  hb1[n - 1] = hb2[n - 1] = 0;
   const int uq = uw * 8; /* u64 words per byte-row of padded width 64*uw */
-  Sh = calloc((size_t)H * (size_t)uq * 8, 1);
-  ybuf = calloc((size_t)uq, 8);
-  accbuf = calloc((size_t)H * (size_t)uq, 8);
+  uint8_t *Sh = sc_buf(sc, SC_SH, (size_t)H * (size_t)uq * 8, 1);
+  uint64_t *ybuf = sc_buf(sc, SC_YBUF, (size_t)uq * 8, 1);
+  uint64_t *accbuf = sc_buf(sc, SC_ACCBUF, (size_t)H * (size_t)uq * 8, 1);
   {
     for (int j = 0; j < n; j++) {
       for (int k = 0; k < uq; k++) ybuf[k] = xtime8(ybuf[k]);
@@ -538,9 +690,9 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   }
 
   /* ---- 3d. Gauss-Jordan over GF(2) on the binary Schur rows, transformation tracked */
-  pivrow = malloc(sizeof(int) * (size_t)(U ? U : 1));       /* column t -> local row or -1 */
-  pivcol_of_row = malloc(sizeof(int) * (size_t)(nb ? nb : 1));
-  freecols = malloc(sizeof(int) * (size_t)(U ? U : 1));
+  int *pivrow = sc_buf(sc, SC_PIVROW, sizeof(int) * (size_t)(U ? U : 1), 0); /* column t -> local row or -1 */
+  int *pivcol_of_row = sc_buf(sc, SC_PIVCOL, sizeof(int) * (size_t)(nb ? nb : 1), 0);
+  int *freecols = sc_buf(sc, SC_FREECOLS, sizeof(int) * (size_t)(U ? U : 1), 0);
   int rho = 0, nfree = 0;
   for (int m = 0; m < nb; m++) pivcol_of_row[m] = -1;
   for (int t = 0; t < U; t++) {
@@ -553,6 +705,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     pivrow[t] = pr;
     if (pr < 0) {
       freecols[nfree++] = t;
+      if (nfree > H) return 1;
       continue;
     }
     pivcol_of_row[pr] = t;
@@ -564,14 +717,10 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
         bits_xor(Tb + (size_t)m * nbw, pt, nbw);
       }
   }
-  if (nfree > H) {
-    rc = 1;
-    goto fail;
-  }
   /* ---- 3e. HDPC rows: eliminate pivot columns (beta = Sh[h][t]), then solve the
    *          H x nfree system Q over GF(256) with a tracked transformation TQ (H x H) */
-  Q = calloc((size_t)H * (size_t)(nfree ? nfree : 1), 1);
-  TQ = calloc((size_t)H * (size_t)H, 1);
+  uint8_t *Q = sc_buf(sc, SC_Q, (size_t)H * (size_t)(nfree ? nfree : 1), 1);
+  uint8_t *TQ = sc_buf(sc, SC_TQ, (size_t)H * (size_t)H, 1);
   for (int h = 0; h < H; h++) {
     const uint8_t *row = Sh + (size_t)h * (size_t)uq * 8;
     for (int f = 0; f < nfree; f++) Q[h * nfree + f] = row[freecols[f]];
@@ -584,9 +733,9 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
     TQ[h * H + h] = 1;
   }
-  int qrow_of_f[16];
+  int qrow_of_f[RQB_MAX_H];
   {
-    uint8_t used[16] = {0};
+    uint8_t used[RQB_MAX_H] = {0};
     for (int f = 0; f < nfree; f++) {
       int pr = -1;
       for (int h = 0; h < H; h++)
@@ -594,10 +743,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
           pr = h;
           break;
         }
-      if (pr < 0) {
-        rc = 1; /* rank(A) < L */
-        goto fail;
-      }
+      if (pr < 0) return 1; /* rank(A) < L */
       used[pr] = 1;
       qrow_of_f[f] = pr;
       uint8_t inv = GF.inv[Q[pr * nfree + f]];
@@ -613,194 +759,237 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   }
   double t3 = now_s();
 
-  /* ---- 4. emit the program.  Slots: matrix row r -> slot r; scratch after R. */
-  const int NC = (n + 1023) / 1024 > 32 ? (n + 1023) / 1024 : (n < 64 ? 1 : 32); /* HORNER chunks */
-  const uint32_t RP = (uint32_t)R;                 /* r'_t, one per pivot column (indexed by t) */
-  const uint32_t Z = RP + (uint32_t)U;             /* z_t                                         */
-  const uint32_t HS = Z + (uint32_t)U;             /* HORNER scratch: NC * (H+1)                  */
-  const uint32_t PS = HS + (uint32_t)NC * (uint32_t)(H + 1); /* GF partial sums               */
-  const int GFCH = 8;                              /* GF sources per partial task               */
-  const int parts_per_h = (rho + NC + GFCH - 1) / GFCH + 1;
-  const uint32_t n_slots = PS + (uint32_t)H * (uint32_t)parts_per_h;
-  if (n_slots > RQB_MAX_SLOTS) {
-    rc = -4;
-    goto fail;
-  }
-  size_t tmpcap = (size_t)(I > U ? I : U) + (size_t)nb + (size_t)n + 4096;
-  tmp16 = malloc(sizeof(uint16_t) * tmpcap);
-  tmp32 = malloc(sizeof(uint32_t) * tmpcap);
-
-  /* counting sort of peeled positions by level */
-  const int nlev = maxlevel + 1;
-  lvl_cnt = calloc((size_t)nlev + 2, sizeof(int));
-  lvl_ord = malloc(sizeof(int) * (size_t)(I ? I : 1));
-  for (int p = 0; p < I; p++) lvl_cnt[level[p] + 1]++;
-  for (int l = 0; l < nlev; l++) lvl_cnt[l + 1] += lvl_cnt[l];
-  {
-    int *cur = malloc(sizeof(int) * ((size_t)nlev + 1));
-    memcpy(cur, lvl_cnt, sizeof(int) * ((size_t)nlev + 1));
-    for (int p = 0; p < I; p++) lvl_ord[cur[level[p]]++] = p;
-    free(cur);
-  }
-
-  /* A: forward substitution Y = X^-1 b_top (level 0 rows have no sources: nothing to do) */
-  for (int l = 1; l < nlev; l++) {
-    for (int k = lvl_cnt[l]; k < lvl_cnt[l + 1]; k++) {
-      int p = lvl_ord[k], ns = 0;
-      for (int e = dptr[p]; e < dptr[p + 1]; e++) tmp16[ns++] = (uint16_t)prow[didx[e]];
-      pb_task(&pb, RQB_T_XOR_ACC, (uint32_t)prow[p], 0, (uint32_t)ns, tmp16, 2);
+  /* ---- 4. emit the program.
+   * Working rows: matrix row r -> WS row r; then r'_t (RP+t), z_t (Z+t), the scan
+   * rows y_j, one row per part, then whatever the reduction trees need.
+   * loc[s] = where the CURRENT value of working row s lives (an input row until
+   * the first task writes it; NONE = known zero: nothing to read). */
+  int NC = n / 32; /* scan chunks: ~32 entries each, few enough that combining them stays cheap */
+  if (NC < 1) NC = 1;
+  if (NC > 512) NC = 512;
+  const uint32_t RP = (uint32_t)R;
+  const uint32_t Z = RP + (uint32_t)U;
+  const uint32_t YS = Z + (uint32_t)U;        /* y_j of the chunk-local alpha-scans, one row per column j < n */
+  const uint32_t PT = YS + (uint32_t)n;
+  const uint32_t WS_FIXED = PT + (uint32_t)nparts;
+  if ((uint64_t)WS_FIXED + (uint64_t)nnz > RQB_MAX_ROWS) return -4;
+  builder bd;
+  memset(&bd, 0, sizeof(bd));
+  bd.sc = sc;
+  bd.ws_next = WS_FIXED;
+  uint32_t *loc = sc_buf(sc, SC_CURLOC, sizeof(uint32_t) * (size_t)WS_FIXED, 0);
+  for (uint32_t s = 0; s < WS_FIXED; s++) loc[s] = NONE_REF;
+  for (int k = 0; k < nlt; k++)
+    if (req->in_row[k] != RQB_ROW_NONE) {
+      if (req->in_row[k] >= RQB_MAX_ROWS) return -1;
+      loc[S + H + k] = RQB_REF(RQB_SP_IN, req->in_row[k]);
     }
-    pb_level_end(&pb);
-  }
-  /* B: residual rows r_m ^= X_low*Y ; HDPC rows through NC chunk scans over columns 0..n-1 */
+  uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)n + (size_t)NC + 4096), 0);
+#define WSREF(s) RQB_REF(RQB_SP_WS, (s))
+#define PUSH(ns, ref)                                  \
+  do {                                                 \
+    uint32_t _r = (ref);                               \
+    if (_r != NONE_REF) tmp[(ns)++] = RQB_SRC(_r, 1);  \
+  } while (0)
+
+  /* the triangular solve (phases A and E): levels base+1 .. base+maxlevel */
+#define TRIANGULAR(base)                                                                        \
+  do {                                                                                          \
+    for (int p = 0; p < I; p++) {                                                               \
+      for (int k = pfirst[p]; k < pfirst[p + 1]; k++) {                                         \
+        uint32_t ns = 0;                                                                        \
+        for (int e = pptr[k]; e < pptr[k + 1]; e++)                                             \
+          PUSH(ns, pitems[e] >= 0 ? loc[prow[pitems[e]]] : loc[PT + (uint32_t)(-1 - pitems[e])]); \
+        b_task(&bd, RQB_T_XOR, WSREF(PT + (uint32_t)k), 0, (base) + (uint32_t)plevel[k], tmp, ns); \
+        loc[PT + (uint32_t)k] = WSREF(PT + (uint32_t)k);                                        \
+      }                                                                                         \
+      if (level[p] == 0) continue;                                                              \
+      uint32_t ns = 0;                                                                          \
+      PUSH(ns, loc[prow[p]]);                                                                   \
+      for (int e = fptr[p]; e < fptr[p + 1]; e++)                                               \
+        PUSH(ns, fitems[e] >= 0 ? loc[prow[fitems[e]]] : loc[PT + (uint32_t)(-1 - fitems[e])]); \
+      b_task(&bd, RQB_T_XOR, WSREF(prow[p]), 0, (base) + (uint32_t)level[p], tmp, ns);          \
+      loc[prow[p]] = WSREF(prow[p]);                                                            \
+    }                                                                                           \
+  } while (0)
+
+  /* A: forward substitution Y = X^-1 b_top */
+  TRIANGULAR(0u);
+  uint32_t lv = (uint32_t)maxlevel + 1, end = lv;
+
+  /* B: residual rows r_m = b_m ^ X_low*Y ; HDPC rows through NC chunk scans over columns 0..n-1 */
   for (int m = 0; m < nb; m++) {
-    int ns = 0;
-    for (int e = xptr[m]; e < xptr[m + 1]; e++) tmp16[ns++] = (uint16_t)prow[xidx[e]];
-    if (ns) pb_task(&pb, RQB_T_XOR_ACC, (uint32_t)lowrows[m], 0, (uint32_t)ns, tmp16, 2);
+    uint32_t ns = 0;
+    if (xptr[m + 1] == xptr[m]) continue;
+    PUSH(ns, loc[lowrows[m]]);
+    for (int e = xptr[m]; e < xptr[m + 1]; e++) PUSH(ns, loc[prow[xidx[e]]]);
+    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(lowrows[m]), tmp, ns, lv);
+    loc[lowrows[m]] = WSREF(lowrows[m]);
+    if (e2 > end) end = e2;
   }
-  int *cs = malloc(sizeof(int) * ((size_t)NC + 1));
+  int *cs = sc_buf(sc, SC_CS, sizeof(int) * ((size_t)NC + 1), 0);
   for (int c = 0; c <= NC; c++) cs[c] = (int)((long)n * c / NC);
   for (int c = 0; c < NC; c++) {
-    int ns = 0;
+    uint32_t ns = 0;
     for (int j = cs[c]; j < cs[c + 1]; j++) {
-      uint32_t slot = col_state[j] == 1 ? (uint32_t)prow[col_pos[j]] : RQB_SLOT_NONE;
-      int fl = (j + 1 < n);
-      tmp32[ns++] = RQB_HORNER_ENTRY(slot, fl ? hb1[j] : 0, fl ? hb2[j] : 0, fl);
+      tmp[ns++] = col_state[j] == 1 ? loc[prow[col_pos[j]]] : NONE_REF;
+      loc[YS + (uint32_t)j] = WSREF(YS + (uint32_t)j);
     }
-    pb_task(&pb, RQB_T_HORNER, HS + (uint32_t)c * (uint32_t)(H + 1), (uint32_t)H, (uint32_t)ns, tmp32, 4);
+    b_task(&bd, RQB_T_SCAN, WSREF(YS + (uint32_t)cs[c]), 0, lv, tmp, ns);
   }
-  pb_level_end(&pb);
+  lv = end + 1;
+  end = lv;
 
-  /* C1: r'_t = XOR_{m in Tb[pivrow t]} r_m ; HDPC base r_h = XOR_c acc_c[h] */
+  /* C1: r'_t = XOR_{m in Tb[pivrow t]} r_m ; HDPC base r_h = XOR_{j <= n-2, h in b(j)} y_j (chunk-local y) */
   for (int t = 0; t < U; t++) {
     if (pivrow[t] < 0) continue;
     const uint64_t *tb = Tb + (size_t)pivrow[t] * nbw;
-    int ns = 0;
+    uint32_t ns = 0;
     for (int m = 0; m < nb; m++)
-      if (bit_get(tb, m)) tmp16[ns++] = (uint16_t)lowrows[m];
-    pb_task(&pb, RQB_T_XOR_SET, RP + (uint32_t)t, 0, (uint32_t)ns, tmp16, 2);
+      if (bit_get(tb, m)) PUSH(ns, loc[lowrows[m]]);
+    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(RP + (uint32_t)t), tmp, ns, lv);
+    loc[RP + (uint32_t)t] = WSREF(RP + (uint32_t)t);
+    if (e2 > end) end = e2;
   }
   for (int h = 0; h < H; h++) {
-    for (int c = 0; c < NC; c++) tmp16[c] = (uint16_t)(HS + (uint32_t)c * (uint32_t)(H + 1) + (uint32_t)h);
-    pb_task(&pb, RQB_T_XOR_SET, (uint32_t)(S + h), 0, (uint32_t)NC, tmp16, 2);
+    uint32_t ns = 0;
+    for (int j = 0; j + 1 < n; j++)
+      if (hb1[j] == h || hb2[j] == h) PUSH(ns, loc[YS + (uint32_t)j]);
+    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(S + h), tmp, ns, lv);
+    loc[S + h] = WSREF(S + h);
+    if (e2 > end) end = e2;
   }
-  pb_level_end(&pb);
+  lv = end + 1;
+  end = lv;
 
-  /* C2: r'_h = r_h ^ sum_c Gc[h][c]*yend_c ^ sum_t beta[h][t]*r'_t, as partial GF sums.
+  /* C2: r'_h = r_h ^ sum_c Gc[h][c]*yend_c ^ sum_t beta[h][t]*r'_t  (GF leaves, XOR tree).
    * Gc[h][c'] = alpha^h alpha^(n-e_c') ^ sum_{c>c'} coef[c][h] alpha^(s_c-e_c'),
    * coef[c][h] = sum_{j in chunk c, j<=n-2, h in b(j)} alpha^(j-s_c+1). */
   {
-    uint8_t *coef = calloc((size_t)NC * (size_t)H, 1);
+    uint8_t *coef = sc_buf(sc, SC_COEF, (size_t)NC * (size_t)H, 1);
     for (int c = 0; c < NC; c++)
       for (int j = cs[c]; j < cs[c + 1] && j + 1 < n; j++) {
         uint8_t a = rqb_gf_pow2(&GF, j - cs[c] + 1);
         coef[c * H + hb1[j]] ^= a;
         coef[c * H + hb2[j]] ^= a;
       }
+    /* suffix[h] = sum_{c > c1} coef[c][h] * alpha^(s_c - e_c1), built backwards in O(NC*H) */
+    uint8_t suf[RQB_MAX_H];
+    uint8_t *gc = sc_buf(sc, SC_CSLOT, (size_t)NC * (size_t)H + 64, 0);
+    memset(suf, 0, sizeof(suf));
+    for (int c1 = NC - 1; c1 >= 0; c1--) {
+      /* moving the reference point from e_{c1+1} (= s_{c1+2}) back to e_{c1} (= s_{c1+1}) multiplies by
+       * alpha^(len of chunk c1+1) and brings in chunk c1+1 itself with exponent 0 */
+      if (c1 + 1 < NC) {
+        uint8_t a = rqb_gf_pow2(&GF, cs[c1 + 2] - cs[c1 + 1]);
+        for (int h = 0; h < H; h++) suf[h] = rqb_gf_mul(&GF, suf[h], a) ^ coef[(c1 + 1) * H + h];
+      }
+      for (int h = 0; h < H; h++)
+        gc[c1 * H + h] = rqb_gf_mul(&GF, rqb_gf_pow2(&GF, h), rqb_gf_pow2(&GF, n - cs[c1 + 1])) ^ suf[h];
+    }
     for (int h = 0; h < H; h++) {
       const uint8_t *row = Sh + (size_t)h * (size_t)uq * 8;
-      int ns = 0;
+      uint32_t ns = 0;
       for (int c1 = 0; c1 < NC; c1++) {
-        uint8_t g = rqb_gf_mul(&GF, rqb_gf_pow2(&GF, h), rqb_gf_pow2(&GF, n - cs[c1 + 1]));
-        for (int c = c1 + 1; c < NC; c++)
-          g ^= rqb_gf_mul(&GF, coef[c * H + h], rqb_gf_pow2(&GF, cs[c] - cs[c1 + 1]));
-        if (g) tmp32[ns++] = (HS + (uint32_t)c1 * (uint32_t)(H + 1) + (uint32_t)H) | ((uint32_t)g << 16);
+        uint8_t g = gc[c1 * H + h];
+        uint32_t ref = loc[YS + (uint32_t)cs[c1 + 1] - 1]; /* y at the end of chunk c1 */
+        if (g && ref != NONE_REF) tmp[ns++] = RQB_SRC(ref, g);
       }
       for (int t = 0; t < U; t++)
-        if (pivrow[t] >= 0 && row[t]) tmp32[ns++] = (RP + (uint32_t)t) | ((uint32_t)row[t] << 16);
-      int part = 0;
-      for (int o = 0; o < ns; o += GFCH, part++) {
-        int cnt = ns - o < GFCH ? ns - o : GFCH;
-        pb_task(&pb, RQB_T_GF_SET, PS + (uint32_t)h * (uint32_t)parts_per_h + (uint32_t)part, 0,
-                (uint32_t)cnt, tmp32 + o, 4);
-      }
-      tmp16[h] = (uint16_t)part; /* remember the count for the combine level */
+        if (pivrow[t] >= 0 && row[t] && loc[RP + (uint32_t)t] != NONE_REF) tmp[ns++] = RQB_SRC(loc[RP + (uint32_t)t], row[t]);
+      if (loc[S + h] != NONE_REF) tmp[ns++] = RQB_SRC(loc[S + h], 1);
+      uint32_t e2 = b_tree(&bd, RQB_T_GF, WSREF(S + h), tmp, ns, lv);
+      loc[S + h] = WSREF(S + h);
+      if (e2 > end) end = e2;
     }
-    free(coef);
-    uint16_t nparts[16];
-    for (int h = 0; h < H; h++) nparts[h] = tmp16[h];
-    pb_level_end(&pb);
-    for (int h = 0; h < H; h++) {
-      for (int q = 0; q < nparts[h]; q++)
-        tmp16[q] = (uint16_t)(PS + (uint32_t)h * (uint32_t)parts_per_h + (uint32_t)q);
-      if (nparts[h]) pb_task(&pb, RQB_T_XOR_ACC, (uint32_t)(S + h), 0, nparts[h], tmp16, 2);
-    }
-    pb_level_end(&pb);
   }
+  lv = end + 1;
+  end = lv;
   /* C3: z_f = sum_h TQ[qrow(f)][h] * r'_h */
   for (int f = 0; f < nfree; f++) {
-    int ns = 0;
+    uint32_t ns = 0;
     for (int h = 0; h < H; h++) {
       uint8_t b = TQ[qrow_of_f[f] * H + h];
-      if (b) tmp32[ns++] = (uint32_t)(S + h) | ((uint32_t)b << 16);
+      if (b && loc[S + h] != NONE_REF) tmp[ns++] = RQB_SRC(loc[S + h], b);
     }
-    pb_task(&pb, RQB_T_GF_SET, Z + (uint32_t)freecols[f], 0, (uint32_t)ns, tmp32, 4);
+    uint32_t e2 = b_tree(&bd, RQB_T_GF, WSREF(Z + (uint32_t)freecols[f]), tmp, ns, lv);
+    loc[Z + (uint32_t)freecols[f]] = WSREF(Z + (uint32_t)freecols[f]);
+    if (e2 > end) end = e2;
   }
-  pb_level_end(&pb);
+  lv = end + 1;
+  end = lv;
   /* C4: z_t = r'_t ^ XOR_{f: bit} z_f for pivot columns */
   for (int t = 0; t < U; t++) {
     if (pivrow[t] < 0) continue;
     const uint64_t *ps = Sb + (size_t)pivrow[t] * uw;
-    int ns = 0;
-    tmp16[ns++] = (uint16_t)(RP + (uint32_t)t);
+    uint32_t ns = 0;
+    PUSH(ns, loc[RP + (uint32_t)t]);
     for (int f = 0; f < nfree; f++)
-      if (bit_get(ps, freecols[f])) tmp16[ns++] = (uint16_t)(Z + (uint32_t)freecols[f]);
-    pb_task(&pb, RQB_T_XOR_SET, Z + (uint32_t)t, 0, (uint32_t)ns, tmp16, 2);
+      if (bit_get(ps, freecols[f])) PUSH(ns, loc[Z + (uint32_t)freecols[f]]);
+    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(Z + (uint32_t)t), tmp, ns, lv);
+    loc[Z + (uint32_t)t] = WSREF(Z + (uint32_t)t);
+    if (e2 > end) end = e2;
   }
-  pb_level_end(&pb);
+  lv = end + 1;
+  end = lv;
 
-  /* load map (also used by D) */
-  plan = calloc(1, sizeof(*plan));
-  plan->load_src = malloc(sizeof(uint32_t) * n_slots);
-  for (uint32_t s = 0; s < n_slots; s++) plan->load_src[s] = RQB_ROW_NONE;
-  for (int k = 0; k < nlt; k++) plan->load_src[S + H + k] = req->in_row[k];
-
-  /* D: b_top' = b_top ^ U_top z   (b_top re-read from the input) */
+  /* D: b_top' = b_top ^ U_top z.  A row without inactive columns just goes back to
+   * its input row (no task); the others are rebuilt from the input row. */
   for (int p = 0; p < I; p++) {
-    int r = prow[p], ns = 0;
+    int r = prow[p];
+    uint32_t ns = 0;
+    uint32_t orig = r >= S + H ? (req->in_row[r - S - H] != RQB_ROW_NONE ? RQB_REF(RQB_SP_IN, req->in_row[r - S - H]) : NONE_REF)
+                               : NONE_REF;
     for (int k = rptr[r]; k < rptr[r + 1]; k++)
-      if (col_state[cidx[k]] == 2) tmp16[ns++] = (uint16_t)(Z + (uint32_t)col_t[cidx[k]]);
-    if (ns == 0 && dptr[p + 1] == dptr[p]) continue; /* x = b: the slot already holds it */
-    pb_task(&pb, RQB_T_LOAD_XOR, (uint32_t)r, plan->load_src[r], (uint32_t)ns, tmp16, 2);
-  }
-  pb_level_end(&pb);
-  /* E: x = X^-1 b_top' */
-  for (int l = 1; l < nlev; l++) {
-    for (int k = lvl_cnt[l]; k < lvl_cnt[l + 1]; k++) {
-      int p = lvl_ord[k], ns = 0;
-      for (int e = dptr[p]; e < dptr[p + 1]; e++) tmp16[ns++] = (uint16_t)prow[didx[e]];
-      pb_task(&pb, RQB_T_XOR_ACC, (uint32_t)prow[p], 0, (uint32_t)ns, tmp16, 2);
+      if (col_state[cidx[k]] == 2) PUSH(ns, loc[Z + (uint32_t)col_t[cidx[k]]]);
+    if (ns == 0) {
+      loc[r] = orig;
+      continue;
     }
-    pb_level_end(&pb);
+    PUSH(ns, orig);
+    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(r), tmp, ns, lv);
+    loc[r] = WSREF(r);
+    if (e2 > end) end = e2;
   }
-  /* O: outputs.  C[col] sits in the slot of the row that pivoted on col, or in z. */
-  cslot = malloc(sizeof(uint16_t) * (size_t)L);
-  for (int c = 0; c < L; c++)
-    cslot[c] = col_state[c] == 1 ? (uint16_t)prow[col_pos[c]] : (uint16_t)(Z + (uint32_t)col_t[c]);
+  /* E: x = X^-1 b_top' */
+  TRIANGULAR(end);
+  lv = end + (uint32_t)maxlevel + 1;
+  end = lv;
+
+  /* O: outputs.  C[col] sits in the row that pivoted on col, or in z. */
+  uint32_t *cloc = sc_buf(sc, SC_CSLOT, sizeof(uint32_t) * (size_t)L, 0);
+  for (int c = 0; c < L; c++) cloc[c] = col_state[c] == 1 ? loc[prow[col_pos[c]]] : loc[Z + (uint32_t)col_t[c]];
   if (req->want_c)
-    for (int c = 0; c < L; c++) pb_task(&pb, RQB_T_OUT_C, 0, (uint32_t)c, 1, &cslot[c], 2);
+    for (int c = 0; c < L; c++) {
+      uint32_t ns = 0;
+      PUSH(ns, cloc[c]);
+      b_task(&bd, RQB_T_XOR, RQB_REF(RQB_SP_C, c), 0, lv, tmp, ns);
+    }
   for (int k = 0; k < req->n_out; k++) {
     uint32_t idx[RQB_MAX_LT_DEGREE];
     int cnt = rqb_host_lt_indices(&P, req->out_isi[k], idx);
-    for (int q = 0; q < cnt; q++) tmp16[q] = cslot[idx[q]];
-    pb_task(&pb, RQB_T_OUT_SYM, 0, (uint32_t)k, (uint32_t)cnt, tmp16, 2);
+    uint32_t ns = 0;
+    for (int q = 0; q < cnt; q++) PUSH(ns, cloc[idx[q]]);
+    b_tree(&bd, RQB_T_XOR, RQB_REF(RQB_SP_SYM, k), tmp, ns, lv);
   }
-  pb_level_end(&pb);
-  pb_close_page(&pb);
-  free(cs);
-  if (pb.error) {
-    rc = -5;
-    goto fail;
+#undef PUSH
+#undef WSREF
+#undef TRIANGULAR
+  if (bd.ws_next > RQB_MAX_ROWS) return -4;
+
+  rqb_plan *plan = plan_acquire();
+  size_t tot_levels = 0;
+  rc = write_pages(&bd, plan, &tot_levels);
+  if (rc) {
+    rqb_plan_free(plan);
+    return rc;
   }
   double t4 = now_s();
 
   plan->P = P;
   plan->K = req->K;
   plan->overhead = oh;
-  plan->n_slots = n_slots;
-  plan->n_pages = (uint32_t)pb.npages;
-  plan->pages = pb.pages;
-  pb.pages = NULL;
+  plan->n_ws_rows = bd.ws_next;
   plan->n_c_rows = req->want_c ? (uint32_t)L : 0;
   plan->n_out = (uint32_t)req->n_out;
   plan->st.i = I;
@@ -808,35 +997,19 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   plan->st.nb = nb;
   plan->st.rho = rho;
   plan->st.nfree = nfree;
-  plan->st.levels_fwd = nlev;
-  plan->st.n_levels = (int)pb.tot_levels;
-  plan->st.n_tasks = (int)pb.tot_tasks;
-  plan->st.n_pages = (int)pb.npages;
-  plan->st.n_srcs = pb.tot_srcs;
-  plan->st.n_gf_srcs = pb.tot_gf;
-  plan->st.n_horner = pb.tot_horner;
+  plan->st.levels_fwd = maxlevel + 1;
+  plan->st.n_parts = nparts;
+  plan->st.n_levels = (int)tot_levels;
+  plan->st.n_tasks = (int)bd.nt;
+  plan->st.n_pages = (int)plan->n_pages;
+  plan->st.n_srcs = bd.tot_x;
+  plan->st.n_gf_srcs = bd.tot_gf;
+  plan->st.n_horner = bd.tot_h;
   plan->st.nnz = (size_t)nnz;
   plan->st.t_matrix = t1 - t0;
   plan->st.t_peel = t2 - t1;
   plan->st.t_dense = t3 - t2;
   plan->st.t_emit = t4 - t3;
-  FREE_ALL();
   *out = plan;
   return 0;
-
-fail:
-  if (plan) {
-    free(plan->load_src);
-    free(plan);
-  }
-  free(pb.pages);
-  FREE_ALL();
-  return rc;
-}
-
-void rqb_plan_free(rqb_plan *p) {
-  if (!p) return;
-  free(p->load_src);
-  free(p->pages);
-  free(p);
 }

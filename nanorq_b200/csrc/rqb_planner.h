@@ -22,7 +22,7 @@ typedef struct {
   int K;                   /* source symbols of the block (selects K')                      */
   int overhead;            /* LT rows beyond K' (received repair symbols - missing symbols) */
   const uint32_t *isi;     /* [K'+overhead] internal symbol id of the LT row k              */
-  const uint32_t *in_row;  /* [K'+overhead] input (staging) row with that symbol's bytes,   */
+  const uint32_t *in_row;  /* [K'+overhead] input row (RQB_SP_IN) with that symbol's bytes, */
                            /*               RQB_ROW_NONE for an all-zero symbol (padding)   */
   int want_c;              /* emit all L intermediate symbols to c_out (row = index)        */
   int n_out;               /* encoding symbols to emit to sym_out (row k = out_isi[k])      */
@@ -33,6 +33,7 @@ typedef struct {
   int i, u;            /* peeled rows / inactivated columns (cf. schedule.i, .u)   */
   int nb, rho, nfree;  /* binary residual rows, their GF(2) rank, columns left for HDPC */
   int levels_fwd;      /* dependency depth of the sparse triangular solve          */
+  int n_parts;         /* partial sums that keep long rows off the critical path   */
   int n_levels, n_tasks, n_pages;
   size_t n_srcs, n_gf_srcs, n_horner;
   size_t nnz;
@@ -42,10 +43,11 @@ typedef struct {
 typedef struct rqb_plan {
   rqb_params P;
   int K, overhead;
-  uint32_t n_slots;    /* shared-memory rows per CTA                           */
-  uint32_t *load_src;  /* [n_slots] input row loaded into the slot, or ROW_NONE */
+  uint32_t n_ws_rows;  /* working rows (RQB_SP_WS) the program uses             */
   uint32_t n_pages;
   uint8_t *pages;      /* n_pages * RQB_PAGE_BYTES                              */
+  size_t pages_cap;    /* bytes allocated behind pages (plans are recycled)     */
+  struct rqb_plan *next_free;
   uint32_t n_c_rows;   /* rows written to c_out (L or 0)                        */
   uint32_t n_out;
   rqb_plan_stats st;

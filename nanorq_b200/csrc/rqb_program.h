@@ -1,21 +1,26 @@
 /* rqb_program.h -- the "solve program": what the host planner hands the device.
  *
- * A source block's symbol matrix is processed by CTAs that each own a w-byte
- * column slice of EVERY row in shared memory ("slots").  Row operations are
- * column-local (reference: deps/oblas/oblas_avx.c:62-73 works byte by byte), so
- * every CTA replays the same program on its own slice with no inter-CTA traffic.
+ * All rows of a source block (received symbols, working rows, intermediate
+ * symbols, emitted symbols) live in HBM, row-major, one pitch.  Row operations
+ * are column-local (reference: deps/oblas/oblas_avx.c:62-73 works byte by byte),
+ * so the block is cut into column slices of RQB_SLICE_BYTES and every CTA
+ * replays the same program on its own slice with no inter-CTA traffic; its
+ * working set (slice width x rows) is what stays hot in L1/L2.
  *
  * The program is a linear stream of fixed-size PAGES (staged into shared memory
  * by TMA bulk copies, see rqb_device.cu).  A page holds whole LEVELS; all tasks
  * of one level are independent, levels are separated by a CTA barrier.  A TASK
- * computes one destination row as a gather over source slots:
+ * computes one destination row as a gather over at most RQB_MAX_SRCS source rows:
  *
- *     dst (=|^=)  [in[arg]] ^ XOR_k  beta_k * ws[src_k]
+ *     row[dst] = XOR_k  beta_k * row[src_k]
  *
  * which subsumes the reference's oaddrow/oaxpy/oscal sequences
  * (lib/precode.c:15-32) merged per destination, the final row permutation
- * (lib/precode.c:3-13,379-389: expressed as OUT tasks) and the LT combine
- * (decode_row, lib/nanorq.c:184-204: an OUT task with several sources).
+ * (lib/precode.c:3-13,379-389: a copy into the C space) and the LT combine
+ * (decode_row, lib/nanorq.c:184-204: a gather into the SYM space).
+ * A destination that accumulates lists its own previous location as a source.
+ *
+ * Row references are 24 bits: space (2) | index (22).
  */
 #ifndef RQB_PROGRAM_H
 #define RQB_PROGRAM_H
@@ -23,41 +28,48 @@
 #include <stdint.h>
 
 #define RQB_PAGE_BYTES 8192u /* multiple of 16 (TMA bulk copy granularity) */
-#define RQB_SLOT_NONE 0xFFFFu
+#define RQB_SLICE_BYTES 128u /* column slice per CTA: one cache line per (task, source) */
+#define RQB_MAX_SRCS 8u      /* sources per XOR/GF task (the kernel keeps them all in flight) */
 #define RQB_ROW_NONE 0xFFFFFFFFu
-#define RQB_MAX_SLOTS 65535u
+
+enum rqb_space {
+  RQB_SP_IN = 0,  /* received / source symbols as uploaded (read-only)      */
+  RQB_SP_WS = 1,  /* working rows                                           */
+  RQB_SP_C = 2,   /* intermediate symbols C[0..L) in RFC order              */
+  RQB_SP_SYM = 3  /* emitted symbols (repair symbols / recovered symbols)   */
+};
+#define RQB_IDX_BITS 22u
+#define RQB_MAX_ROWS (1u << RQB_IDX_BITS)
+#define RQB_REF(space, idx) (((uint32_t)(space) << RQB_IDX_BITS) | (uint32_t)(idx))
+#define RQB_REF_MASK 0x00FFFFFFu
+#define RQB_REF_NONE 0x00FFFFFFu /* SCAN: "no row here" */
+/* XOR / GF source: ref | beta << 24 (beta is 1 for XOR tasks) */
+#define RQB_SRC(ref, beta) ((uint32_t)(ref) | ((uint32_t)(beta) << 24))
 
 enum rqb_task_kind {
-  RQB_T_XOR_SET = 0,  /* ws[dst]  = XOR ws[src]                      srcs: u16          */
-  RQB_T_XOR_ACC = 1,  /* ws[dst] ^= XOR ws[src]                      srcs: u16          */
-  RQB_T_GF_SET = 2,   /* ws[dst]  = XOR beta*ws[src]                 srcs: u32 slot|beta<<16 */
-  RQB_T_GF_ACC = 3,   /* ws[dst] ^= XOR beta*ws[src]                 srcs: u32          */
-  RQB_T_LOAD_XOR = 4, /* ws[dst]  = in[arg] ^ XOR ws[src]  (arg may be RQB_ROW_NONE)   */
-  RQB_T_OUT_C = 5,    /* c_out[arg]   = XOR ws[src]                  srcs: u16          */
-  RQB_T_OUT_SYM = 6,  /* sym_out[arg] = XOR ws[src]                  srcs: u16          */
-  RQB_T_HORNER = 7    /* HDPC chunk scan, see below                  srcs: u32          */
+  RQB_T_XOR = 0, /* row[dst] = XOR row[src_k]              nsrc <= RQB_MAX_SRCS (0 => zero row) */
+  RQB_T_GF = 1,  /* row[dst] = XOR beta_k * row[src_k]     nsrc <= RQB_MAX_SRCS                 */
+  RQB_T_SCAN = 2 /* alpha-scan over nsrc entries, see below                                    */
 };
 
-/* HORNER (restates the structure of precode_matrix_make_HDPC, lib/precode.c:60-83:
- * column j = alpha * column j+1 plus two ones).  For the entries e_0..e_{n-1}:
- *     y = alpha*y ^ ws[slot(e)]   (slot NONE => just y = alpha*y)
- *     if (flag(e)) { acc[b1(e)] ^= y; acc[b2(e)] ^= y; }
- * acc[h] lives in ws[dst+h], h < arg (=H); the final y goes to ws[dst+arg].
- * entry = slot | b1<<16 | b2<<20 | flag<<24. */
-#define RQB_HORNER_ENTRY(slot, b1, b2, flag) \
-  ((uint32_t)(slot) | ((uint32_t)(b1) << 16) | ((uint32_t)(b2) << 20) | ((uint32_t)(flag) << 24))
+/* SCAN (restates the structure of precode_matrix_make_HDPC, lib/precode.c:60-83:
+ * column j = alpha * column j+1 plus two ones, i.e. HDPC*C is a Horner scheme
+ * in alpha).  For the entries e_0..e_{n-1}, starting from y = 0:
+ *     y = alpha*y ^ row[ref(e_k)]      (ref NONE => just y = alpha*y)
+ *     WS row idx(dst)+k = y
+ * The HDPC rows are then ordinary XOR/GF gathers over the y rows. */
 
 typedef struct {
-  uint32_t src_off; /* byte offset of the source list from the page start */
-  uint32_t arg;     /* in row / out row / H, by kind                      */
+  uint32_t src_off; /* byte offset of the source list from the page start (16-byte aligned) */
+  uint32_t dst;     /* row reference                                                        */
   uint16_t nsrc;
-  uint16_t dst;
   uint8_t kind;
-  uint8_t pad[3];
+  uint8_t aux;
+  uint32_t pad;
 } rqb_task; /* 16 bytes: one 128-bit shared-memory load */
 
 /* page := rqb_page_hdr, then levels back to back (each 16-byte aligned)
- * level := rqb_level_hdr, rqb_task[n_tasks], source lists                */
+ * level := rqb_level_hdr, rqb_task[n_tasks], source lists (u32, each list 16-byte aligned) */
 typedef struct {
   uint32_t n_levels;
   uint32_t pad[3];
@@ -68,5 +80,7 @@ typedef struct {
   uint32_t next_off; /* byte offset (from page start) of the next level */
   uint32_t pad[2];
 } rqb_level_hdr;
+
+#define RQB_MAX_H 16u /* HDPC rows, RFC 6330 table 2: H <= 16 */
 
 #endif

@@ -121,7 +121,6 @@ typedef struct enc_plan {
   uint32_t n_out;
   rqb_plan *plan;
   uint8_t *d_pages;
-  uint32_t *d_load;
   struct enc_plan *next;
 } enc_plan;
 static enc_plan *g_enc_plans;
@@ -135,16 +134,15 @@ struct rqb_solver {
   uint32_t max_in, max_out;
   void *stream, *ev0, *ev1, *ev2, *ev3;
   uint8_t *h_in, *d_in, *d_c, *d_sym, *h_sym;
+  uint8_t *d_ws; /* working rows of the current program (grown on demand) */
+  size_t d_ws_cap;
   uint32_t *d_isi, *h_isi;
   /* current program */
   rqb_plan *plan; /* owned unless shared */
-  int plan_shared, has_c, vec_bytes, timed;
-  uint8_t *d_pages;
-  size_t d_pages_cap;
-  uint32_t *d_load;
-  size_t d_load_cap;
-  const uint8_t *cur_pages; /* device pointers actually used (own or cached) */
-  const uint32_t *cur_load;
+  int plan_shared, has_c, timed;
+  uint8_t *d_pages, *h_pages; /* device copy / pinned staging of the program pages */
+  size_t d_pages_cap, h_pages_cap;
+  const uint8_t *cur_pages; /* device pointer actually used (own or cached) */
   rqb_solve_args *h_args, *d_args; /* pinned / device, one entry (batch uses [n]) */
   uint32_t n_out_last;
 };
@@ -164,10 +162,11 @@ void rqb_solver_destroy(rqb_solver *s) {
   pool_put(s->d_sym, (size_t)s->max_out * s->pitch, 0);
   pool_put(s->h_sym, (size_t)s->max_out * s->pitch, 1);
   pool_put(s->d_isi, (size_t)s->max_out * 4, 0);
-  pool_put(s->h_isi, (size_t)s->max_out * 4, 1);
+  free(s->h_isi);
   pool_put(s->d_pages, s->d_pages_cap, 0);
-  pool_put(s->d_load, s->d_load_cap, 0);
-  pool_put(s->h_args, RQB_ARGS_BYTES, 1);
+  pool_put(s->h_pages, s->h_pages_cap, 1);
+  pool_put(s->d_ws, s->d_ws_cap, 0);
+  free(s->h_args);
   pool_put(s->d_args, RQB_ARGS_BYTES, 0);
   if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
   if (s->ev0) rqb_event_destroy(s->ev0);
@@ -215,8 +214,11 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   e = e ? e : pool_get((void **)&s->d_sym, (size_t)s->max_out * s->pitch, 0);
   e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->max_out * s->pitch, 1);
   e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->max_out * 4, 0);
-  e = e ? e : pool_get((void **)&s->h_isi, (size_t)s->max_out * 4, 1);
-  e = e ? e : pool_get((void **)&s->h_args, RQB_ARGS_BYTES, 1);
+  /* small control blocks are sent from PAGEABLE memory on purpose: cudaMemcpyAsync
+   * stages a pageable source before it returns, so these buffers may be rewritten
+   * for the next launch while earlier copies are still queued on the stream */
+  s->h_isi = malloc((size_t)s->max_out * 4);
+  s->h_args = calloc(1, RQB_ARGS_BYTES);
   e = e ? e : pool_get((void **)&s->d_args, RQB_ARGS_BYTES, 0);
   if (e) {
     dev_fail(e, "rqb_solver_create allocation");
@@ -240,40 +242,51 @@ int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
   return 0;
 }
 
-static void fill_stats(const rqb_plan *p, int vec, rqb_solver_stats *o) {
+static void fill_stats(const rqb_plan *p, rqb_solver_stats *o) {
   memset(o, 0, sizeof(*o));
   o->i = p->st.i; o->u = p->st.u; o->nb = p->st.nb; o->rho = p->st.rho; o->nfree = p->st.nfree;
   o->levels_fwd = p->st.levels_fwd; o->n_levels = p->st.n_levels; o->n_tasks = p->st.n_tasks;
   o->n_pages = p->st.n_pages; o->n_srcs = p->st.n_srcs; o->n_gf_srcs = p->st.n_gf_srcs;
   o->n_horner = p->st.n_horner; o->nnz = p->st.nnz; o->t_matrix = p->st.t_matrix;
   o->t_peel = p->st.t_peel; o->t_dense = p->st.t_dense; o->t_emit = p->st.t_emit;
-  o->n_slots = p->n_slots;
-  o->vec_bytes = vec;
+  o->n_ws_rows = p->n_ws_rows;
+  o->n_parts = p->st.n_parts;
+  o->slice_bytes = RQB_SLICE_BYTES;
 }
 
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out) {
   if (!s->plan) return RQB_E_ARG;
-  fill_stats(s->plan, s->vec_bytes, out);
+  fill_stats(s->plan, out);
+  return 0;
+}
+
+/* make room for the program's working rows; buffers are only handed back to the
+ * pool once nothing queued on the stream can still touch them */
+static int ensure_cap(rqb_solver *s, void **buf, size_t *cap, size_t need, int pinned) {
+  if (need <= *cap) return 0;
+  if (*buf) {
+    DEV(rqb_stream_sync(s->stream));
+    pool_put(*buf, *cap, pinned);
+    *buf = NULL;
+    *cap = 0;
+  }
+  DEV(pool_get(buf, need, pinned));
+  *cap = pool_class(need);
   return 0;
 }
 
 static int solver_set_args(rqb_solver *s) {
   const rqb_plan *p = s->plan;
-  s->vec_bytes = rqb_solve_pick_vec(p->n_slots);
-  if (!s->vec_bytes) {
-    snprintf(g_err, sizeof(g_err), "block needs %u shared-memory rows: too large for the column-sliced solver",
-             p->n_slots);
-    return RQB_E_TOOBIG;
-  }
+  int rc = ensure_cap(s, (void **)&s->d_ws, &s->d_ws_cap, (size_t)p->n_ws_rows * s->pitch, 0);
+  if (rc) return rc;
   rqb_solve_args *a = s->h_args;
   memset(a, 0, sizeof(*a));
-  a->in = s->d_in;
-  a->c_out = s->d_c;
-  a->sym_out = s->d_sym;
-  a->load_src = s->cur_load;
+  a->base[RQB_SP_IN] = s->d_in;
+  a->base[RQB_SP_WS] = s->d_ws;
+  a->base[RQB_SP_C] = s->d_c;
+  a->base[RQB_SP_SYM] = s->d_sym;
   a->pages = s->cur_pages;
-  a->in_pitch = a->c_pitch = a->sym_pitch = (uint32_t)s->pitch;
-  a->n_slots = p->n_slots;
+  a->pitch = (uint32_t)s->pitch;
   a->n_pages = p->n_pages;
   a->width = (uint32_t)round_up(s->T, 16);
   DEV(rqb_copy_h2d(s->d_args, s->h_args, sizeof(*a), s->stream));
@@ -303,26 +316,16 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
   s->plan = p;
   s->plan_shared = 0;
-  size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES, lb = (size_t)p->n_slots * 4;
-  if (pb > s->d_pages_cap) {
-    pool_put(s->d_pages, s->d_pages_cap, 0);
-    s->d_pages = NULL;
-    s->d_pages_cap = 0;
-    DEV(pool_get((void **)&s->d_pages, pb, 0));
-    s->d_pages_cap = pb;
-  }
-  if (lb > s->d_load_cap) {
-    pool_put(s->d_load, s->d_load_cap, 0);
-    s->d_load = NULL;
-    s->d_load_cap = 0;
-    DEV(pool_get((void **)&s->d_load, lb, 0));
-    s->d_load_cap = lb;
-  }
-  /* the plan's host arrays are pageable; the copies are small and stream-ordered */
-  DEV(rqb_copy_h2d(s->d_pages, p->pages, pb, s->stream));
-  DEV(rqb_copy_h2d(s->d_load, p->load_src, lb, s->stream));
+  size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
+  rc = ensure_cap(s, (void **)&s->d_pages, &s->d_pages_cap, pb, 0);
+  rc = rc ? rc : ensure_cap(s, (void **)&s->h_pages, &s->h_pages_cap, pb, 1);
+  if (rc) return rc;
+  /* the pages go through pinned memory so that the copy is truly asynchronous; the
+   * staging buffer may be rewritten by the next plan only after this copy has run */
+  DEV(rqb_stream_sync(s->stream));
+  memcpy(s->h_pages, p->pages, pb);
+  DEV(rqb_copy_h2d(s->d_pages, s->h_pages, pb, s->stream));
   s->cur_pages = s->d_pages;
-  s->cur_load = s->d_load;
   return solver_set_args(s);
 }
 
@@ -360,11 +363,9 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
     e->n_out = n_rep;
     e->dev = s->dev;
     e->plan = p;
-    size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES, lb = (size_t)p->n_slots * 4;
+    size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
     int de = rqb_dev_malloc((void **)&e->d_pages, pb);
-    de = de ? de : rqb_dev_malloc((void **)&e->d_load, lb);
     de = de ? de : rqb_copy_h2d(e->d_pages, p->pages, pb, s->stream);
-    de = de ? de : rqb_copy_h2d(e->d_load, p->load_src, lb, s->stream);
     de = de ? de : rqb_stream_sync(s->stream);
     if (de) {
       pthread_mutex_unlock(&g_plan_mu);
@@ -378,7 +379,6 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
   s->plan = e->plan;
   s->plan_shared = 1;
   s->cur_pages = e->d_pages;
-  s->cur_load = e->d_load;
   return solver_set_args(s);
 }
 
@@ -386,7 +386,7 @@ int rqb_solver_run(rqb_solver *s) {
   if (!s->plan) return RQB_E_ARG;
   BIND(s->dev);
   DEV(rqb_event_record(s->ev0, s->stream));
-  DEV(rqb_launch_solve(s->d_args, 1, s->plan->n_slots, s->h_args->width, s->vec_bytes, s->stream));
+  DEV(rqb_launch_solve(s->d_args, 1, s->h_args->width, s->stream));
   DEV(rqb_event_record(s->ev1, s->stream));
   s->timed = 1;
   return 0;
@@ -411,20 +411,16 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   if (n <= 0 || !own) return RQB_E_ARG;
   BIND(own->dev);
   if ((size_t)(n + 1) * sizeof(rqb_solve_args) > RQB_ARGS_BYTES) return RQB_E_ARG;
-  uint32_t max_slots = 0;
-  int vec = 16;
   /* entry 0 of the owner's buffer stays its own single-run argument block */
   rqb_solve_args *h = own->h_args + 1, *d = own->d_args + 1;
   for (int k = 0; k < n; k++) {
     if (!sv[k]->plan || sv[k]->T != own->T || sv[k]->dev != own->dev) return RQB_E_ARG;
     if (sv[k] != own) DEV(rqb_stream_sync(sv[k]->stream)); /* its uploads must have landed */
-    if (sv[k]->plan->n_slots > max_slots) max_slots = sv[k]->plan->n_slots;
-    if (sv[k]->vec_bytes < vec) vec = sv[k]->vec_bytes;
     h[k] = *sv[k]->h_args;
   }
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
   DEV(rqb_event_record(own->ev0, own->stream));
-  DEV(rqb_launch_solve(d, n, max_slots, h[0].width, vec, own->stream));
+  DEV(rqb_launch_solve(d, n, h[0].width, own->stream));
   DEV(rqb_event_record(own->ev1, own->stream));
   own->timed = 1;
   return 0;
@@ -490,15 +486,12 @@ int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out)
   memset(out, 0, sizeof(*out));
   if (rc == 1) return RQB_NEED_MORE;
   if (rc) return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
-  out->n_slots = p->n_slots;
+  out->n_ws_rows = p->n_ws_rows;
   out->n_pages = p->n_pages;
   out->page_bytes = RQB_PAGE_BYTES;
-  out->load_src = p->load_src;
   out->pages = p->pages;
   out->opaque = p;
-  int vec = 16;
-  while (vec >= 2 && (size_t)p->n_slots * (size_t)vec + 4 * RQB_PAGE_BYTES + 128 > 232448) vec >>= 1;
-  fill_stats(p, vec >= 2 ? vec : 0, &out->stats);
+  fill_stats(p, &out->stats);
   return 0;
 }
 

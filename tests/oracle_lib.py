@@ -122,17 +122,18 @@ _interp = None
 
 def interp_run(blob, inp, T, n_c, n_out):
     """Run a plan blob (nanorq_b200.plan_blob) on the CPU interpreter.
-    -> (rc, C[n_c,T], syms[n_out,T])"""
+    -> (rc, C[n_c,T], syms[n_out,T]); rc 10 = hazard inside a level, 12 = misaligned,
+    13 = more than RQB_MAX_SRCS sources in a task."""
     global _interp
     if _interp is None:
         _interp = C.CDLL(INTERP_SO)
-        _interp.rqb_interp_run.argtypes = [C.c_uint32, u32p, C.c_uint32, u8p, u8p, C.c_size_t, C.c_size_t,
-                                           u8p, C.c_size_t, u8p, C.c_size_t]
+        sz = C.c_size_t
+        _interp.rqb_interp_run.argtypes = [C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz, u8p, sz, sz, u8p, sz, sz]
     inp = np.ascontiguousarray(inp, dtype=np.uint8)
-    cout = np.zeros((max(n_c, 1), T), np.uint8)
-    sout = np.zeros((max(n_out, 1), T), np.uint8)
-    rc = _interp.rqb_interp_run(blob["n_slots"], ptr(blob["load_src"], u32p), blob["n_pages"], ptr(blob["pages"]),
-                                ptr(inp), inp.strides[0], T, ptr(cout), T, ptr(sout), T)
+    cout = np.full((max(n_c, 1), T), 0x5A, np.uint8)
+    sout = np.full((max(n_out, 1), T), 0x5A, np.uint8)
+    rc = _interp.rqb_interp_run(blob["n_ws_rows"], blob["n_pages"], ptr(blob["pages"]), ptr(inp), inp.shape[0],
+                                inp.strides[0], T, ptr(cout), cout.shape[0], T, ptr(sout), sout.shape[0], T)
     return rc, cout[:n_c], sout[:n_out]
 
 

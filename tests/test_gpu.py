@@ -221,6 +221,32 @@ def test_batched_blocks_single_launch():
         s.close()
 
 
+def test_back_to_back_batches_on_one_stream():
+    """Two batched launches queued without a sync in between (different block
+    sizes) must not share argument storage: regression for the bench step."""
+    T = 256
+    groups = []
+    for K, n in ((300, 5), (120, 7)):
+        g = []
+        for b in range(n):
+            src = np.random.default_rng(100 * K + b).integers(0, 256, (K, T), dtype=np.uint8)
+            s = nb.Solver(K, T)
+            s.staging[:K, :T] = src
+            s.upload(0, K)
+            s.plan_encode(True, 0)
+            g.append((s, orc_encode(K, T, src)[0]))
+        groups.append(g)
+    own = groups[0][0][0]
+    for _ in range(3):
+        for g in groups:
+            nb.Solver.run_batch([s for s, _ in g], own)
+    own.sync()
+    for g in groups:
+        for s, want in g:
+            assert np.array_equal(s.fetch_c(), want)
+            s.close()
+
+
 # ------------------------------------------------- reference-format replay
 @pytest.mark.parametrize("K,T", [(10, 64), (257, 48), (1024, 1280)])
 def test_schedule_replay_of_reference_format_schedule(K, T):

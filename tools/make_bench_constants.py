@@ -68,7 +68,7 @@ def main():
                         "n_scal": r[2], "solve_bytes": pitch * (3 * r[1] + 2 * r[2]), "lt_bytes": lt})
             print(name, "seed", seed, dec[-1], flush=True)
         # repair symbols an encoder emits for the same patterns: ESI K.. (ISI K'..)
-        lt_rep = [(lt_degree(p, p.Kprime + k) + 1) * T for k in range(max(d["lost"] + oh + d["extra"] for d in dec))]
+        lt_rep = [(lt_degree(p, p.Kprime + k) + 1) * T for k in range(max(1024, max(d["lost"] + oh + d["extra"] for d in dec)))]
         res[name] = {"K": K, "T": T, "loss": loss, "overhead": oh, "pitch": pitch, "L": p.L, "Kprime": p.Kprime,
                      "encode": enc, "decode": dec, "lt_repair_bytes_prefix": list(np.cumsum(lt_rep).tolist()),
                      "compulsory_bytes": {"encode": K * T + p.L * T, "decode_per_lost_symbol": T}}
