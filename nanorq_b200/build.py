@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
         s, o = os.path.join(CSRC, src), os.path.join(objdir, src + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", s, "-o", o] + inc
+            cmd = [NVCC] + ARCH + os.environ.get("RQB_NVCC_EXTRA", "").split() + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", s, "-o", o] + inc
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)

@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rfc6330_tables.h"
@@ -36,7 +37,10 @@ __constant__ uint32_t c_rand_v[4][256];
 __constant__ uint32_t c_degree_cdf[31];
 
 static constexpr int kSolveThreads = 256;
-static constexpr int kSolveMinCtas = 4;                        // CTAs per SM the register budget allows
+#ifndef RQB_SOLVE_MIN_CTAS
+#define RQB_SOLVE_MIN_CTAS 3
+#endif
+static constexpr int kSolveMinCtas = RQB_SOLVE_MIN_CTAS;       // CTAs per SM the register budget allows
 static constexpr int kLanesPerTask = RQB_SLICE_BYTES / 16;     // 8 lanes x 16 bytes
 static constexpr int kTaskGroups = kSolveThreads / kLanesPerTask;
 static constexpr int kRingStages = 4;
@@ -118,9 +122,58 @@ struct RowSpaces {
   __device__ __forceinline__ uint8_t *at(uint32_t ref) const {
     const uint32_t sp = (ref >> RQB_IDX_BITS) & 3u;
     uint8_t *lo = (sp & 1u) ? b1 : b0, *hi = (sp & 1u) ? b3 : b2;
-    return ((sp & 2u) ? hi : lo) + (size_t)(ref & (RQB_MAX_ROWS - 1u)) * pitch;
+    uint8_t *p = ((sp & 2u) ? hi : lo) + (size_t)(ref & (RQB_MAX_ROWS - 1u)) * pitch;
+    __builtin_assume(__isGlobal(p)); // LDG/STG instead of generic accesses
+    return p;
   }
 };
+
+// The two rare task kinds live out of line so that the XOR gather (the hot path)
+// gets the kernel's register budget to itself.
+// SCAN: y = alpha*y ^ row[e_k]; row[dst+k] = y.  Loads run four entries ahead of the chain.
+__device__ __noinline__ void task_scan(const RowSpaces R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
+  uint4 y = make_uint4(0, 0, 0, 0);
+  uint8_t *dp = R.at(dst);
+  for (uint32_t k0 = 0; k0 < nsrc; k0 += 4) {
+    const uint4 e = *reinterpret_cast<const uint4 *>(sp + k0);
+    const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+    uint4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      x[u] = make_uint4(0, 0, 0, 0);
+      if (k0 + u < nsrc && (ev[u] & RQB_REF_MASK) != RQB_REF_NONE)
+        x[u] = *reinterpret_cast<const uint4 *>(R.at(ev[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k0 + u < nsrc) {
+        y.x = xtime4(y.x) ^ x[u].x; y.y = xtime4(y.y) ^ x[u].y;
+        y.z = xtime4(y.z) ^ x[u].z; y.w = xtime4(y.w) ^ x[u].w;
+        *reinterpret_cast<uint4 *>(dp) = y;
+        dp += R.pitch;
+      }
+    }
+  }
+}
+// GF: row[dst] = XOR beta_k * row[src_k], nsrc <= 8; all loads first, then the multiplies.
+__device__ __noinline__ void task_gf(const RowSpaces R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
+  uint4 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    v[u] = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)u < nsrc) v[u] = *reinterpret_cast<const uint4 *>(R.at(sp[u]));
+  }
+  uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    if ((uint32_t)u < nsrc) {
+      const BetaPlanes bp = beta_planes(sp[u] >> 24);
+      acc.x ^= gfmul4(v[u].x, bp); acc.y ^= gfmul4(v[u].y, bp);
+      acc.z ^= gfmul4(v[u].z, bp); acc.w ^= gfmul4(v[u].w, bp);
+    }
+  }
+  *reinterpret_cast<uint4 *>(R.at(dst)) = acc;
+}
 
 __global__ void __launch_bounds__(kSolveThreads, kSolveMinCtas)
 rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
@@ -169,29 +222,9 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
           const uint32_t nsrc = th.z & 0xffffu, kind = (th.z >> 16) & 0xffu;
           const uint32_t *sp = reinterpret_cast<const uint32_t *>(page + th.x);
           if (kind == RQB_T_SCAN) {
-            // y = alpha*y ^ row[e_k]; row[dst+k] = y.  Loads run four entries ahead of the chain.
-            uint4 y = make_uint4(0, 0, 0, 0);
-            uint8_t *dp = R.at(th.y);
-            for (uint32_t k0 = 0; k0 < nsrc; k0 += 4) {
-              const uint4 e = *reinterpret_cast<const uint4 *>(sp + k0);
-              const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
-              uint4 x[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                x[u] = make_uint4(0, 0, 0, 0);
-                if (k0 + u < nsrc && (ev[u] & RQB_REF_MASK) != RQB_REF_NONE)
-                  x[u] = *reinterpret_cast<const uint4 *>(R.at(ev[u]));
-              }
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                if (k0 + u < nsrc) {
-                  y.x = xtime4(y.x) ^ x[u].x; y.y = xtime4(y.y) ^ x[u].y;
-                  y.z = xtime4(y.z) ^ x[u].z; y.w = xtime4(y.w) ^ x[u].w;
-                  *reinterpret_cast<uint4 *>(dp) = y;
-                  dp += R.pitch;
-                }
-              }
-            }
+            task_scan(R, sp, nsrc, th.y);
+          } else if (kind == RQB_T_GF) {
+            task_gf(R, sp, nsrc, th.y);
           } else {
             // up to RQB_MAX_SRCS row segments, all requested before the first is consumed
             const uint4 i0 = *reinterpret_cast<const uint4 *>(sp);
@@ -205,22 +238,8 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
               if ((uint32_t)u < nsrc) v[u] = *reinterpret_cast<const uint4 *>(R.at(id[u]));
             }
             uint4 acc = make_uint4(0, 0, 0, 0);
-            if (kind == RQB_T_XOR) {
 #pragma unroll
-              for (int u = 0; u < 8; u++) xor4(acc, v[u]);
-            } else {
-#pragma unroll 1
-              for (uint32_t u = 0; u < nsrc; u++) {
-                const BetaPlanes bp = beta_planes(sp[u] >> 24); // beta re-read from shared memory: no dynamic register index
-                // v[] is indexed dynamically here only through this select chain (keeps it in registers)
-                uint4 x = v[0];
-#pragma unroll
-                for (int w = 1; w < 8; w++)
-                  if (u == (uint32_t)w) x = v[w];
-                acc.x ^= gfmul4(x.x, bp); acc.y ^= gfmul4(x.y, bp);
-                acc.z ^= gfmul4(x.z, bp); acc.w ^= gfmul4(x.w, bp);
-              }
-            }
+            for (int u = 0; u < 8; u++) xor4(acc, v[u]);
             *reinterpret_cast<uint4 *>(R.at(th.y)) = acc;
           }
         }
@@ -378,7 +397,28 @@ int rqb_stream_create(void **s) {
   return 0;
 }
 int rqb_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
-int rqb_stream_sync(void *s) { CK(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
+// Waiting threads SLEEP instead of spinning (cudaStreamSynchronize spins by default):
+// the host side runs more worker threads than cores so that planning one block
+// overlaps the device work of another.  A per-thread, per-device blocking-sync
+// event is recorded behind the stream's work and waited on.
+int rqb_stream_sync(void *s) {
+  static thread_local cudaEvent_t ev[64];
+  static thread_local bool spin_checked = false, spin = false;
+  if (!spin_checked) {
+    const char *e = getenv("NANORQ_B200_SPIN_WAIT");
+    spin = e && e[0] == '1';
+    spin_checked = true;
+  }
+  int dev = 0;
+  if (spin || cudaGetDevice(&dev) != cudaSuccess || dev >= 64) {
+    CK(cudaStreamSynchronize((cudaStream_t)s));
+    return 0;
+  }
+  if (!ev[dev]) CK(cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming));
+  CK(cudaEventRecord(ev[dev], (cudaStream_t)s));
+  CK(cudaEventSynchronize(ev[dev]));
+  return 0;
+}
 int rqb_dev_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int rqb_copy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));

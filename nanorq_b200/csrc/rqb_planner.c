@@ -216,40 +216,6 @@ static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint3
   return level;
 }
 
-static int cmp_task_idx(const void *a, const void *b, void *ctx) {
-  const ptask *T = ctx;
-  const ptask *x = &T[*(const uint32_t *)a], *y = &T[*(const uint32_t *)b];
-  if (x->kind != y->kind) return (int)x->kind - (int)y->kind;
-  if (x->nsrc != y->nsrc) return (int)y->nsrc - (int)x->nsrc;
-  return (int)(*(const uint32_t *)a > *(const uint32_t *)b) - (int)(*(const uint32_t *)a < *(const uint32_t *)b);
-}
-
-/* insertion sort is enough: levels are small, and qsort_r is not portable C11 */
-static void sort_level(uint32_t *idx, size_t n, const ptask *T) {
-  if (n > 64) { /* shell sort for the few wide levels */
-    for (size_t gap = n / 2; gap > 0; gap /= 2)
-      for (size_t i = gap; i < n; i++) {
-        uint32_t v = idx[i];
-        size_t j = i;
-        while (j >= gap && cmp_task_idx(&idx[j - gap], &v, (void *)T) > 0) {
-          idx[j] = idx[j - gap];
-          j -= gap;
-        }
-        idx[j] = v;
-      }
-    return;
-  }
-  for (size_t i = 1; i < n; i++) {
-    uint32_t v = idx[i];
-    size_t j = i;
-    while (j > 0 && cmp_task_idx(&idx[j - 1], &v, (void *)T) > 0) {
-      idx[j] = idx[j - 1];
-      j--;
-    }
-    idx[j] = v;
-  }
-}
-
 static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + (((size_t)t->nsrc * 4 + 15) & ~(size_t)15); }
 
 /* pack the tasks, level by level, into pages (a level may be split over pages:
@@ -257,15 +223,15 @@ static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + (((size_t)t
 static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
   scratch_t *sc = b->sc;
   const uint32_t nl = b->max_level + 1;
-  uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nl + 2) * 4, 1);
+  /* one stable counting sort by (level, kind): tasks of a kind sit together inside a
+   * level so that the lanes of a warp follow the same path */
+  const uint32_t nkeys = nl * 3;
+  uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nkeys + 2) * 4, 1);
   uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
-  for (size_t k = 0; k < b->nt; k++) cnt[b->tasks[k].level + 1]++;
-  for (uint32_t l = 0; l < nl; l++) cnt[l + 1] += cnt[l];
-  { /* stable counting sort by level; cnt[l] is consumed as the cursor, restore afterwards */
-    for (size_t k = 0; k < b->nt; k++) order[cnt[b->tasks[k].level]++] = (uint32_t)k;
-    for (uint32_t l = nl; l > 0; l--) cnt[l] = cnt[l - 1];
-    cnt[0] = 0;
-  }
+  for (size_t k = 0; k < b->nt; k++) cnt[b->tasks[k].level * 3 + b->tasks[k].kind + 1]++;
+  for (uint32_t l = 0; l < nkeys; l++) cnt[l + 1] += cnt[l];
+  for (size_t k = 0; k < b->nt; k++) order[cnt[b->tasks[k].level * 3 + b->tasks[k].kind]++] = (uint32_t)k;
+  /* cnt[key] now holds the END of its bucket: level l spans [cnt[3l-1], cnt[3l+2]) */
   size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
   uint8_t *pages = plan->pages;
 #define OPEN_PAGE()                                                         \
@@ -285,9 +251,8 @@ static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
     cur = 0;                                                                                      \
   } while (0)
   for (uint32_t l = 0; l < nl; l++) {
-    size_t lo = cnt[l], hi = cnt[l + 1];
+    size_t lo = l ? cnt[3 * l - 1] : 0, hi = cnt[3 * l + 2];
     if (lo == hi) continue;
-    sort_level(order + lo, hi - lo, b->tasks);
     size_t idx = lo;
     while (idx < hi) {
       if (!cur) OPEN_PAGE();
@@ -569,16 +534,30 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
           int q = col_pos[c];
           if (q >= p) return -3; /* cannot happen: would contradict the peeling invariant */
           bits_xor(g, G + (size_t)q * uw, uw);
-          /* insert sorted by the level at which the term exists */
-          int lv = level[q], j = cnt++;
-          while (j > 0 && rd[j - 1] > lv) {
-            rd[j] = rd[j - 1];
-            it[j] = it[j - 1];
-            j--;
-          }
-          rd[j] = lv;
-          it[j] = q;
+          rd[cnt] = level[q];
+          it[cnt++] = q;
         }
+      }
+      if (cnt <= CAPF) { /* the common case: one task, only the latest term matters */
+        int mx = -1;
+        fptr[p] = nf;
+        for (int k = 0; k < cnt; k++) {
+          fitems[nf++] = it[k];
+          if (rd[k] > mx) mx = rd[k];
+        }
+        level[p] = mx + 1;
+        if (level[p] > maxlevel) maxlevel = level[p];
+        continue;
+      }
+      for (int a = 1; a < cnt; a++) { /* sort by the level at which the term exists */
+        int lv = rd[a], q = it[a], j = a;
+        while (j > 0 && rd[j - 1] > lv) {
+          rd[j] = rd[j - 1];
+          it[j] = it[j - 1];
+          j--;
+        }
+        rd[j] = lv;
+        it[j] = q;
       }
       int head = 0; /* items [head, cnt) are live, sorted by readiness */
       while (cnt - head > CAPF) {
@@ -784,7 +763,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       if (req->in_row[k] >= RQB_MAX_ROWS) return -1;
       loc[S + H + k] = RQB_REF(RQB_SP_IN, req->in_row[k]);
     }
-  uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)n + (size_t)NC + 4096), 0);
+  uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)4 * (size_t)n + (size_t)NC + 4096), 0);
 #define WSREF(s) RQB_REF(RQB_SP_WS, (s))
 #define PUSH(ns, ref)                                  \
   do {                                                 \
@@ -851,13 +830,28 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     loc[RP + (uint32_t)t] = WSREF(RP + (uint32_t)t);
     if (e2 > end) end = e2;
   }
-  for (int h = 0; h < H; h++) {
-    uint32_t ns = 0;
-    for (int j = 0; j + 1 < n; j++)
-      if (hb1[j] == h || hb2[j] == h) PUSH(ns, loc[YS + (uint32_t)j]);
-    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(S + h), tmp, ns, lv);
-    loc[S + h] = WSREF(S + h);
-    if (e2 > end) end = e2;
+  {
+    /* bucket the columns by HDPC row in one pass: hcnt[h] = start of row h's list in tmp2 */
+    uint32_t hcnt[RQB_MAX_H + 1];
+    memset(hcnt, 0, sizeof(hcnt));
+    for (int j = 0; j + 1 < n; j++) {
+      hcnt[hb1[j] + 1]++;
+      hcnt[hb2[j] + 1]++;
+    }
+    for (int h = 0; h < H; h++) hcnt[h + 1] += hcnt[h];
+    uint32_t *tmp2 = tmp + (size_t)2 * (size_t)n + 64; /* tmp holds more than 4n words */
+    uint32_t hcur[RQB_MAX_H];
+    memcpy(hcur, hcnt, sizeof(hcur));
+    for (int j = 0; j + 1 < n; j++) {
+      uint32_t src = RQB_SRC(loc[YS + (uint32_t)j], 1);
+      tmp2[hcur[hb1[j]]++] = src;
+      tmp2[hcur[hb2[j]]++] = src;
+    }
+    for (int h = 0; h < H; h++) {
+      uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(S + h), tmp2 + hcnt[h], hcnt[h + 1] - hcnt[h], lv);
+      loc[S + h] = WSREF(S + h);
+      if (e2 > end) end = e2;
+    }
   }
   lv = end + 1;
   end = lv;

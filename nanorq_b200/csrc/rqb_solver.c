@@ -289,6 +289,7 @@ static int solver_set_args(rqb_solver *s) {
   a->pitch = (uint32_t)s->pitch;
   a->n_pages = p->n_pages;
   a->width = (uint32_t)round_up(s->T, 16);
+  a->pad = s->max_in; /* rows of the input space */
   DEV(rqb_copy_h2d(s->d_args, s->h_args, sizeof(*a), s->stream));
   s->has_c = p->n_c_rows != 0;
   s->n_out_last = p->n_out;
