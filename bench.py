@@ -323,6 +323,7 @@ def run_own(args, rank, world, local_rank):
     for w in range(0 if args.skip_e2e else max(args.warmup, 3)):
         roundtrip(rt_so, min(NB, 2 * threads), threads, 900 + w)
     barrier()
+    nb.host_profile(reset=True)
     h0, d0 = nb.transfer_bytes()
     l1 = nb.kernel_launches()
     parts, t_e2e = np.zeros(4), 0.0
@@ -334,6 +335,7 @@ def run_own(args, rank, world, local_rank):
         t_e2e += r.wall_s
     barrier()
     h1, d1 = nb.transfer_bytes()
+    host_prof = nb.host_profile() if os.environ.get("NANORQ_B200_PROFILE") == "1" else None
     e2e_launches = nb.kernel_launches() - l1
     t_e2e = max_over_ranks(t_e2e)
     e2e = None if args.skip_e2e else {"value": gbits(NB * world * args.steps, t_e2e), "unit": "Gbit/s",
@@ -342,6 +344,8 @@ def run_own(args, rank, world, local_rank):
            "gpu_launches": e2e_launches,
            "phase_seconds_summed_over_threads": dict(zip(("generate_symbols", "encode_emit", "add_symbol", "repair_block"),
                                                          [float(x) for x in parts]))}
+    if e2e is not None and host_prof is not None:
+        e2e["host_profile_seconds_summed_over_threads"] = {k: round(v, 4) for k, v in host_prof.items()}
 
     # ---- cpu_baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None

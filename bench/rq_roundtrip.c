@@ -168,7 +168,8 @@ int rq_roundtrip_run(const rt_config *cfg, rt_result *res) {
   uint8_t **payload = calloc((size_t)nb, sizeof(*payload)), **decoded = calloc((size_t)nb, sizeof(*decoded));
   for (int b = 0; b < nb; b++) {
     payload[b] = malloc(F + 4);
-    decoded[b] = calloc(F + 4, 1);
+    decoded[b] = malloc(F + 4);
+    memset(decoded[b], 0, F + 4); /* faulted in before the clock starts, like the payload and packet buffers */
     uint32_t s = cfg->seed + 42u + (uint32_t)b;
     if (!s) s = 1;
     for (size_t k = 0; k < F; k += 4) {

@@ -44,6 +44,13 @@ unsigned long long rqb_kernel_launches(void);
 /* bytes copied host->device / device->host by this library so far */
 void rqb_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
 
+/* host-side time accounting of the nanorq.h layer (enabled by the environment
+ * variable NANORQ_B200_PROFILE=1; off by default).  seconds[k] = time summed over
+ * all threads in slot k, names from rqb_host_profile_name(k) (NULL past the end). */
+void rqb_host_profile(double *seconds, int n);
+const char *rqb_host_profile_name(int k);
+void rqb_host_profile_reset(void);
+
 /* ---- RFC 6330 construction helpers (host, integer only) */
 typedef struct {
   int Kprime, S, H, W, L, P, P1, U, B, J;
@@ -60,7 +67,12 @@ int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32
 /* K_params selects K' (the reference uses block 0's parameters for every block of
  * an object, lib/nanorq.c:289,372, so a shorter block may be padded further) */
 int rqb_solver_create_ex(rqb_solver **out, int K, int K_params, size_t T, uint32_t max_in, uint32_t max_out);
+/* destroy waits for the solver's queued work, then keeps the context (stream,
+ * pinned and device buffers) for the next create of the same shape: CUDA object
+ * creation is too slow for blocks that come and go at wire rate.
+ * rqb_release_cached() really frees every kept context. */
 void rqb_solver_destroy(rqb_solver *s);
+void rqb_release_cached(void);
 /* pinned host staging area for the input rows: max_in rows of rqb_solver_pitch bytes */
 uint8_t *rqb_solver_staging(rqb_solver *s);
 size_t rqb_solver_pitch(const rqb_solver *s);
@@ -90,6 +102,9 @@ int rqb_solver_sync(rqb_solver *s);
 /* copy results back: emitted symbols [first, first+n) of the last run/emit, or
  * intermediate symbols; dst rows are dst_pitch apart, T bytes each */
 int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch);
+/* queue the copy of emitted symbols into the pinned mirror without waiting;
+ * rqb_solver_sync() completes it */
+int rqb_solver_fetch_syms_async(rqb_solver *s, uint32_t first, uint32_t n);
 int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch);
 /* pinned host mirror of the emitted symbols (valid after fetch with dst == NULL) */
 const uint8_t *rqb_solver_sym_mirror(rqb_solver *s);
@@ -120,6 +135,10 @@ int rqb_solver_marked_ms(rqb_solver *s, float *ms);
  * free with rqb_plan_blob_free. */
 typedef struct {
   uint32_t n_ws_rows, n_pages, page_bytes;
+  /* arena layout the program addresses: first row of the spaces IN, SYM, C, WS; the
+   * all-zero row; total rows.  IN is sized to the largest in_row of the request + 1,
+   * SYM to n_out. */
+  uint32_t row0[4], zero_row, n_rows;
   const uint8_t *pages;
   rqb_solver_stats stats;
   void *opaque;

@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     SolveRequest,
     block_params,
     device_count,
+    host_profile,
     kernel_launches,
     last_error,
     lib,

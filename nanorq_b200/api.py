@@ -44,6 +44,7 @@ class SolverStats(C.Structure):
 
 class PlanBlob(C.Structure):
     _fields_ = [("n_ws_rows", C.c_uint32), ("n_pages", C.c_uint32), ("page_bytes", C.c_uint32),
+                ("row0", C.c_uint32 * 4), ("zero_row", C.c_uint32), ("n_rows", C.c_uint32),
                 ("pages", u8p), ("stats", SolverStats), ("opaque", vp)]
 
 
@@ -107,6 +108,9 @@ def lib():
     sig("rqb_set_device", C.c_int, C.c_int)
     sig("rqb_kernel_launches", C.c_ulonglong)
     sig("rqb_transfer_bytes", None, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
+    sig("rqb_host_profile", None, C.POINTER(C.c_double), C.c_int)
+    sig("rqb_host_profile_name", C.c_char_p, C.c_int)
+    sig("rqb_host_profile_reset", None)
     sig("rqb_solver_mark", C.c_int, vp, C.c_int)
     sig("rqb_solver_marked_ms", C.c_int, vp, C.POINTER(C.c_float))
     sig("rqb_block_params_init", C.c_int, C.c_int, C.POINTER(BlockParams))
@@ -114,6 +118,7 @@ def lib():
     sig("rqb_solver_create", C.c_int, C.POINTER(vp), C.c_int, sz, C.c_uint32, C.c_uint32)
     sig("rqb_solver_create_ex", C.c_int, C.POINTER(vp), C.c_int, C.c_int, sz, C.c_uint32, C.c_uint32)
     sig("rqb_solver_destroy", None, vp)
+    sig("rqb_release_cached", None)
     sig("rqb_solver_staging", vp, vp)
     sig("rqb_solver_pitch", sz, vp)
     sig("rqb_solver_upload", C.c_int, vp, C.c_uint32, C.c_uint32)
@@ -123,6 +128,7 @@ def lib():
     sig("rqb_solver_emit", C.c_int, vp, u32p, C.c_uint32)
     sig("rqb_solver_sync", C.c_int, vp)
     sig("rqb_solver_fetch_syms", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
+    sig("rqb_solver_fetch_syms_async", C.c_int, vp, C.c_uint32, C.c_uint32)
     sig("rqb_solver_fetch_c", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
     sig("rqb_solver_sym_mirror", vp, vp)
     sig("rqb_solver_last_kernel_ms", C.c_int, vp, C.POINTER(C.c_float))
@@ -157,10 +163,11 @@ EXPORTED_SYMBOLS = [
     "nanorq_repair_block", "ioctx_from_file", "ioctx_mmap_file", "ioctx_from_mem",
     "rqb_last_error", "rqb_device_count", "rqb_set_device", "rqb_kernel_launches", "rqb_transfer_bytes",
     "rqb_solver_mark", "rqb_solver_marked_ms", "rqb_solver_run_batch_on",
+    "rqb_host_profile", "rqb_host_profile_name", "rqb_host_profile_reset",
     "rqb_block_params_init", "rqb_lt_row_indices", "rqb_solver_create", "rqb_solver_create_ex",
-    "rqb_solver_destroy", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
+    "rqb_solver_destroy", "rqb_release_cached", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
     "rqb_solver_plan", "rqb_solver_plan_encode", "rqb_solver_run", "rqb_solver_emit",
-    "rqb_solver_sync", "rqb_solver_fetch_syms", "rqb_solver_fetch_c", "rqb_solver_sym_mirror",
+    "rqb_solver_sync", "rqb_solver_fetch_syms", "rqb_solver_fetch_c", "rqb_solver_fetch_syms_async", "rqb_solver_sym_mirror",
     "rqb_solver_last_kernel_ms", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_plan_blob_build",
     "rqb_plan_blob_free", "rqb_matrix_create", "rqb_matrix_destroy", "rqb_matrix_pitch",
     "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
@@ -188,6 +195,18 @@ def transfer_bytes():
     h, d = C.c_ulonglong(), C.c_ulonglong()
     lib().rqb_transfer_bytes(C.byref(h), C.byref(d))
     return int(h.value), int(d.value)
+
+
+def host_profile(reset=False):
+    """seconds per slot of the nanorq.h layer, summed over threads (NANORQ_B200_PROFILE=1)"""
+    out = (C.c_double * 32)()
+    lib().rqb_host_profile(out, 32)
+    names = []
+    while lib().rqb_host_profile_name(len(names)):
+        names.append(lib().rqb_host_profile_name(len(names)).decode())
+    if reset:
+        lib().rqb_host_profile_reset()
+    return {n: out[k] for k, n in enumerate(names)}
 
 
 def _check(rc, what):
@@ -272,6 +291,7 @@ def plan_blob(K_params, req):
         return rc, None
     out = {
         "n_ws_rows": b.n_ws_rows, "n_pages": b.n_pages, "page_bytes": b.page_bytes,
+        "row0": list(b.row0), "zero_row": b.zero_row, "n_rows": b.n_rows,
         "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(),
         "stats": b.stats.as_dict(),
     }

@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include "rqb200.h"
+#include "rqb_hostcopy.h"
+#include "rqb_prof.h"
 
 #define Z_MAX 256
 #define K_MAX 56403
@@ -31,6 +33,8 @@ struct block {
   uint32_t in_cap;
   /* encoder: window of repair symbols already produced on the device */
   uint32_t win_first, win_n, win_cap;
+  bool win_pending; /* the window's copy to the host is queued but not waited for */
+  uint32_t loaded_rows; /* staging rows already queued for upload */
 };
 
 struct nanorq {
@@ -216,13 +220,21 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   return b;
 }
 
+#define UPLOAD_CHUNK 512u /* rows per host->device copy queued while the block is still being read */
+
 static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
-  /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging rows */
+  /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging
+   * rows; the rows start moving to the GPU while the rest is still being read */
   uint8_t *st = rqb_solver_staging(b->sv);
+  b->loaded_rows = 0;
   for (uint32_t esi = 0; esi < b->K; esi++) {
     uint8_t *row = st + (size_t)esi * b->pitch;
     size_t got = transfer_symbol(rq, sbn, esi, row, io, 0);
     if (got < rq->T) memset(row + got, 0, rq->T - got);
+    if (esi + 1 - b->loaded_rows == UPLOAD_CHUNK) {
+      if (rqb_solver_upload(b->sv, b->loaded_rows, UPLOAD_CHUNK)) return false;
+      b->loaded_rows = esi + 1;
+    }
   }
   return true;
 }
@@ -231,20 +243,31 @@ bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :20
   struct block *b = get_block(rq, sbn);
   if (!b) return false;
   if (b->inverted) return true;
+  PF_T0;
   if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
   if (!b->loaded) return false;
-  if (rqb_solver_upload(b->sv, 0, b->K)) return false;
-  if (rqb_solver_plan_encode(b->sv, 1, 0)) return false; /* cached per K: cf. rq->S :219-221 */
-  if (rqb_solver_run(b->sv) || rqb_solver_sync(b->sv)) return false;
+  PF(RQB_PF_GEN_LOAD);
+  if (rqb_solver_upload(b->sv, b->loaded_rows, b->K - b->loaded_rows)) return false;
+  b->loaded_rows = b->K;
+  PF(RQB_PF_GEN_UPLOAD);
+  /* the program (cached per K: cf. rq->S :219-221) also emits the first window of
+   * repair symbols, ESI K.. ; nothing here waits for the device -- the first
+   * nanorq_encode of a repair symbol does */
+  if (rqb_solver_plan_encode(b->sv, 1, b->win_cap)) return false;
+  PF(RQB_PF_GEN_PLAN);
+  if (rqb_solver_run(b->sv) || rqb_solver_fetch_syms_async(b->sv, 0, b->win_cap)) return false;
+  PF(RQB_PF_GEN_RUN);
   b->inverted = true;
-  b->win_n = 0;
+  b->win_first = b->K;
+  b->win_n = b->win_cap;
+  b->win_pending = true;
   return true;
 }
 
 bool nanorq_precalculate(nanorq *rq) { /* :393-401 */
   struct block *b = get_block(rq, 0);
   if (!b) return false;
-  return rqb_solver_plan_encode(b->sv, 1, 0) == 0;
+  return rqb_solver_plan_encode(b->sv, 1, b->win_cap) == 0;
 }
 
 size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct ioctx *io) { /* :403-435 */
@@ -255,11 +278,19 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
      * them from the intermediate symbols once inverted; same bytes) */
     if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
     if (!b->loaded) return 0;
+    PF_T0;
     memcpy(data, rqb_solver_staging(b->sv) + (size_t)esi * b->pitch, rq->T);
+    PF(RQB_PF_EMIT_SRC);
     return rq->T;
   }
   if (esi > ((1u << 24) - 1)) return 0;
   if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  PF_T0;
+  if (b->win_pending) { /* the solve and the copy of the first window were queued by generate_symbols */
+    if (rqb_solver_sync(b->sv)) return 0;
+    b->win_pending = false;
+    PF(RQB_PF_GEN_SYNC);
+  }
   if (!(b->win_n && esi >= b->win_first && esi < b->win_first + b->win_n)) {
     /* produce the next window of repair symbols on the device in one LT launch */
     uint32_t n = b->win_cap, pad = (uint32_t)rq->P.Kprime - b->K;
@@ -273,6 +304,7 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
     b->win_n = n;
   }
   memcpy(data, rqb_solver_sym_mirror(b->sv) + (size_t)(esi - b->win_first) * b->pitch, rq->T);
+  PF(RQB_PF_EMIT_WINDOW);
   return rq->T;
 }
 
@@ -285,8 +317,10 @@ void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn) { /* :437-451 */
 void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
   struct block *b = rq->blocks[sbn];
   if (!b) return;
-  b->loaded = b->inverted = false;
+  if (b->win_pending) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
+  b->loaded = b->inverted = b->win_pending = false;
   b->win_n = 0;
+  b->loaded_rows = 0;
   b->nrep = 0;
   if (b->mask) {
     memset(b->mask, 0, b->mask_words * sizeof(uint32_t));
@@ -296,8 +330,10 @@ void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
 
 void nanorq_free(nanorq *rq) { /* :298-307 (NULL-safe here) */
   if (!rq) return;
+  PF_T0;
   for (int sbn = 0; sbn < Z_MAX; sbn++) nanorq_encoder_cleanup(rq, (uint8_t)sbn);
   free(rq);
+  PF(RQB_PF_FREE);
 }
 
 static inline bool mask_get(const struct block *b, uint32_t id) { return (b->mask[id / 32] >> (id % 32)) & 1; }
@@ -306,14 +342,18 @@ static inline void mask_set(struct block *b, uint32_t id) { b->mask[id / 32] |= 
 int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx *io) { /* :478-509 */
   uint8_t sbn = (tag >> 24) & 0xff;
   uint32_t esi = tag & 0x00ffffff;
+  PF_T0;
   struct block *b = get_block(rq, sbn);
+  PF(RQB_PF_ADD_CREATE);
   if (!b || !b->mask || esi > rq->max_esi || esi / 32 >= b->mask_words) return NANORQ_SYM_ERR;
   if (b->gaps == 0) return NANORQ_SYM_IGN;
   if (mask_get(b, esi)) return NANORQ_SYM_DUP;
   uint8_t *st = rqb_solver_staging(b->sv);
   if (esi < b->K) {
-    memcpy(st + (size_t)esi * b->pitch, data, rq->T);
+    rqb_copy_stream(st + (size_t)esi * b->pitch, data, rq->T);
+    PF(RQB_PF_ADD_COPY);
     transfer_symbol(rq, sbn, esi, data, io, 1); /* source symbols go straight to the output */
+    PF(RQB_PF_ADD_WRITE);
     b->gaps--;
   } else {
     uint32_t row = (uint32_t)rq->P.Kprime + (uint32_t)b->nrep;
@@ -322,7 +362,8 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
       b->rep_cap = b->rep_cap ? b->rep_cap * 2 : 256;
       b->rep_esi = realloc(b->rep_esi, b->rep_cap * sizeof(uint32_t));
     }
-    memcpy(st + (size_t)row * b->pitch, data, rq->T); /* arrival order, like repair_bin */
+    rqb_copy_stream(st + (size_t)row * b->pitch, data, rq->T); /* arrival order, like repair_bin */
+    PF(RQB_PF_ADD_COPY);
     b->rep_esi[b->nrep++] = esi;
   }
   mask_set(b, esi);
@@ -348,7 +389,9 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
   const size_t gaps = b->gaps, overhead = b->nrep - gaps;
   const uint32_t pad = (uint32_t)Kp - b->K;
   /* the symbol bytes start moving to the GPU while the host analyses the matrix */
+  PF_T0;
   if (rqb_solver_upload(b->sv, 0, (uint32_t)Kp + (uint32_t)b->nrep)) return false;
+  PF(RQB_PF_REP_UPLOAD);
   size_t nlt = (size_t)Kp + overhead;
   uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);
   uint32_t *missing = malloc(sizeof(uint32_t) * gaps);
@@ -374,11 +417,17 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
     in_row[Kp + x] = (uint32_t)Kp + (uint32_t)rep;
   }
   rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing};
-  int rc = rqb_solver_plan(b->sv, &req);
+  PF(RQB_PF_REP_REQUEST);
+  int rc = rqb_solver_plan(b->sv, &req); /* charges repair.plan / .pages / .args itself */
   free(isi);
   free(in_row);
   bool ok = false;
-  if (rc == 0 && rqb_solver_run(b->sv) == 0 && rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0) == 0) {
+  if (rqb_prof_enabled()) pf_t = rqb_prof_now();
+  if (rc == 0) rc = rqb_solver_run(b->sv);
+  PF(RQB_PF_REP_RUN);
+  if (rc == 0) rc = rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0);
+  PF(RQB_PF_REP_FETCH);
+  if (rc == 0) {
     /* decode_repair_rows + write_repair_rows (:567-589) */
     const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
     for (size_t k = 0; k < nm; k++) {
@@ -387,6 +436,7 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
     }
     b->gaps = 0;
     ok = true;
+    PF(RQB_PF_REP_WRITE);
   } else {
     rqb_solver_sync(b->sv);
   }

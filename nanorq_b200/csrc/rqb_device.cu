@@ -116,24 +116,38 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // every row its group touches.  Rows written in one level are read in later
 // levels by other threads of the SAME CTA only (slices are disjoint), so the CTA
 // barrier between levels is all the ordering the program needs.
-struct RowSpaces {
-  uint8_t *b0, *b1, *b2, *b3; // space bases, already offset to this thread's column
+// A row reference is the row number inside the block's arena (rqb_program.h):
+// address = base + row * pitch, one IMAD.WIDE per source.
+struct Rows {
+  uint8_t *base; // arena, already offset to this thread's column
   uint32_t pitch;
-  __device__ __forceinline__ uint8_t *at(uint32_t ref) const {
-    const uint32_t sp = (ref >> RQB_IDX_BITS) & 3u;
-    uint8_t *lo = (sp & 1u) ? b1 : b0, *hi = (sp & 1u) ? b3 : b2;
-    uint8_t *p = ((sp & 2u) ? hi : lo) + (size_t)(ref & (RQB_MAX_ROWS - 1u)) * pitch;
-    __builtin_assume(__isGlobal(p)); // LDG/STG instead of generic accesses
-    return p;
+  __device__ __forceinline__ uint8_t *at(uint32_t row) const {
+    uint64_t p; // one IMAD.WIDE: base + row * pitch
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(row), "r"(pitch), "l"(base));
+    return reinterpret_cast<uint8_t *>(p);
+  }
+  // 16 bytes of a row; rows are rewritten by other threads of the CTA between levels,
+  // so the loads and stores keep their program order ("memory")
+  __device__ __forceinline__ uint4 ld(uint32_t row) const {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(at(row))
+                 : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(uint32_t row, const uint4 &v) const {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(at(row)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
   }
 };
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
 
 // The two rare task kinds live out of line so that the XOR gather (the hot path)
 // gets the kernel's register budget to itself.
 // SCAN: y = alpha*y ^ row[e_k]; row[dst+k] = y.  Loads run four entries ahead of the chain.
-__device__ __noinline__ void task_scan(const RowSpaces R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
+__device__ __noinline__ void task_scan(const Rows R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
   uint4 y = make_uint4(0, 0, 0, 0);
-  uint8_t *dp = R.at(dst);
   for (uint32_t k0 = 0; k0 < nsrc; k0 += 4) {
     const uint4 e = *reinterpret_cast<const uint4 *>(sp + k0);
     const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
@@ -141,27 +155,25 @@ __device__ __noinline__ void task_scan(const RowSpaces R, const uint32_t *sp, ui
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       x[u] = make_uint4(0, 0, 0, 0);
-      if (k0 + u < nsrc && (ev[u] & RQB_REF_MASK) != RQB_REF_NONE)
-        x[u] = *reinterpret_cast<const uint4 *>(R.at(ev[u]));
+      if (k0 + u < nsrc && ev[u] != RQB_REF_NONE) x[u] = R.ld(ev[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       if (k0 + u < nsrc) {
         y.x = xtime4(y.x) ^ x[u].x; y.y = xtime4(y.y) ^ x[u].y;
         y.z = xtime4(y.z) ^ x[u].z; y.w = xtime4(y.w) ^ x[u].w;
-        *reinterpret_cast<uint4 *>(dp) = y;
-        dp += R.pitch;
+        R.st(dst + k0 + u, y);
       }
     }
   }
 }
 // GF: row[dst] = XOR beta_k * row[src_k], nsrc <= 8; all loads first, then the multiplies.
-__device__ __noinline__ void task_gf(const RowSpaces R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
+__device__ __noinline__ void task_gf(const Rows R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
   uint4 v[8];
 #pragma unroll
   for (int u = 0; u < 8; u++) {
     v[u] = make_uint4(0, 0, 0, 0);
-    if ((uint32_t)u < nsrc) v[u] = *reinterpret_cast<const uint4 *>(R.at(sp[u]));
+    if ((uint32_t)u < nsrc) v[u] = R.ld(sp[u] & RQB_REF_MASK);
   }
   uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -172,7 +184,7 @@ __device__ __noinline__ void task_gf(const RowSpaces R, const uint32_t *sp, uint
       acc.z ^= gfmul4(v[u].z, bp); acc.w ^= gfmul4(v[u].w, bp);
     }
   }
-  *reinterpret_cast<uint4 *>(R.at(dst)) = acc;
+  R.st(dst, acc);
 }
 
 __global__ void __launch_bounds__(kSolveThreads, kSolveMinCtas)
@@ -203,8 +215,8 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   const uint32_t col = col0 + (uint32_t)(tid % kLanesPerTask) * 16u;
   const bool active = col < width; // the last slice of a row may be narrower than 128 bytes
   const uint32_t grp = (uint32_t)tid / kLanesPerTask;
-  RowSpaces R;
-  R.b0 = a.base[0] + col; R.b1 = a.base[1] + col; R.b2 = a.base[2] + col; R.b3 = a.base[3] + col;
+  Rows R;
+  R.base = a.base + col;
   R.pitch = a.pitch;
 
   for (uint32_t pg = 0; pg < n_pages; pg++) {
@@ -221,26 +233,30 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
           const uint4 th = tasks[t]; // {src_off, dst, nsrc | kind<<16 | aux<<24, pad}
           const uint32_t nsrc = th.z & 0xffffu, kind = (th.z >> 16) & 0xffu;
           const uint32_t *sp = reinterpret_cast<const uint32_t *>(page + th.x);
-          if (kind == RQB_T_SCAN) {
-            task_scan(R, sp, nsrc, th.y);
-          } else if (kind == RQB_T_GF) {
-            task_gf(R, sp, nsrc, th.y);
-          } else {
-            // up to RQB_MAX_SRCS row segments, all requested before the first is consumed
+          if (kind == RQB_T_XOR) {
+            // the list holds exactly 4 or 8 rows (padded with the ZERO row): every load is
+            // issued before the first value is consumed, no per-source predicates
             const uint4 i0 = *reinterpret_cast<const uint4 *>(sp);
-            uint4 i1 = make_uint4(0, 0, 0, 0);
-            if (nsrc > 4) i1 = *reinterpret_cast<const uint4 *>(sp + 4);
-            const uint32_t id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-            uint4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              v[u] = make_uint4(0, 0, 0, 0);
-              if ((uint32_t)u < nsrc) v[u] = *reinterpret_cast<const uint4 *>(R.at(id[u]));
+            uint4 v0 = R.ld(i0.x), v1 = R.ld(i0.y), v2 = R.ld(i0.z), v3 = R.ld(i0.w);
+            uint4 acc;
+            if (nsrc > 4) {
+              const uint4 i1 = *reinterpret_cast<const uint4 *>(sp + 4);
+              uint4 v4 = R.ld(i1.x), v5 = R.ld(i1.y), v6 = R.ld(i1.z), v7 = R.ld(i1.w);
+              acc.x = xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+              acc.y = xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+              acc.z = xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+              acc.w = xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+            } else {
+              acc.x = xor3(v0.x, v1.x, v2.x) ^ v3.x;
+              acc.y = xor3(v0.y, v1.y, v2.y) ^ v3.y;
+              acc.z = xor3(v0.z, v1.z, v2.z) ^ v3.z;
+              acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
             }
-            uint4 acc = make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int u = 0; u < 8; u++) xor4(acc, v[u]);
-            *reinterpret_cast<uint4 *>(R.at(th.y)) = acc;
+            R.st(th.y, acc);
+          } else if (kind == RQB_T_SCAN) {
+            task_scan(R, sp, nsrc, th.y);
+          } else {
+            task_gf(R, sp, nsrc, th.y);
           }
         }
       }

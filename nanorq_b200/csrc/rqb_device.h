@@ -25,7 +25,7 @@ typedef struct {
 /* arguments of one source block for the column-sliced solve kernel
  * (all pointers are DEVICE pointers) */
 typedef struct {
-  uint8_t *base[4];     /* row spaces of rqb_program.h: in, working rows, C, emitted symbols */
+  uint8_t *base;        /* the block's arena: [IN | SYM | C | WS] rows (rqb_program.h)        */
   const uint8_t *pages; /* program pages                                                     */
   uint32_t pitch;       /* bytes between rows (all spaces), multiple of 64                   */
   uint32_t n_pages;

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include "io.h"
+#include "rqb_hostcopy.h"
 
 /* ------------------------------------------------------------- stdio file */
 typedef struct {
@@ -63,14 +64,14 @@ static size_t m_clip(mem_ctx *c, size_t n) { return c->pos + n > c->len ? c->len
 static size_t m_read(struct ioctx *io, uint8_t *b, size_t n) {
   mem_ctx *c = (mem_ctx *)io;
   n = m_clip(c, n);
-  memcpy(b, c->base + c->pos, n);
+  rqb_copy_stream(b, c->base + c->pos, n); /* the library reads into pinned staging rows */
   c->pos += n;
   return n;
 }
 static size_t m_write(struct ioctx *io, const uint8_t *b, size_t n) {
   mem_ctx *c = (mem_ctx *)io;
   n = m_clip(c, n);
-  memcpy(c->base + c->pos, b, n);
+  rqb_copy_stream(c->base + c->pos, b, n); /* decoded output: not read again soon */
   c->pos += n;
   return n;
 }

@@ -64,6 +64,12 @@ static void tables_build(void) {
   }
 }
 
+#ifdef RQB_PLAN_FINE
+double rqb_plan_fine[24];
+#define FINE(k) do { double _t = now_s(); rqb_plan_fine[k] += _t - fine_t; fine_t = _t; } while (0)
+#else
+#define FINE(k) do { } while (0)
+#endif
 static double now_s(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -170,6 +176,7 @@ typedef struct {
   size_t nt;
   uint32_t *srcs;
   size_t ns;
+  uint32_t ws_base; /* arena row of working row 0 */
   uint32_t ws_next; /* next unused working row */
   uint32_t max_level;
   size_t tot_x, tot_gf, tot_h;
@@ -185,7 +192,11 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
   t->nsrc = (uint16_t)n;
   t->kind = (uint8_t)kind;
   t->aux = (uint8_t)aux;
-  if (n) memcpy(b->srcs + b->ns, srcs, (size_t)n * sizeof(uint32_t));
+  if (kind == RQB_T_GF) {
+    if (n) memcpy(b->srcs + b->ns, srcs, (size_t)n * sizeof(uint32_t));
+  } else { /* XOR and SCAN sources are bare row numbers */
+    for (uint32_t k = 0; k < n; k++) b->srcs[b->ns + k] = srcs[k] & RQB_REF_MASK;
+  }
   b->ns += n;
   if (level > b->max_level) b->max_level = level;
   if (kind == RQB_T_GF)
@@ -204,7 +215,7 @@ static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint3
     uint32_t m = 0;
     for (uint32_t o = 0; o < n; o += RQB_MAX_SRCS) {
       uint32_t cnt = n - o < RQB_MAX_SRCS ? n - o : RQB_MAX_SRCS;
-      uint32_t r = RQB_REF(RQB_SP_WS, b->ws_next++);
+      uint32_t r = b->ws_base + b->ws_next++;
       b_task(b, kind, r, 0, level, srcs + o, cnt);
       srcs[m++] = RQB_SRC(r, 1);
     }
@@ -216,22 +227,29 @@ static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint3
   return level;
 }
 
-static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + (((size_t)t->nsrc * 4 + 15) & ~(size_t)15); }
+/* bytes of a task's source list in the page: XOR lists are padded to 4 or 8 entries */
+static size_t list_bytes(const ptask *t) {
+  if (t->kind == RQB_T_XOR) return t->nsrc <= 4 ? 16 : 32;
+  return ((size_t)t->nsrc * 4 + 15) & ~(size_t)15;
+}
+static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + list_bytes(t); }
 
 /* pack the tasks, level by level, into pages (a level may be split over pages:
  * its tasks are independent).  Returns 0 or a negative error. */
-static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
+static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *tot_levels) {
   scratch_t *sc = b->sc;
   const uint32_t nl = b->max_level + 1;
-  /* one stable counting sort by (level, kind): tasks of a kind sit together inside a
-   * level so that the lanes of a warp follow the same path */
-  const uint32_t nkeys = nl * 3;
+  /* one stable counting sort by (level, kind, narrow/wide list): tasks that take the
+   * same path through the kernel sit together inside a level */
+  const uint32_t nkeys = nl * 4;
   uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nkeys + 2) * 4, 1);
   uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
-  for (size_t k = 0; k < b->nt; k++) cnt[b->tasks[k].level * 3 + b->tasks[k].kind + 1]++;
+#define TKEY(t) ((t).level * 4 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
+  for (size_t k = 0; k < b->nt; k++) cnt[TKEY(b->tasks[k]) + 1]++;
   for (uint32_t l = 0; l < nkeys; l++) cnt[l + 1] += cnt[l];
-  for (size_t k = 0; k < b->nt; k++) order[cnt[b->tasks[k].level * 3 + b->tasks[k].kind]++] = (uint32_t)k;
-  /* cnt[key] now holds the END of its bucket: level l spans [cnt[3l-1], cnt[3l+2]) */
+  for (size_t k = 0; k < b->nt; k++) order[cnt[TKEY(b->tasks[k])]++] = (uint32_t)k;
+#undef TKEY
+  /* cnt[key] now holds the END of its bucket: level l spans [cnt[4l-1], cnt[4l+3]) */
   size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
   uint8_t *pages = plan->pages;
 #define OPEN_PAGE()                                                         \
@@ -251,7 +269,7 @@ static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
     cur = 0;                                                                                      \
   } while (0)
   for (uint32_t l = 0; l < nl; l++) {
-    size_t lo = l ? cnt[3 * l - 1] : 0, hi = cnt[3 * l + 2];
+    size_t lo = l ? cnt[4 * l - 1] : 0, hi = cnt[4 * l + 3];
     if (lo == hi) continue;
     size_t idx = lo;
     while (idx < hi) {
@@ -277,8 +295,10 @@ static int write_pages(builder *b, rqb_plan *plan, size_t *tot_levels) {
       uint32_t soff = (uint32_t)(cur + sizeof(rqb_level_hdr) + n * sizeof(rqb_task));
       for (size_t k = 0; k < n; k++) {
         const ptask *t = &b->tasks[order[idx + k]];
-        size_t sb = ((size_t)t->nsrc * 4 + 15) & ~(size_t)15;
+        size_t sb = list_bytes(t);
         memcpy(page + soff, b->srcs + t->src_at, (size_t)t->nsrc * 4);
+        if (t->kind == RQB_T_XOR)
+          for (size_t q = t->nsrc; q < sb / 4; q++) ((uint32_t *)(page + soff))[q] = zero_row;
         dst[k].src_off = soff;
         dst[k].dst = t->dst;
         dst[k].nsrc = t->nsrc;
@@ -347,6 +367,9 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   const int oh = req->overhead, R = L + oh, n = Kp + S, nlt = Kp + oh;
   if ((uint32_t)H > RQB_MAX_H) return -1;
   double t0 = now_s();
+#ifdef RQB_PLAN_FINE
+  double fine_t = t0;
+#endif
   scratch_t *sc = sc_get();
   int rc = 0;
 
@@ -501,6 +524,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   const int nb = R - H - I;
   if (I + U != L || nb < 0) return -2;
   double t2 = now_s();
+  FINE(5);
 
   /* ---- 3a. dependencies of the triangular solve, G = X^-1 U_top (bits), and the
    * schedule of each row: at most RQB_MAX_SRCS-1 terms besides the row itself;
@@ -589,6 +613,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     pfirst[I] = nparts;
   }
 
+  FINE(0);
   /* ---- 3b. residual binary rows: Schur bits and their X-part source lists */
   int *lowrows = sc_buf(sc, SC_LOWROWS, sizeof(int) * (size_t)(nb ? nb : 1), 0);
   {
@@ -624,6 +649,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     xptr[nb] = nx;
   }
 
+  FINE(1);
   /* ---- 3c. HDPC Schur rows (H x U bytes) by the alpha recurrence.
    * HDPC[:,j] = alpha*HDPC[:,j+1] ^ e_b1(j) ^ e_b2(j), last column alpha^h
    * (lib/precode.c:60-83)  =>  sum_j HDPC[h][j] v_j = alpha^h y_{n-1} ^ sum_{j<=n-2, h in b(j)} y_j
@@ -668,6 +694,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
   }
 
+  FINE(2);
   /* ---- 3d. Gauss-Jordan over GF(2) on the binary Schur rows, transformation tracked */
   int *pivrow = sc_buf(sc, SC_PIVROW, sizeof(int) * (size_t)(U ? U : 1), 0); /* column t -> local row or -1 */
   int *pivcol_of_row = sc_buf(sc, SC_PIVCOL, sizeof(int) * (size_t)(nb ? nb : 1), 0);
@@ -696,6 +723,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
         bits_xor(Tb + (size_t)m * nbw, pt, nbw);
       }
   }
+  FINE(3);
   /* ---- 3e. HDPC rows: eliminate pivot columns (beta = Sh[h][t]), then solve the
    *          H x nfree system Q over GF(256) with a tracked transformation TQ (H x H) */
   uint8_t *Q = sc_buf(sc, SC_Q, (size_t)H * (size_t)(nfree ? nfree : 1), 1);
@@ -738,6 +766,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   }
   double t3 = now_s();
 
+  FINE(4);
   /* ---- 4. emit the program.
    * Working rows: matrix row r -> WS row r; then r'_t (RP+t), z_t (Z+t), the scan
    * rows y_j, one row per part, then whatever the reduction trees need.
@@ -751,20 +780,29 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   const uint32_t YS = Z + (uint32_t)U;        /* y_j of the chunk-local alpha-scans, one row per column j < n */
   const uint32_t PT = YS + (uint32_t)n;
   const uint32_t WS_FIXED = PT + (uint32_t)nparts;
-  if ((uint64_t)WS_FIXED + (uint64_t)nnz > RQB_MAX_ROWS) return -4;
+  /* arena layout: [IN | SYM | C | WS] */
+  uint32_t row0[4];
+  row0[RQB_SP_IN] = 0;
+  row0[RQB_SP_SYM] = req->in_rows;
+  row0[RQB_SP_C] = row0[RQB_SP_SYM] + req->sym_rows;
+  const uint32_t zero_row = row0[RQB_SP_C] + (uint32_t)L;
+  row0[RQB_SP_WS] = zero_row + 1;
+  if (req->sym_rows < (uint32_t)req->n_out) return -1;
+  if ((uint64_t)row0[RQB_SP_WS] + (uint64_t)WS_FIXED + (uint64_t)nnz > RQB_MAX_ROWS) return -4;
   builder bd;
   memset(&bd, 0, sizeof(bd));
   bd.sc = sc;
+  bd.ws_base = row0[RQB_SP_WS];
   bd.ws_next = WS_FIXED;
   uint32_t *loc = sc_buf(sc, SC_CURLOC, sizeof(uint32_t) * (size_t)WS_FIXED, 0);
   for (uint32_t s = 0; s < WS_FIXED; s++) loc[s] = NONE_REF;
   for (int k = 0; k < nlt; k++)
     if (req->in_row[k] != RQB_ROW_NONE) {
-      if (req->in_row[k] >= RQB_MAX_ROWS) return -1;
-      loc[S + H + k] = RQB_REF(RQB_SP_IN, req->in_row[k]);
+      if (req->in_row[k] >= req->in_rows) return -1;
+      loc[S + H + k] = row0[RQB_SP_IN] + req->in_row[k];
     }
   uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)4 * (size_t)n + (size_t)NC + 4096), 0);
-#define WSREF(s) RQB_REF(RQB_SP_WS, (s))
+#define WSREF(s) (row0[RQB_SP_WS] + (uint32_t)(s))
 #define PUSH(ns, ref)                                  \
   do {                                                 \
     uint32_t _r = (ref);                               \
@@ -796,6 +834,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   TRIANGULAR(0u);
   uint32_t lv = (uint32_t)maxlevel + 1, end = lv;
 
+  FINE(6);
   /* B: residual rows r_m = b_m ^ X_low*Y ; HDPC rows through NC chunk scans over columns 0..n-1 */
   for (int m = 0; m < nb; m++) {
     uint32_t ns = 0;
@@ -819,6 +858,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   lv = end + 1;
   end = lv;
 
+  FINE(7);
   /* C1: r'_t = XOR_{m in Tb[pivrow t]} r_m ; HDPC base r_h = XOR_{j <= n-2, h in b(j)} y_j (chunk-local y) */
   for (int t = 0; t < U; t++) {
     if (pivrow[t] < 0) continue;
@@ -856,6 +896,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   lv = end + 1;
   end = lv;
 
+  FINE(8);
   /* C2: r'_h = r_h ^ sum_c Gc[h][c]*yend_c ^ sum_t beta[h][t]*r'_t  (GF leaves, XOR tree).
    * Gc[h][c'] = alpha^h alpha^(n-e_c') ^ sum_{c>c'} coef[c][h] alpha^(s_c-e_c'),
    * coef[c][h] = sum_{j in chunk c, j<=n-2, h in b(j)} alpha^(j-s_c+1). */
@@ -899,6 +940,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   }
   lv = end + 1;
   end = lv;
+  FINE(9);
   /* C3: z_f = sum_h TQ[qrow(f)][h] * r'_h */
   for (int f = 0; f < nfree; f++) {
     uint32_t ns = 0;
@@ -927,12 +969,13 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   lv = end + 1;
   end = lv;
 
+  FINE(10);
   /* D: b_top' = b_top ^ U_top z.  A row without inactive columns just goes back to
    * its input row (no task); the others are rebuilt from the input row. */
   for (int p = 0; p < I; p++) {
     int r = prow[p];
     uint32_t ns = 0;
-    uint32_t orig = r >= S + H ? (req->in_row[r - S - H] != RQB_ROW_NONE ? RQB_REF(RQB_SP_IN, req->in_row[r - S - H]) : NONE_REF)
+    uint32_t orig = r >= S + H ? (req->in_row[r - S - H] != RQB_ROW_NONE ? row0[RQB_SP_IN] + req->in_row[r - S - H] : NONE_REF)
                                : NONE_REF;
     for (int k = rptr[r]; k < rptr[r + 1]; k++)
       if (col_state[cidx[k]] == 2) PUSH(ns, loc[Z + (uint32_t)col_t[cidx[k]]]);
@@ -945,11 +988,13 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     loc[r] = WSREF(r);
     if (e2 > end) end = e2;
   }
+  FINE(11);
   /* E: x = X^-1 b_top' */
   TRIANGULAR(end);
   lv = end + (uint32_t)maxlevel + 1;
   end = lv;
 
+  FINE(12);
   /* O: outputs.  C[col] sits in the row that pivoted on col, or in z. */
   uint32_t *cloc = sc_buf(sc, SC_CSLOT, sizeof(uint32_t) * (size_t)L, 0);
   for (int c = 0; c < L; c++) cloc[c] = col_state[c] == 1 ? loc[prow[col_pos[c]]] : loc[Z + (uint32_t)col_t[c]];
@@ -957,33 +1002,38 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     for (int c = 0; c < L; c++) {
       uint32_t ns = 0;
       PUSH(ns, cloc[c]);
-      b_task(&bd, RQB_T_XOR, RQB_REF(RQB_SP_C, c), 0, lv, tmp, ns);
+      b_task(&bd, RQB_T_XOR, row0[RQB_SP_C] + (uint32_t)c, 0, lv, tmp, ns);
     }
   for (int k = 0; k < req->n_out; k++) {
     uint32_t idx[RQB_MAX_LT_DEGREE];
     int cnt = rqb_host_lt_indices(&P, req->out_isi[k], idx);
     uint32_t ns = 0;
     for (int q = 0; q < cnt; q++) PUSH(ns, cloc[idx[q]]);
-    b_tree(&bd, RQB_T_XOR, RQB_REF(RQB_SP_SYM, k), tmp, ns, lv);
+    b_tree(&bd, RQB_T_XOR, row0[RQB_SP_SYM] + (uint32_t)k, tmp, ns, lv);
   }
 #undef PUSH
 #undef WSREF
 #undef TRIANGULAR
-  if (bd.ws_next > RQB_MAX_ROWS) return -4;
+  if ((uint64_t)row0[RQB_SP_WS] + bd.ws_next > RQB_MAX_ROWS) return -4;
 
+  FINE(13);
   rqb_plan *plan = plan_acquire();
   size_t tot_levels = 0;
-  rc = write_pages(&bd, plan, &tot_levels);
+  rc = write_pages(&bd, plan, zero_row, &tot_levels);
   if (rc) {
     rqb_plan_free(plan);
     return rc;
   }
   double t4 = now_s();
+  FINE(14);
 
   plan->P = P;
   plan->K = req->K;
   plan->overhead = oh;
   plan->n_ws_rows = bd.ws_next;
+  memcpy(plan->row0, row0, sizeof(row0));
+  plan->n_rows = row0[RQB_SP_WS] + bd.ws_next;
+  plan->zero_row = zero_row;
   plan->n_c_rows = req->want_c ? (uint32_t)L : 0;
   plan->n_out = (uint32_t)req->n_out;
   plan->st.i = I;

@@ -27,6 +27,8 @@ typedef struct {
   int want_c;              /* emit all L intermediate symbols to c_out (row = index)        */
   int n_out;               /* encoding symbols to emit to sym_out (row k = out_isi[k])      */
   const uint32_t *out_isi; /* [n_out] internal symbol ids                                   */
+  uint32_t in_rows;        /* rows the arena reserves for the input space  (> every in_row) */
+  uint32_t sym_rows;       /* rows the arena reserves for emitted symbols  (>= n_out)       */
 } rqb_plan_request;
 
 typedef struct {
@@ -44,6 +46,9 @@ typedef struct rqb_plan {
   rqb_params P;
   int K, overhead;
   uint32_t n_ws_rows;  /* working rows (RQB_SP_WS) the program uses             */
+  uint32_t row0[4];    /* first arena row of each space (rqb_program.h)         */
+  uint32_t n_rows;     /* arena rows the program addresses: row0[WS] + n_ws_rows */
+  uint32_t zero_row;   /* the all-zero row (the solver clears it, nothing writes it) */
   uint32_t n_pages;
   uint8_t *pages;      /* n_pages * RQB_PAGE_BYTES                              */
   size_t pages_cap;    /* bytes allocated behind pages (plans are recycled)     */

@@ -20,7 +20,12 @@
  * (decode_row, lib/nanorq.c:184-204: a gather into the SYM space).
  * A destination that accumulates lists its own previous location as a source.
  *
- * Row references are 24 bits: space (2) | index (22).
+ * All rows of a block sit in ONE arena, one pitch, in the order
+ *     [ IN: in_rows | SYM: sym_rows | C: L | ZERO: 1 | WS: working rows ]
+ * and a row reference is simply the 24-bit row number inside that arena, so the
+ * kernel turns a reference into an address with one multiply-add.  The ZERO row
+ * is never written: the source list of an XOR task is padded with it to exactly
+ * 4 or 8 entries, so the kernel issues its loads without per-source predicates.
  */
 #ifndef RQB_PROGRAM_H
 #define RQB_PROGRAM_H
@@ -32,22 +37,21 @@
 #define RQB_MAX_SRCS 8u      /* sources per XOR/GF task (the kernel keeps them all in flight) */
 #define RQB_ROW_NONE 0xFFFFFFFFu
 
-enum rqb_space {
+enum rqb_space { /* in arena order */
   RQB_SP_IN = 0,  /* received / source symbols as uploaded (read-only)      */
-  RQB_SP_WS = 1,  /* working rows                                           */
+  RQB_SP_SYM = 1, /* emitted symbols (repair symbols / recovered symbols)   */
   RQB_SP_C = 2,   /* intermediate symbols C[0..L) in RFC order              */
-  RQB_SP_SYM = 3  /* emitted symbols (repair symbols / recovered symbols)   */
+  RQB_SP_WS = 3   /* working rows                                           */
 };
-#define RQB_IDX_BITS 22u
-#define RQB_MAX_ROWS (1u << RQB_IDX_BITS)
-#define RQB_REF(space, idx) (((uint32_t)(space) << RQB_IDX_BITS) | (uint32_t)(idx))
+#define RQB_MAX_ROWS 0x00FFFFFEu /* rows an arena can hold */
 #define RQB_REF_MASK 0x00FFFFFFu
 #define RQB_REF_NONE 0x00FFFFFFu /* SCAN: "no row here" */
-/* XOR / GF source: ref | beta << 24 (beta is 1 for XOR tasks) */
+/* GF source: row | beta << 24.  XOR and SCAN sources are the bare row number. */
 #define RQB_SRC(ref, beta) ((uint32_t)(ref) | ((uint32_t)(beta) << 24))
 
 enum rqb_task_kind {
-  RQB_T_XOR = 0, /* row[dst] = XOR row[src_k]              nsrc <= RQB_MAX_SRCS (0 => zero row) */
+  RQB_T_XOR = 0, /* row[dst] = XOR row[src_k]              nsrc <= RQB_MAX_SRCS (0 => zero row);
+                    the list holds 4 (nsrc <= 4) or 8 entries, padded with the ZERO row            */
   RQB_T_GF = 1,  /* row[dst] = XOR beta_k * row[src_k]     nsrc <= RQB_MAX_SRCS                 */
   RQB_T_SCAN = 2 /* alpha-scan over nsrc entries, see below                                    */
 };
@@ -61,7 +65,7 @@ enum rqb_task_kind {
 
 typedef struct {
   uint32_t src_off; /* byte offset of the source list from the page start (16-byte aligned) */
-  uint32_t dst;     /* row reference                                                        */
+  uint32_t dst;     /* row number                                                           */
   uint16_t nsrc;
   uint8_t kind;
   uint8_t aux;

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "rqb200.h"
 #include "rqb_device.h"
@@ -28,6 +29,37 @@ static int dev_fail(int e, const char *what) {
     int _e = (x);                            \
     if (_e) return dev_fail(_e, #x);         \
   } while (0)
+
+/* ------------------------------------------------ host time accounting */
+#include "rqb_prof.h"
+static _Atomic unsigned long long g_prof_ns[RQB_PF_COUNT];
+static int g_prof_on = -1;
+static const char *const g_prof_names[RQB_PF_COUNT] = {
+    "gen.load", "gen.upload", "gen.plan", "gen.run", "gen.sync", "emit.source", "emit.window", "add.create",
+    "add.copy", "add.write", "repair.upload", "repair.request", "repair.plan", "repair.pages", "repair.args",
+    "repair.run", "repair.fetch", "repair.write", "free"};
+int rqb_prof_enabled(void) {
+  if (g_prof_on < 0) {
+    const char *e = getenv("NANORQ_B200_PROFILE");
+    g_prof_on = e && e[0] == '1';
+  }
+  return g_prof_on;
+}
+double rqb_prof_now(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void rqb_prof_add(int slot, double seconds) {
+  if (slot >= 0 && slot < RQB_PF_COUNT) g_prof_ns[slot] += (unsigned long long)(seconds * 1e9);
+}
+void rqb_host_profile(double *seconds, int n) {
+  for (int k = 0; k < n; k++) seconds[k] = k < RQB_PF_COUNT ? 1e-9 * (double)g_prof_ns[k] : 0.0;
+}
+const char *rqb_host_profile_name(int k) { return k >= 0 && k < RQB_PF_COUNT ? g_prof_names[k] : NULL; }
+void rqb_host_profile_reset(void) {
+  for (int k = 0; k < RQB_PF_COUNT; k++) g_prof_ns[k] = 0;
+}
 
 int rqb_device_count(void) { return rqb_dev_count(); }
 int rqb_set_device(int dev) {
@@ -118,7 +150,7 @@ static void pool_put(void *p, size_t bytes, int pinned) {
  * it is cached process-wide together with its device copy. */
 typedef struct enc_plan {
   int K, Kparams, want_c, dev;
-  uint32_t n_out;
+  uint32_t n_out, in_rows, sym_rows; /* the arena layout is part of the program */
   rqb_plan *plan;
   uint8_t *d_pages;
   struct enc_plan *next;
@@ -131,11 +163,20 @@ struct rqb_solver {
   int K, Kparams, dev;
   size_t T, pitch;
   rqb_params P;
-  uint32_t max_in, max_out;
+  uint32_t max_in, max_out;       /* rows this owner asked for                      */
+  uint32_t in_cap, out_cap; /* rows the pinned buffers really have (recycled contexts) */
+  int busy;   /* work has been queued on the stream since the last wait */
+  int broken; /* a device call failed: do not recycle                    */
+  int pages_pending;             /* the pinned page staging is still being copied */
+  struct rqb_solver *batch_owner; /* last batched launch ran on this solver's stream */
+  struct rqb_solver *next_shell;
   void *stream, *ev0, *ev1, *ev2, *ev3;
-  uint8_t *h_in, *d_in, *d_c, *d_sym, *h_sym;
-  uint8_t *d_ws; /* working rows of the current program (grown on demand) */
-  size_t d_ws_cap;
+  uint8_t *h_in, *h_sym; /* pinned: staging rows of the input space, mirror of the emitted symbols */
+  /* every row of the block lives in ONE device arena (rqb_program.h):
+   * [IN: max_in | SYM: max_out | C: L | ZERO: 1 | WS: working rows, grown on demand] */
+  uint8_t *d_arena;
+  size_t arena_cap; /* bytes */
+  uint32_t row0[4], zero_row;
   uint32_t *d_isi, *h_isi;
   /* current program */
   rqb_plan *plan; /* owned unless shared */
@@ -151,24 +192,47 @@ size_t rqb_solver_pitch(const rqb_solver *s) { return s->pitch; }
 uint8_t *rqb_solver_staging(rqb_solver *s) { return s->h_in; }
 const uint8_t *rqb_solver_sym_mirror(rqb_solver *s) { return s->h_sym; }
 
-void rqb_solver_destroy(rqb_solver *s) {
-  if (!s) return;
-  if (s->stream) rqb_stream_sync(s->stream);
+/* Solver contexts are recycled whole (stream, events, pinned and device buffers):
+ * creating and destroying CUDA objects takes the driver's global lock, and with a
+ * dozen decoder threads coming and going at wire rate that lock was where they
+ * met (0.6 ms per block at 16 threads, 6 ms at 32).  A destroyed solver goes to a
+ * free list and is handed out again to the next create with the same device and
+ * symbol size whose rows fit. */
+static int solver_wait(rqb_solver *s);
+static rqb_solver *g_shells;
+
+/* arena rows a fresh context gets: the fixed spaces plus room for the working rows of
+ * a typical program (about 3.5 L; the arena is regrown if a program needs more) */
+static size_t arena_rows_wanted(uint32_t max_in, uint32_t max_out, const rqb_params *P) {
+  return (size_t)max_in + max_out + (size_t)P->L + 1 + 4 * (size_t)P->L + 512;
+}
+
+/* place the row spaces for this owner's max_in / max_out and clear the ZERO row */
+static int solver_layout(rqb_solver *s) {
+  s->row0[RQB_SP_IN] = 0;
+  s->row0[RQB_SP_SYM] = s->max_in;
+  s->row0[RQB_SP_C] = s->max_in + s->max_out;
+  s->zero_row = s->row0[RQB_SP_C] + (uint32_t)s->P.L;
+  s->row0[RQB_SP_WS] = s->zero_row + 1;
+  s->busy = 1;
+  return rqb_dev_memset(s->d_arena + (size_t)s->zero_row * s->pitch, 0, s->pitch, s->stream);
+}
+#define ROW_PTR(s, space, k) ((s)->d_arena + ((size_t)(s)->row0[space] + (k)) * (s)->pitch)
+static pthread_mutex_t g_shell_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void solver_release(rqb_solver *s) { /* really free everything */
   int cur = rqb_dev_get();
   if (cur != s->dev) rqb_dev_set(s->dev);
-  pool_put(s->h_in, (size_t)s->max_in * s->pitch, 1);
-  pool_put(s->d_in, (size_t)s->max_in * s->pitch, 0);
-  pool_put(s->d_c, (size_t)s->P.L * s->pitch, 0);
-  pool_put(s->d_sym, (size_t)s->max_out * s->pitch, 0);
-  pool_put(s->h_sym, (size_t)s->max_out * s->pitch, 1);
-  pool_put(s->d_isi, (size_t)s->max_out * 4, 0);
+  if (s->stream) rqb_stream_sync(s->stream);
+  pool_put(s->h_in, (size_t)s->in_cap * s->pitch, 1);
+  pool_put(s->d_arena, s->arena_cap, 0);
+  pool_put(s->h_sym, (size_t)s->out_cap * s->pitch, 1);
+  pool_put(s->d_isi, (size_t)s->out_cap * 4, 0);
   free(s->h_isi);
   pool_put(s->d_pages, s->d_pages_cap, 0);
   pool_put(s->h_pages, s->h_pages_cap, 1);
-  pool_put(s->d_ws, s->d_ws_cap, 0);
   free(s->h_args);
   pool_put(s->d_args, RQB_ARGS_BYTES, 0);
-  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
   if (s->ev0) rqb_event_destroy(s->ev0);
   if (s->ev1) rqb_event_destroy(s->ev1);
   if (s->ev2) rqb_event_destroy(s->ev2);
@@ -176,6 +240,38 @@ void rqb_solver_destroy(rqb_solver *s) {
   if (s->stream) rqb_stream_destroy(s->stream);
   if (cur != s->dev && cur >= 0) rqb_dev_set(cur);
   free(s);
+}
+
+void rqb_solver_destroy(rqb_solver *s) {
+  if (!s) return;
+  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  s->plan = NULL;
+  if (s->busy || s->batch_owner) { /* nothing queued may outlive the owner's use of the buffers */
+    int cur = rqb_dev_get();
+    if (cur != s->dev) rqb_dev_set(s->dev);
+    solver_wait(s);
+  }
+  if (s->broken) {
+    solver_release(s);
+    return;
+  }
+  pthread_mutex_lock(&g_shell_mu);
+  s->next_shell = g_shells;
+  g_shells = s;
+  pthread_mutex_unlock(&g_shell_mu);
+}
+
+/* free every cached solver context and pooled buffer (tests, long-lived hosts) */
+void rqb_release_cached(void) {
+  pthread_mutex_lock(&g_shell_mu);
+  rqb_solver *s = g_shells;
+  g_shells = NULL;
+  pthread_mutex_unlock(&g_shell_mu);
+  while (s) {
+    rqb_solver *n = s->next_shell;
+    solver_release(s);
+    s = n;
+  }
 }
 
 int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32_t max_out) {
@@ -193,43 +289,98 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     snprintf(g_err, sizeof(g_err), "no CUDA device visible: the nanorq_b200 hot path has no CPU fallback");
     return RQB_E_NODEVICE;
   }
-  rqb_solver *s = calloc(1, sizeof(*s));
+  if (!max_out) max_out = 1;
+  const int dev = rqb_dev_default();
+  rqb_solver *s = NULL;
+  pthread_mutex_lock(&g_shell_mu);
+  {
+    /* best fit, and never a context much larger than asked for: encoders and decoders
+     * of one block size must not keep taking each other's contexts */
+    rqb_solver **best = NULL;
+    for (rqb_solver **pp = &g_shells; *pp; pp = &(*pp)->next_shell) {
+      rqb_solver *c = *pp;
+      if (c->dev != dev || c->T != T || c->in_cap < max_in || c->out_cap < max_out) continue;
+      if (c->arena_cap < arena_rows_wanted(max_in, max_out, &P) * c->pitch) continue;
+      if ((size_t)c->in_cap > (size_t)max_in + max_in / 4 + 64 || (size_t)c->out_cap > (size_t)max_out + max_out / 4 + 64) continue;
+      if (!best || c->in_cap + c->out_cap < (*best)->in_cap + (*best)->out_cap) best = pp;
+    }
+    if (best) {
+      s = *best;
+      *best = s->next_shell;
+    }
+  }
+  pthread_mutex_unlock(&g_shell_mu);
+  if (s) {
+    s->K = K;
+    s->Kparams = Kparams;
+    s->P = P;
+    s->max_in = max_in;
+    s->max_out = max_out;
+    s->plan = NULL;
+    s->plan_shared = s->has_c = s->timed = 0;
+    s->cur_pages = NULL;
+    s->n_out_last = 0;
+    s->next_shell = NULL;
+    s->batch_owner = NULL;
+    if (bind_dev(s->dev)) return dev_fail(0, "rqb_solver_create bind");
+    if (solver_layout(s)) {
+      s->broken = 1;
+      rqb_solver_destroy(s);
+      return RQB_E_NODEVICE;
+    }
+    *out = s;
+    return 0;
+  }
+  s = calloc(1, sizeof(*s));
   s->K = K;
   s->Kparams = Kparams;
   s->T = T;
   s->pitch = round_up(T, 64);
   s->P = P;
-  s->max_in = max_in;
-  s->max_out = max_out ? max_out : 1;
-  s->dev = rqb_dev_default();
+  s->max_in = s->in_cap = max_in;
+  s->max_out = s->out_cap = max_out;
+  s->dev = dev;
+  s->arena_cap = pool_class(arena_rows_wanted(max_in, max_out, &P) * s->pitch);
   int e = bind_dev(s->dev);
   e = e ? e : rqb_stream_create(&s->stream);
   e = e ? e : rqb_event_create(&s->ev2);
   e = e ? e : rqb_event_create(&s->ev3);
   e = e ? e : rqb_event_create(&s->ev0);
   e = e ? e : rqb_event_create(&s->ev1);
-  e = e ? e : pool_get((void **)&s->h_in, (size_t)s->max_in * s->pitch, 1);
-  e = e ? e : pool_get((void **)&s->d_in, (size_t)s->max_in * s->pitch, 0);
-  e = e ? e : pool_get((void **)&s->d_c, (size_t)P.L * s->pitch, 0);
-  e = e ? e : pool_get((void **)&s->d_sym, (size_t)s->max_out * s->pitch, 0);
-  e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->max_out * s->pitch, 1);
-  e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->max_out * 4, 0);
+  e = e ? e : pool_get((void **)&s->h_in, (size_t)s->in_cap * s->pitch, 1);
+  e = e ? e : pool_get((void **)&s->d_arena, s->arena_cap, 0);
+  e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->out_cap * s->pitch, 1);
+  e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->out_cap * 4, 0);
   /* small control blocks are sent from PAGEABLE memory on purpose: cudaMemcpyAsync
    * stages a pageable source before it returns, so these buffers may be rewritten
    * for the next launch while earlier copies are still queued on the stream */
-  s->h_isi = malloc((size_t)s->max_out * 4);
+  s->h_isi = malloc((size_t)s->out_cap * 4);
   s->h_args = calloc(1, RQB_ARGS_BYTES);
   e = e ? e : pool_get((void **)&s->d_args, RQB_ARGS_BYTES, 0);
+  e = e ? e : solver_layout(s);
   if (e) {
     dev_fail(e, "rqb_solver_create allocation");
+    s->broken = 1;
     rqb_solver_destroy(s);
     return RQB_E_NODEVICE;
   }
   /* pad bytes of the staging rows must be zero: they are transformed too (pool
    * buffers are recycled, symbol bytes are always overwritten before use) */
   if (s->pitch > T)
-    for (uint32_t r = 0; r < s->max_in; r++) memset(s->h_in + (size_t)r * s->pitch + T, 0, s->pitch - T);
+    for (uint32_t r = 0; r < s->in_cap; r++) memset(s->h_in + (size_t)r * s->pitch + T, 0, s->pitch - T);
   *out = s;
+  return 0;
+}
+
+static int solver_wait(rqb_solver *s) {
+  if (s->batch_owner && s->batch_owner != s) {
+    /* a batched launch on another solver's stream works on this solver's rows */
+    DEV(rqb_stream_sync(s->batch_owner->stream));
+  }
+  s->batch_owner = NULL;
+  DEV(rqb_stream_sync(s->stream));
+  s->busy = 0;
+  s->pages_pending = 0;
   return 0;
 }
 
@@ -237,8 +388,9 @@ int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
   BIND(s->dev);
   if ((uint64_t)first + n > s->max_in) return RQB_E_ARG;
   if (!n) return 0;
-  DEV(rqb_copy_h2d(s->d_in + (size_t)first * s->pitch, s->h_in + (size_t)first * s->pitch,
-                   (size_t)n * s->pitch, s->stream));
+  s->busy = 1;
+  DEV(rqb_copy_h2d(ROW_PTR(s, RQB_SP_IN, first), s->h_in + (size_t)first * s->pitch, (size_t)n * s->pitch,
+                   s->stream));
   return 0;
 }
 
@@ -265,11 +417,12 @@ int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out) {
 static int ensure_cap(rqb_solver *s, void **buf, size_t *cap, size_t need, int pinned) {
   if (need <= *cap) return 0;
   if (*buf) {
-    DEV(rqb_stream_sync(s->stream));
+    { int _w = solver_wait(s); if (_w) return _w; }
     pool_put(*buf, *cap, pinned);
     *buf = NULL;
     *cap = 0;
   }
+  need += need / 8; /* programs of one block size differ a little from block to block: do not regrow for each */
   DEV(pool_get(buf, need, pinned));
   *cap = pool_class(need);
   return 0;
@@ -277,19 +430,34 @@ static int ensure_cap(rqb_solver *s, void **buf, size_t *cap, size_t need, int p
 
 static int solver_set_args(rqb_solver *s) {
   const rqb_plan *p = s->plan;
-  int rc = ensure_cap(s, (void **)&s->d_ws, &s->d_ws_cap, (size_t)p->n_ws_rows * s->pitch, 0);
-  if (rc) return rc;
+  if (memcmp(p->row0, s->row0, sizeof(s->row0)) || p->zero_row != s->zero_row) {
+    snprintf(g_err, sizeof(g_err), "solve program was built for another arena layout");
+    return RQB_E_ARG;
+  }
+  size_t need = (size_t)p->n_rows * s->pitch;
+  if (need > s->arena_cap) {
+    /* the program needs more working rows than the arena has: move the fixed spaces
+     * (uploaded symbols included) into a larger one */
+    uint8_t *bigger = NULL;
+    size_t cap = pool_class(need + need / 8);
+    int w = solver_wait(s);
+    if (w) return w;
+    DEV(pool_get((void **)&bigger, cap, 0));
+    DEV(rqb_copy_d2d(bigger, s->d_arena, (size_t)s->row0[RQB_SP_WS] * s->pitch, s->stream));
+    w = solver_wait(s);
+    if (w) return w;
+    pool_put(s->d_arena, s->arena_cap, 0);
+    s->d_arena = bigger;
+    s->arena_cap = cap;
+  }
   rqb_solve_args *a = s->h_args;
   memset(a, 0, sizeof(*a));
-  a->base[RQB_SP_IN] = s->d_in;
-  a->base[RQB_SP_WS] = s->d_ws;
-  a->base[RQB_SP_C] = s->d_c;
-  a->base[RQB_SP_SYM] = s->d_sym;
+  a->base = s->d_arena;
   a->pages = s->cur_pages;
   a->pitch = (uint32_t)s->pitch;
   a->n_pages = p->n_pages;
   a->width = (uint32_t)round_up(s->T, 16);
-  a->pad = s->max_in; /* rows of the input space */
+  s->busy = 1;
   DEV(rqb_copy_h2d(s->d_args, s->h_args, sizeof(*a), s->stream));
   s->has_c = p->n_c_rows != 0;
   s->n_out_last = p->n_out;
@@ -307,8 +475,12 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   pr.want_c = req->want_c;
   pr.n_out = (int)req->n_out;
   pr.out_isi = req->out_isi;
+  pr.in_rows = s->max_in;
+  pr.sym_rows = s->max_out;
   rqb_plan *p = NULL;
+  PF_T0;
   int rc = rqb_plan_build(&pr, &p);
+  PF(RQB_PF_REP_PLAN);
   if (rc == 1) return RQB_NEED_MORE;
   if (rc) {
     snprintf(g_err, sizeof(g_err), "rqb_plan_build failed (%d)", rc);
@@ -323,11 +495,19 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   if (rc) return rc;
   /* the pages go through pinned memory so that the copy is truly asynchronous; the
    * staging buffer may be rewritten by the next plan only after this copy has run */
-  DEV(rqb_stream_sync(s->stream));
+  if (s->pages_pending) {
+    int w = solver_wait(s);
+    if (w) return w;
+  }
   memcpy(s->h_pages, p->pages, pb);
+  s->pages_pending = 1;
+  s->busy = 1;
   DEV(rqb_copy_h2d(s->d_pages, s->h_pages, pb, s->stream));
   s->cur_pages = s->d_pages;
-  return solver_set_args(s);
+  PF(RQB_PF_REP_PAGES);
+  rc = solver_set_args(s);
+  PF(RQB_PF_REP_ARGS);
+  return rc;
 }
 
 int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
@@ -336,7 +516,9 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
   pthread_mutex_lock(&g_plan_mu);
   enc_plan *e = g_enc_plans;
   for (; e; e = e->next)
-    if (e->K == s->K && e->Kparams == s->Kparams && e->want_c == want_c && e->n_out == n_rep && e->dev == s->dev) break;
+    if (e->K == s->K && e->Kparams == s->Kparams && e->want_c == want_c && e->n_out == n_rep && e->dev == s->dev &&
+        e->in_rows == s->max_in && e->sym_rows == s->max_out)
+      break;
   if (!e) {
     const int Kp = s->P.Kprime;
     uint32_t *isi = malloc(sizeof(uint32_t) * (size_t)Kp), *in_row = malloc(sizeof(uint32_t) * (size_t)Kp);
@@ -346,7 +528,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
       in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
     }
     for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
-    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi};
+    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out};
     rqb_plan *p = NULL;
     int rc = rqb_plan_build(&pr, &p);
     free(isi);
@@ -362,6 +544,8 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
     e->Kparams = s->Kparams;
     e->want_c = want_c;
     e->n_out = n_rep;
+    e->in_rows = s->max_in;
+    e->sym_rows = s->max_out;
     e->dev = s->dev;
     e->plan = p;
     size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
@@ -386,6 +570,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
 int rqb_solver_run(rqb_solver *s) {
   if (!s->plan) return RQB_E_ARG;
   BIND(s->dev);
+  s->busy = 1;
   DEV(rqb_event_record(s->ev0, s->stream));
   DEV(rqb_launch_solve(s->d_args, 1, s->h_args->width, s->stream));
   DEV(rqb_event_record(s->ev1, s->stream));
@@ -396,6 +581,7 @@ int rqb_solver_run(rqb_solver *s) {
 /* time a region of work queued on this solver's stream with CUDA events */
 int rqb_solver_mark(rqb_solver *s, int end) {
   BIND(s->dev);
+  s->busy = 1;
   DEV(rqb_event_record(end ? s->ev3 : s->ev2, s->stream));
   return 0;
 }
@@ -416,9 +602,14 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   rqb_solve_args *h = own->h_args + 1, *d = own->d_args + 1;
   for (int k = 0; k < n; k++) {
     if (!sv[k]->plan || sv[k]->T != own->T || sv[k]->dev != own->dev) return RQB_E_ARG;
-    if (sv[k] != own) DEV(rqb_stream_sync(sv[k]->stream)); /* its uploads must have landed */
+    if (sv[k] != own && sv[k]->busy) { /* its uploads must have landed */
+      int w = solver_wait(sv[k]);
+      if (w) return w;
+    }
     h[k] = *sv[k]->h_args;
+    sv[k]->batch_owner = own;
   }
+  own->busy = 1;
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
   DEV(rqb_event_record(own->ev0, own->stream));
   DEV(rqb_launch_solve(d, n, h[0].width, own->stream));
@@ -437,16 +628,17 @@ int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n) {
   BIND(s->dev);
   if (!s->has_c || n > s->max_out) return RQB_E_ARG;
   memcpy(s->h_isi, isi, (size_t)n * 4);
+  s->busy = 1;
   DEV(rqb_copy_h2d(s->d_isi, s->h_isi, (size_t)n * 4, s->stream));
-  DEV(rqb_launch_lt(&s->P, s->d_c, (uint32_t)s->pitch, s->d_isi, n, s->d_sym, (uint32_t)s->pitch,
-                    (uint32_t)round_up(s->T, 16), s->stream));
+  DEV(rqb_launch_lt(&s->P, ROW_PTR(s, RQB_SP_C, 0), (uint32_t)s->pitch, s->d_isi, n, ROW_PTR(s, RQB_SP_SYM, 0),
+                    (uint32_t)s->pitch, (uint32_t)round_up(s->T, 16), s->stream));
   s->n_out_last = n;
   return 0;
 }
 
 int rqb_solver_sync(rqb_solver *s) {
   BIND(s->dev);
-  DEV(rqb_stream_sync(s->stream));
+  { int _w = solver_wait(s); if (_w) return _w; }
   return 0;
 }
 
@@ -462,32 +654,55 @@ int rqb_solver_fetch_syms(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *ds
   BIND(s->dev);
   if ((uint64_t)first + n > s->max_out) return RQB_E_ARG;
   if (!n) return 0;
-  DEV(rqb_copy_d2h(s->h_sym + (size_t)first * s->pitch, s->d_sym + (size_t)first * s->pitch,
-                   (size_t)n * s->pitch, s->stream));
-  DEV(rqb_stream_sync(s->stream));
+  s->busy = 1;
+  DEV(rqb_copy_d2h(s->h_sym + (size_t)first * s->pitch, ROW_PTR(s, RQB_SP_SYM, first), (size_t)n * s->pitch,
+                   s->stream));
+  { int _w = solver_wait(s); if (_w) return _w; }
   if (dst)
     for (uint32_t k = 0; k < n; k++)
       memcpy(dst + (size_t)k * dst_pitch, s->h_sym + (size_t)(first + k) * s->pitch, s->T);
   return 0;
 }
 
+/* queue the copy of emitted symbols [first, first+n) into the pinned mirror without
+ * waiting; rqb_solver_sync() (or any fetch) completes it */
+int rqb_solver_fetch_syms_async(rqb_solver *s, uint32_t first, uint32_t n) {
+  BIND(s->dev);
+  if ((uint64_t)first + n > s->max_out) return RQB_E_ARG;
+  if (!n) return 0;
+  s->busy = 1;
+  DEV(rqb_copy_d2h(s->h_sym + (size_t)first * s->pitch, ROW_PTR(s, RQB_SP_SYM, first), (size_t)n * s->pitch,
+                   s->stream));
+  return 0;
+}
+
 int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch) {
   BIND(s->dev);
   if (!s->has_c || (uint64_t)first + n > (uint32_t)s->P.L) return RQB_E_ARG;
-  DEV(rqb_copy2d_d2h(dst, dst_pitch, s->d_c + (size_t)first * s->pitch, s->pitch, s->T, n, s->stream));
-  DEV(rqb_stream_sync(s->stream));
+  s->busy = 1;
+  DEV(rqb_copy2d_d2h(dst, dst_pitch, ROW_PTR(s, RQB_SP_C, first), s->pitch, s->T, n, s->stream));
+  { int _w = solver_wait(s); if (_w) return _w; }
   return 0;
 }
 
 /* ------------------------------------------------ host-only plan access */
 int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out) {
-  rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi};
+  rqb_params P;
+  memset(out, 0, sizeof(*out));
+  if (rqb_params_init(K, &P) || req->overhead < 0) return RQB_E_ARG;
+  uint32_t in_rows = 1; /* the smallest input space that holds every row the request names */
+  for (int k = 0; k < P.Kprime + req->overhead; k++)
+    if (req->in_row[k] != RQB_NO_ROW && req->in_row[k] >= in_rows) in_rows = req->in_row[k] + 1;
+  rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi,
+                         in_rows, req->n_out ? req->n_out : 1};
   rqb_plan *p = NULL;
   int rc = rqb_plan_build(&pr, &p);
-  memset(out, 0, sizeof(*out));
   if (rc == 1) return RQB_NEED_MORE;
   if (rc) return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
   out->n_ws_rows = p->n_ws_rows;
+  memcpy(out->row0, p->row0, sizeof(out->row0));
+  out->zero_row = p->zero_row;
+  out->n_rows = p->n_rows;
   out->n_pages = p->n_pages;
   out->page_bytes = RQB_PAGE_BYTES;
   out->pages = p->pages;

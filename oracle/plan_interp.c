@@ -26,42 +26,44 @@ static uint8_t gmul(uint8_t a, uint8_t b) { /* shift-and-add, poly 0x11D */
 }
 
 typedef struct {
-  uint8_t *base[4];
-  size_t pitch[4], rows[4];
-  uint32_t *wstamp[4], *wowner[4]; /* level id / task that last wrote the row */
+  uint8_t *arena;
+  size_t pitch, rows;
+  uint32_t *wstamp, *wowner; /* level id / task that last wrote the row */
 } spaces;
 
-static uint8_t *row_ptr(spaces *sp, uint32_t ref, int *rc) {
-  uint32_t s = (ref >> RQB_IDX_BITS) & 3u, idx = ref & (RQB_MAX_ROWS - 1);
-  if (idx >= sp->rows[s]) {
+static uint8_t *row_ptr(spaces *sp, uint32_t row, int *rc) {
+  if (row >= sp->rows) {
     *rc = 11;
     return NULL;
   }
-  return sp->base[s] + (size_t)idx * sp->pitch[s];
+  return sp->arena + (size_t)row * sp->pitch;
 }
 
-/* returns 0 ok, 10 = intra-level hazard, 11 = malformed, 12 = misaligned, 13 = too many sources,
- * 14 = a task writes the input space */
-int rqb_interp_run(uint32_t n_ws_rows, uint32_t n_pages, const uint8_t *pages, const uint8_t *in, size_t in_rows,
-                   size_t in_pitch, size_t T, uint8_t *c_out, size_t c_rows, size_t c_pitch, uint8_t *sym_out,
-                   size_t sym_rows, size_t sym_pitch) {
+/* Runs a program on an arena laid out as rqb_program.h says: row0[] = first row of
+ * the spaces IN, SYM, C, WS; zero_row; n_rows in total.
+ * returns 0 ok, 10 = intra-level hazard, 11 = malformed, 12 = misaligned, 13 = too many sources,
+ * 14 = a task writes the input space or the ZERO row, 15 = an XOR list is not padded with the ZERO row */
+int rqb_interp_run(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, uint32_t n_pages, const uint8_t *pages,
+                   const uint8_t *in, size_t in_rows, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_rows,
+                   size_t c_pitch, uint8_t *sym_out, size_t sym_rows, size_t sym_pitch) {
   spaces sp;
   memset(&sp, 0, sizeof(sp));
-  uint8_t *ws = malloc((size_t)n_ws_rows * T + 1);
-  memset(ws, 0xA5, (size_t)n_ws_rows * T + 1); /* working rows start undefined, like device memory */
-  sp.base[RQB_SP_IN] = (uint8_t *)in; sp.pitch[RQB_SP_IN] = in_pitch; sp.rows[RQB_SP_IN] = in_rows;
-  sp.base[RQB_SP_WS] = ws; sp.pitch[RQB_SP_WS] = T; sp.rows[RQB_SP_WS] = n_ws_rows;
-  sp.base[RQB_SP_C] = c_out; sp.pitch[RQB_SP_C] = c_pitch; sp.rows[RQB_SP_C] = c_rows;
-  sp.base[RQB_SP_SYM] = sym_out; sp.pitch[RQB_SP_SYM] = sym_pitch; sp.rows[RQB_SP_SYM] = sym_rows;
-  for (int s = 0; s < 4; s++) {
-    sp.wstamp[s] = calloc(sp.rows[s] + 1, sizeof(uint32_t));
-    sp.wowner[s] = calloc(sp.rows[s] + 1, sizeof(uint32_t));
-  }
+  if (row0[RQB_SP_IN] != 0 || row0[RQB_SP_SYM] < in_rows || row0[RQB_SP_C] < row0[RQB_SP_SYM] + sym_rows ||
+      zero_row < row0[RQB_SP_C] + c_rows || row0[RQB_SP_WS] != zero_row + 1 || n_rows < row0[RQB_SP_WS])
+    return 11;
+  sp.rows = n_rows;
+  sp.pitch = T;
+  sp.arena = malloc((size_t)n_rows * T + 1);
+  memset(sp.arena, 0xA5, (size_t)n_rows * T + 1); /* rows start undefined, like device memory */
+  for (size_t r = 0; r < in_rows; r++) memcpy(sp.arena + r * T, in + r * in_pitch, T);
+  memset(sp.arena + (size_t)zero_row * T, 0, T);
+  sp.wstamp = calloc((size_t)n_rows + 1, sizeof(uint32_t));
+  sp.wowner = calloc((size_t)n_rows + 1, sizeof(uint32_t));
   uint8_t *tmp = malloc(T ? T : 1);
   int rc = 0;
   uint32_t level_id = 0;
-#define STAMP(ref) sp.wstamp[((ref) >> RQB_IDX_BITS) & 3u][(ref) & (RQB_MAX_ROWS - 1)]
-#define OWNER(ref) sp.wowner[((ref) >> RQB_IDX_BITS) & 3u][(ref) & (RQB_MAX_ROWS - 1)]
+#define STAMP(ref) sp.wstamp[(ref)]
+#define OWNER(ref) sp.wowner[(ref)]
   for (uint32_t pg = 0; pg < n_pages && !rc; pg++) {
     const uint8_t *page = pages + (size_t)pg * RQB_PAGE_BYTES;
     const rqb_page_hdr *ph = (const rqb_page_hdr *)page;
@@ -75,8 +77,8 @@ int rqb_interp_run(uint32_t n_ws_rows, uint32_t n_pages, const uint8_t *pages, c
       for (uint32_t k = 0; k < lh->n_tasks && !rc; k++) {
         const rqb_task *t = &tasks[k];
         uint32_t cnt = t->kind == RQB_T_SCAN ? t->nsrc : 1u;
-        if (((t->dst >> RQB_IDX_BITS) & 3u) == RQB_SP_IN) { rc = 14; break; }
-        if (t->kind == RQB_T_SCAN && ((t->dst >> RQB_IDX_BITS) & 3u) != RQB_SP_WS) { rc = 11; break; }
+        if (t->dst < row0[RQB_SP_SYM] || t->dst == zero_row) { rc = 14; break; }
+        if (t->kind == RQB_T_SCAN && t->dst < row0[RQB_SP_WS]) { rc = 11; break; }
         for (uint32_t q = 0; q < cnt; q++) {
           uint32_t ref = t->dst + q;
           if (!row_ptr(&sp, ref, &rc)) break;
@@ -95,9 +97,16 @@ int rqb_interp_run(uint32_t n_ws_rows, uint32_t n_pages, const uint8_t *pages, c
           case RQB_T_XOR:
           case RQB_T_GF: {
             if (t->nsrc > RQB_MAX_SRCS) { rc = 13; break; }
+            if (t->kind == RQB_T_XOR) { /* the kernel loads exactly 4 or 8 rows */
+              uint32_t padded = t->nsrc <= 4 ? 4u : 8u;
+              if (t->src_off + (size_t)padded * 4 > RQB_PAGE_BYTES) { rc = 11; break; }
+              for (uint32_t q = t->nsrc; q < padded; q++)
+                if (s32[q] != zero_row) rc = 15;
+              if (rc) break;
+            }
             memset(tmp, 0, T);
             for (uint32_t q = 0; q < t->nsrc && !rc; q++) {
-              uint32_t ref = s32[q] & RQB_REF_MASK;
+              uint32_t ref = t->kind == RQB_T_GF ? (s32[q] & RQB_REF_MASK) : s32[q];
               uint8_t beta = t->kind == RQB_T_GF ? (uint8_t)(s32[q] >> 24) : 1;
               const uint8_t *src = row_ptr(&sp, ref, &rc);
               if (!src) break;
@@ -110,7 +119,7 @@ int rqb_interp_run(uint32_t n_ws_rows, uint32_t n_pages, const uint8_t *pages, c
           case RQB_T_SCAN: {
             memset(tmp, 0, T);
             for (uint32_t q = 0; q < t->nsrc && !rc; q++) {
-              uint32_t ref = s32[q] & RQB_REF_MASK;
+              uint32_t ref = s32[q];
               const uint8_t *src = NULL;
               if (ref != RQB_REF_NONE) {
                 src = row_ptr(&sp, ref, &rc);
@@ -129,11 +138,11 @@ int rqb_interp_run(uint32_t n_ws_rows, uint32_t n_pages, const uint8_t *pages, c
       off = lh->next_off;
     }
   }
-  for (int s = 0; s < 4; s++) {
-    free(sp.wstamp[s]);
-    free(sp.wowner[s]);
-  }
-  free(ws);
+  for (size_t r = 0; r < c_rows; r++) memcpy(c_out + r * c_pitch, sp.arena + ((size_t)row0[RQB_SP_C] + r) * T, T);
+  for (size_t r = 0; r < sym_rows; r++) memcpy(sym_out + r * sym_pitch, sp.arena + ((size_t)row0[RQB_SP_SYM] + r) * T, T);
+  free(sp.wstamp);
+  free(sp.wowner);
+  free(sp.arena);
   free(tmp);
   return rc;
 }

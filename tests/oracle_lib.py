@@ -123,17 +123,21 @@ _interp = None
 def interp_run(blob, inp, T, n_c, n_out):
     """Run a plan blob (nanorq_b200.plan_blob) on the CPU interpreter.
     -> (rc, C[n_c,T], syms[n_out,T]); rc 10 = hazard inside a level, 12 = misaligned,
-    13 = more than RQB_MAX_SRCS sources in a task."""
+    13 = more than RQB_MAX_SRCS sources in a task, 14 = writes the input space / ZERO row,
+    15 = an XOR source list is not padded with the ZERO row."""
     global _interp
     if _interp is None:
         _interp = C.CDLL(INTERP_SO)
         sz = C.c_size_t
-        _interp.rqb_interp_run.argtypes = [C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz, u8p, sz, sz, u8p, sz, sz]
+        _interp.rqb_interp_run.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz,
+                                           u8p, sz, sz, u8p, sz, sz]
     inp = np.ascontiguousarray(inp, dtype=np.uint8)
+    row0 = np.asarray(blob["row0"], dtype=np.uint32)
+    in_rows = min(inp.shape[0], int(row0[1]))  # rows past the plan's input space are never referenced
     cout = np.full((max(n_c, 1), T), 0x5A, np.uint8)
     sout = np.full((max(n_out, 1), T), 0x5A, np.uint8)
-    rc = _interp.rqb_interp_run(blob["n_ws_rows"], blob["n_pages"], ptr(blob["pages"]), ptr(inp), inp.shape[0],
-                                inp.strides[0], T, ptr(cout), cout.shape[0], T, ptr(sout), sout.shape[0], T)
+    rc = _interp.rqb_interp_run(ptr(row0, u32p), blob["zero_row"], blob["n_rows"], blob["n_pages"], ptr(blob["pages"]),
+                                ptr(inp), in_rows, inp.strides[0], T, ptr(cout), n_c, T, ptr(sout), n_out, T)
     return rc, cout[:n_c], sout[:n_out]
 
 
