@@ -319,7 +319,8 @@ def run_own(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through nanorq.h (bench/rq_roundtrip.c)
     rt_so = os.path.join(ROOT, "nanorq_b200", "librq_roundtrip.so")
-    threads = max(1, min(args.threads or (os.cpu_count() or 1) // world, 64))
+    # 1.25 worker threads per host core: a thread that waits for its block's solve yields its core
+    threads = max(1, min(args.threads or (5 * (os.cpu_count() or 1)) // (4 * world), 64))
     for w in range(0 if args.skip_e2e else max(args.warmup, 3)):
         roundtrip(rt_so, min(NB, 2 * threads), threads, 900 + w)
     barrier()

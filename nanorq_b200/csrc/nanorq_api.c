@@ -331,6 +331,7 @@ void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
 void nanorq_free(nanorq *rq) { /* :298-307 (NULL-safe here) */
   if (!rq) return;
   PF_T0;
+  rqb_copy_fence();
   for (int sbn = 0; sbn < Z_MAX; sbn++) nanorq_encoder_cleanup(rq, (uint8_t)sbn);
   free(rq);
   PF(RQB_PF_FREE);
@@ -354,7 +355,7 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
     PF(RQB_PF_ADD_COPY);
     transfer_symbol(rq, sbn, esi, data, io, 1); /* source symbols go straight to the output */
     PF(RQB_PF_ADD_WRITE);
-    b->gaps--;
+    if (--b->gaps == 0) rqb_copy_fence(); /* the block's output is complete: publish the streamed rows */
   } else {
     uint32_t row = (uint32_t)rq->P.Kprime + (uint32_t)b->nrep;
     if (row >= b->in_cap) return NANORQ_SYM_ERR;
@@ -436,6 +437,7 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
     }
     b->gaps = 0;
     ok = true;
+    rqb_copy_fence();
     PF(RQB_PF_REP_WRITE);
   } else {
     rqb_solver_sync(b->sv);

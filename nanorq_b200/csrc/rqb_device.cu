@@ -20,6 +20,7 @@
 //
 // All arithmetic is GF(2)/GF(256) integer work (poly 0x11D); no tensor cores.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <atomic>
 #include <cstdint>
@@ -413,20 +414,39 @@ int rqb_stream_create(void **s) {
   return 0;
 }
 int rqb_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
-// Waiting threads SLEEP instead of spinning (cudaStreamSynchronize spins by default):
-// the host side runs more worker threads than cores so that planning one block
-// overlaps the device work of another.  A per-thread, per-device blocking-sync
-// event is recorded behind the stream's work and waited on.
+// How a host thread waits for its stream (NANORQ_B200_WAIT = yield | spin | block):
+//   yield (default)  poll cudaStreamQuery and sched_yield() between polls: as prompt as
+//                    spinning when every thread has a core, and a waiting thread gives its
+//                    core away when there are more worker threads than cores;
+//   spin             cudaStreamSynchronize (busy-waits);
+//   block            a blocking-sync event: the thread sleeps until the interrupt.  Measured
+//                    on the B200 hosts the wake-up costs ~0.5-1 ms, as long as a whole
+//                    K=4096 solve, so this is only for hosts that must not burn cycles.
 int rqb_stream_sync(void *s) {
   static thread_local cudaEvent_t ev[64];
-  static thread_local bool spin_checked = false, spin = false;
-  if (!spin_checked) {
-    const char *e = getenv("NANORQ_B200_SPIN_WAIT");
-    spin = e && e[0] == '1';
-    spin_checked = true;
+  static std::atomic<int> mode{-1};
+  int m = mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char *e = getenv("NANORQ_B200_WAIT");
+    m = 0;
+    if (e && !strcmp(e, "spin")) m = 1;
+    if (e && !strcmp(e, "block")) m = 2;
+    mode.store(m, std::memory_order_relaxed);
+  }
+  if (m == 0) {
+    for (unsigned spins = 0;; spins++) {
+      cudaError_t q = cudaStreamQuery((cudaStream_t)s);
+      if (q == cudaSuccess) return 0;
+      if (q != cudaErrorNotReady) return fail(q, "cudaStreamQuery");
+      if (spins < 64) {
+        for (int k = 0; k < 32; k++) __builtin_ia32_pause();
+      } else {
+        sched_yield();
+      }
+    }
   }
   int dev = 0;
-  if (spin || cudaGetDevice(&dev) != cudaSuccess || dev >= 64) {
+  if (m == 1 || cudaGetDevice(&dev) != cudaSuccess || dev >= 64) {
     CK(cudaStreamSynchronize((cudaStream_t)s));
     return 0;
   }

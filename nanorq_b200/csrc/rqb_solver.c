@@ -31,6 +31,7 @@ static int dev_fail(int e, const char *what) {
   } while (0)
 
 /* ------------------------------------------------ host time accounting */
+#include "rqb_hostcopy.h"
 #include "rqb_prof.h"
 static _Atomic unsigned long long g_prof_ns[RQB_PF_COUNT];
 static int g_prof_on = -1;
@@ -388,6 +389,7 @@ int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
   BIND(s->dev);
   if ((uint64_t)first + n > s->max_in) return RQB_E_ARG;
   if (!n) return 0;
+  rqb_copy_fence(); /* the staging rows may have been written with non-temporal stores */
   s->busy = 1;
   DEV(rqb_copy_h2d(ROW_PTR(s, RQB_SP_IN, first), s->h_in + (size_t)first * s->pitch, (size_t)n * s->pitch,
                    s->stream));
