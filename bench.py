@@ -202,6 +202,7 @@ def run_own(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import nanorq_b200 as nb
+    from nanorq_b200 import sharding
 
     if nb.device_count() <= 0:
         raise SystemExit("no CUDA device: the nanorq_b200 hot path has no CPU fallback")
@@ -223,11 +224,7 @@ def run_own(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device="cuda")
 
     NB = args.blocks
     encs, decs, checks = build_blocks(nb, NB, seed0=1000 * rank)
