@@ -383,8 +383,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--blocks", type=int, default=88,
-                    help="source blocks per GPU per step (44 blocks x 10 column slices fill the 444 resident CTA slots once)")
+    ap.add_argument("--blocks", type=int, default=118,
+                    help="source blocks per GPU per step (59 blocks x 10 column slices fill the 148 x 4 resident CTA slots once)")
     ap.add_argument("--threads", type=int, default=0, help="host threads for the e2e arm (default: cores / ranks)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")

@@ -116,7 +116,7 @@ enum {
   SC_PCOL, SC_UCOL, SC_STK1, SC_STK2, SC_LEVEL, SC_G, SC_LOWROWS, SC_SB, SC_TB, SC_XPTR, SC_XIDX, SC_SH,
   SC_HB1, SC_HB2, SC_YBUF, SC_ACCBUF, SC_PIVROW, SC_PIVCOL, SC_FREECOLS, SC_Q, SC_TQ, SC_TMP, SC_CSLOT,
   SC_FPTR, SC_FITEMS, SC_PFIRST, SC_PLEVEL, SC_PPTR, SC_PITEMS, SC_CURLOC, SC_TASKS, SC_SRCS, SC_ORDER,
-  SC_LVLCNT, SC_CS, SC_COEF, SC_COUNT
+  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_COUNT
 };
 typedef struct {
   void *p[SC_COUNT];
@@ -355,6 +355,112 @@ void rqb_plan_free(rqb_plan *p) {
   pthread_mutex_unlock(&g_plans_mu);
 }
 
+/* ------------------------------------------------- per-K' matrix cache
+ * The part of the constraint matrix that does not depend on which symbols were
+ * received: the S LDPC rows (lib/precode.c:34-58) and the LT row of every
+ * source/padding ISI 0..K'-1 (params_set_idxs, lib/params.c:47-65), as CSR, plus
+ * each row's number of non-zeros in the columns [0, W).  Built once per K'. */
+typedef struct base_matrix {
+  int Kp;
+  int *rptr; /* S + H + K' + 1 */
+  int *cidx;
+  int *deg;  /* S + H + K' */
+  struct base_matrix *next;
+} base_matrix;
+static base_matrix *g_base[64];
+static pthread_mutex_t g_base_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static const base_matrix *base_get(const rqb_params *P) {
+  const int S = P->S, H = P->H, W = P->W, Kp = P->Kprime, B = P->B;
+  base_matrix **slot = &g_base[(unsigned)Kp % 64u];
+  pthread_mutex_lock(&g_base_mu); /* held for a list walk of a few entries; building happens once per K' */
+  base_matrix *m = *slot;
+  while (m && m->Kp != Kp) m = m->next;
+  if (!m) {
+    const int rows = S + H + Kp;
+    m = calloc(1, sizeof(*m));
+    m->Kp = Kp;
+    m->rptr = calloc((size_t)rows + 2, sizeof(int));
+    m->deg = calloc((size_t)rows + 1, sizeof(int));
+    m->cidx = malloc(sizeof(int) * ((size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)Kp + 16));
+    int *rptr = m->rptr, *cidx = m->cidx;
+    for (int col = 0; col < B; col++) {
+      int sub = col / S;
+      rptr[1 + col % S]++;
+      rptr[1 + (col + sub + 1) % S]++;
+      rptr[1 + (col + 2 * (sub + 1)) % S]++;
+    }
+    for (int r = 0; r < S; r++) rptr[1 + r] += 3;
+    int acc = 0;
+    for (int r = 0; r < S; r++) {
+      int c = rptr[1 + r];
+      rptr[r] = acc;
+      acc += c;
+    }
+    for (int r = S; r <= S + H; r++) rptr[r] = acc;
+    int *cur = malloc(sizeof(int) * (size_t)(S + 1));
+    memcpy(cur, rptr, sizeof(int) * (size_t)S);
+    for (int col = 0; col < B; col++) {
+      int sub = col / S;
+      cidx[cur[col % S]++] = col;
+      cidx[cur[(col + sub + 1) % S]++] = col;
+      cidx[cur[(col + 2 * (sub + 1)) % S]++] = col;
+    }
+    for (int r = 0; r < S; r++) {
+      cidx[cur[r]++] = B + r;
+      cidx[cur[r]++] = W + r % P->P;
+      cidx[cur[r]++] = W + (r + 1) % P->P;
+    }
+    free(cur);
+    uint32_t idx[RQB_MAX_LT_DEGREE];
+    for (int k = 0; k < Kp; k++) {
+      int cnt = rqb_host_lt_indices(P, (uint32_t)k, idx);
+      for (int q = 0; q < cnt; q++) cidx[acc + q] = (int)idx[q];
+      acc += cnt;
+      rptr[S + H + k + 1] = acc;
+    }
+    for (int r = 0; r < rows; r++)
+      for (int k = rptr[r]; k < rptr[r + 1]; k++) m->deg[r] += (cidx[k] < W);
+    m->next = *slot;
+    *slot = m;
+  }
+  pthread_mutex_unlock(&g_base_mu);
+  return m;
+}
+
+/* sort the n pairs (rd[k], it[k]) by rd ascending, stable.  Short lists by insertion;
+ * long ones (LDPC rows carry ~90 terms) by an 8-bit LSD radix over the level. */
+static void sort_by_level(int *rd, int *it, int n, int maxkey, uint64_t *tmp /* 2n */) {
+  if (n <= 20) {
+    for (int a = 1; a < n; a++) {
+      int lv = rd[a], q = it[a], j = a;
+      while (j > 0 && rd[j - 1] > lv) {
+        rd[j] = rd[j - 1];
+        it[j] = it[j - 1];
+        j--;
+      }
+      rd[j] = lv;
+      it[j] = q;
+    }
+    return;
+  }
+  uint64_t *x = tmp, *y = tmp + n;
+  for (int k = 0; k < n; k++) x[k] = ((uint64_t)(uint32_t)rd[k] << 32) | (uint32_t)it[k];
+  for (int shift = 32; shift < 64 && (maxkey >> (shift - 32)) != 0; shift += 8) {
+    int cnt[257] = {0};
+    for (int k = 0; k < n; k++) cnt[((x[k] >> shift) & 255u) + 1]++;
+    for (int k = 0; k < 256; k++) cnt[k + 1] += cnt[k];
+    for (int k = 0; k < n; k++) y[cnt[(x[k] >> shift) & 255u]++] = x[k];
+    uint64_t *t = x;
+    x = y;
+    y = t;
+  }
+  for (int k = 0; k < n; k++) {
+    rd[k] = (int)(x[k] >> 32);
+    it[k] = (int)(uint32_t)x[k];
+  }
+}
+
 /* ---------------------------------------------------------------- planner */
 #define NONE_REF RQB_REF_NONE /* "this row is all zero / has no location" */
 
@@ -375,44 +481,39 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
 
   /* ---- 1. sparse matrix A, rows: [0,S) LDPC, [S,S+H) HDPC (kept empty, closed form),
    *         [S+H, R) LT rows.  Same contents as precode_matrix_gen (+patching). */
-  int *rptr = sc_buf(sc, SC_RPTR, ((size_t)R + 2) * sizeof(int), 1);
-  {
-    for (int col = 0; col < B; col++) {
-      int sub = col / S;
-      rptr[1 + col % S]++;
-      rptr[1 + (col + sub + 1) % S]++;
-      rptr[1 + (col + 2 * (sub + 1)) % S]++;
-    }
-    for (int r = 0; r < S; r++) rptr[1 + r] += 3;
-  }
+  const base_matrix *bm = base_get(&P);
+  if (!bm) return -6;
+  int *rptr = sc_buf(sc, SC_RPTR, ((size_t)R + 2) * sizeof(int), 0);
   size_t cap = (size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)nlt + 16;
   int *cidx = sc_buf(sc, SC_CIDX, cap * sizeof(int), 0);
+  int *deg = sc_buf(sc, SC_DEG, (size_t)R * sizeof(int), 0); /* non-zeros in the columns [0, W) */
   {
-    int acc = 0;
-    for (int r = 0; r < S; r++) {
-      int c = rptr[1 + r];
-      rptr[r] = acc;
-      acc += c;
-    }
-    for (int r = S; r <= S + H; r++) rptr[r] = acc;
-    int *cur = sc_buf(sc, SC_CUR, sizeof(int) * (size_t)(S > L ? S : L), 0);
-    memcpy(cur, rptr, sizeof(int) * (size_t)S);
-    for (int col = 0; col < B; col++) {
-      int sub = col / S;
-      cidx[cur[col % S]++] = col;
-      cidx[cur[(col + sub + 1) % S]++] = col;
-      cidx[cur[(col + 2 * (sub + 1)) % S]++] = col;
-    }
-    for (int r = 0; r < S; r++) {
-      cidx[cur[r]++] = B + r;
-      cidx[cur[r]++] = W + r % P.P;
-      cidx[cur[r]++] = W + (r + 1) % P.P;
-    }
+    /* LDPC rows and the LT rows of the source symbols (ISI k in row k) are the same for
+     * every block of this K': copied from the per-K' cache; only the rows of repair
+     * symbols are generated (Tuple + index walk, ~100 ns each) */
+    const int fixed = bm->rptr[S + H];
+    memcpy(rptr, bm->rptr, sizeof(int) * (size_t)(S + H + 1));
+    memcpy(cidx, bm->cidx, sizeof(int) * (size_t)fixed);
+    memcpy(deg, bm->deg, sizeof(int) * (size_t)(S + H));
+    int acc = fixed;
     uint32_t idx[RQB_MAX_LT_DEGREE];
     for (int k = 0; k < nlt; k++) {
-      int cnt = rqb_host_lt_indices(&P, req->isi[k], idx);
-      for (int q = 0; q < cnt; q++) cidx[acc + q] = (int)idx[q];
-      acc += cnt;
+      const uint32_t x = req->isi[k];
+      if (x < (uint32_t)Kp) {
+        const int *src = bm->cidx + bm->rptr[S + H + x];
+        const int cnt = bm->rptr[S + H + x + 1] - bm->rptr[S + H + x];
+        for (int q = 0; q < cnt; q++) cidx[acc + q] = src[q];
+        acc += cnt;
+        deg[S + H + k] = bm->deg[S + H + x];
+      } else {
+        int cnt = rqb_host_lt_indices(&P, x, idx), dg = 0;
+        for (int q = 0; q < cnt; q++) {
+          cidx[acc + q] = (int)idx[q];
+          dg += idx[q] < (uint32_t)W;
+        }
+        acc += cnt;
+        deg[S + H + k] = dg;
+      }
       rptr[S + H + k + 1] = acc;
     }
   }
@@ -431,7 +532,6 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   double t1 = now_s();
 
   /* ---- 2. peeling */
-  int *deg = sc_buf(sc, SC_DEG, (size_t)R * sizeof(int), 1);
   uint8_t *col_state = sc_buf(sc, SC_COLSTATE, (size_t)L, 1); /* 0 active, 1 peeled, 2 inactive */
   int *col_pos = sc_buf(sc, SC_COLPOS, sizeof(int) * (size_t)L, 0);
   int *col_t = sc_buf(sc, SC_COLT, sizeof(int) * (size_t)L, 0);
@@ -449,8 +549,6 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     col_t[c] = nu;
     ucol[nu++] = c;
   }
-  for (int r = 0; r < R; r++)
-    for (int k = rptr[r]; k < rptr[r + 1]; k++) deg[r] += (cidx[k] < W);
   for (int r = S + H; r < R; r++) {
     if (deg[r] == 1) stk1[n1++] = r;
     if (deg[r] == 2) stk2[n2++] = r;
@@ -545,6 +643,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     int nf = 0;
     int *it = sc_buf(sc, SC_TMP, sizeof(int) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
     int *rd = it + ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64);
+    uint64_t *sortbuf = sc_buf(sc, SC_SORT, sizeof(uint64_t) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
     pptr[0] = 0;
     for (int p = 0; p < I; p++) {
       int r = prow[p], cnt = 0;
@@ -573,16 +672,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
         if (level[p] > maxlevel) maxlevel = level[p];
         continue;
       }
-      for (int a = 1; a < cnt; a++) { /* sort by the level at which the term exists */
-        int lv = rd[a], q = it[a], j = a;
-        while (j > 0 && rd[j - 1] > lv) {
-          rd[j] = rd[j - 1];
-          it[j] = it[j - 1];
-          j--;
-        }
-        rd[j] = lv;
-        it[j] = q;
-      }
+      sort_by_level(rd, it, cnt, maxlevel, sortbuf); /* by the level at which the term exists */
       int head = 0; /* items [head, cnt) are live, sorted by readiness */
       while (cnt - head > CAPF) {
         int take = cnt - head - CAPF + 1;
