@@ -356,3 +356,88 @@ def test_api_decoder_needs_more_symbols_then_succeeds():
     assert dec.num_missing(0) == 0
     assert np.array_equal(out, payload)
     assert dec.add_symbol(enc.encode(0, 0, io_in), api.tag(0, 0), io_out) == nb.SYM_IGN
+
+
+# ------------------------------------------------- context recycling / arena
+def test_solver_contexts_are_recycled_and_stay_correct():
+    """rqb_solver_destroy keeps the context; a later create of the same shape gets it
+    back (same staging address) and still produces the oracle's bytes, also after a
+    different block shape was used in between and after rqb_release_cached()."""
+    rng = np.random.default_rng(11)
+    seen = []
+    for rnd, (K, T) in enumerate([(64, 48), (64, 48), (200, 48), (64, 48), (64, 48)]):
+        if rnd == 4:
+            nb.lib().rqb_release_cached()
+        src = rng.integers(0, 256, (K, T), dtype=np.uint8)
+        s = nb.Solver(K, T, max_in=K, max_out=8)
+        seen.append((K, nb.lib().rqb_solver_staging(s.h)))
+        s.staging[:K, :T] = src
+        s.upload(0, K)
+        s.plan_encode(True, 8)
+        s.run()
+        Cm = s.fetch_c()
+        rep = s.fetch_syms(8)
+        s.close()
+        Co, _, _ = orc_encode(K, T, src.reshape(-1))
+        p = orc_params(K)
+        assert np.array_equal(Cm, Co)
+        assert np.array_equal(rep, np.stack([orc_lt(K, T, Co, p.Kprime + k) for k in range(8)]))
+    assert seen[0][1] == seen[1][1] == seen[3][1]  # the K=64 context came back
+    assert seen[2][1] != seen[0][1]                # a K=200 block does not fit a K=64 context
+
+
+def test_arena_grows_when_a_program_needs_more_working_rows(monkeypatch):
+    """The arena reserves room for the working rows of a typical program; when a program
+    needs more, the fixed spaces (uploaded symbols included) move to a larger arena.
+    Forced here by reserving almost nothing (NANORQ_B200_WS_RESERVE)."""
+    nb.lib().rqb_release_cached()
+    monkeypatch.setenv("NANORQ_B200_WS_RESERVE", "8")
+    K, T = 3000, 40  # large enough that the pool's 4 KiB size classes cannot hide the growth
+    p = orc_params(K)
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (K, T), dtype=np.uint8)
+    Co, _, _ = orc_encode(K, T, src.reshape(-1))
+    keep = np.nonzero(rng.random(K) > 0.3)[0]
+    need = K - len(keep)
+    esis = np.concatenate([keep, np.arange(K, K + need + 2)]).astype(np.uint32)
+    syms = np.stack([src[e] if e < K else orc_lt(K, T, Co, int(e) + p.Kprime - K) for e in esis])
+    rc, rec, Cg = gpu_decode(K, T, esis, syms)
+    nb.lib().rqb_release_cached()
+    assert rc == 0
+    missing, got = rec
+    assert np.array_equal(got, src[missing])
+    assert np.array_equal(Cg, Co)
+
+
+def test_api_encoder_windows_reset_and_source_symbols_before_generate():
+    """nanorq_encode: source symbols are available before generate_symbols ran; repair
+    ESIs far apart are served from successive device windows; encoder_reset reloads."""
+    K, T = 120, 56
+    rng = np.random.default_rng(9)
+    payload = rng.integers(0, 256, K * T, dtype=np.uint8)
+    enc = nb.Encoder(K * T, T, K, 0, 8)
+    io_in = nb.MemIO(payload)
+    assert np.array_equal(enc.encode(5, 0, io_in), payload[5 * T:6 * T])  # not inverted yet: plain copy
+    Co, _, _ = orc_encode(K, T, payload)
+    p = orc_params(K)
+    for esi in [K, K + 1, K + 31, K + 32, K + 5000, K + 5001, K + 7, (1 << 24) - 1]:
+        assert np.array_equal(enc.encode(esi, 0, io_in), orc_lt(K, T, Co, esi + p.Kprime - K)), esi
+    assert enc.encode(1 << 24, 0, io_in) is None
+    # new payload through the same object after a reset
+    payload2 = rng.integers(0, 256, K * T, dtype=np.uint8)
+    io2 = nb.MemIO(payload2)
+    enc.encoder_reset(0)
+    assert enc.generate_symbols(0, io2)
+    Co2, _, _ = orc_encode(K, T, payload2)
+    assert np.array_equal(enc.encode(K + 3, 0, io2), orc_lt(K, T, Co2, K + 3 + p.Kprime - K))
+    assert np.array_equal(enc.encode(17, 0, io2), payload2[17 * T:18 * T])
+
+
+def test_c4_eight_blocks_of_one_object_roundtrip():
+    """BASELINE config 4 at reduced symbol size: ONE object of 8 source blocks of K=4096
+    (all blocks share block 0's parameters), 10 % loss per block, decoded block by block."""
+    K, T, Z = 4096, 64, 8
+    ok, payload, out, _, enc = api_roundtrip(K * T * Z, T, K, 0, 0.10, 3, seed=44)
+    assert enc.blocks() == Z and all(enc.block_symbols(b) == K for b in range(Z))
+    assert ok
+    assert np.array_equal(out, payload)
