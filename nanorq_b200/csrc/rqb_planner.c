@@ -116,7 +116,7 @@ enum {
   SC_PCOL, SC_UCOL, SC_STK1, SC_STK2, SC_LEVEL, SC_G, SC_LOWROWS, SC_SB, SC_TB, SC_XPTR, SC_XIDX, SC_SH,
   SC_HB1, SC_HB2, SC_YBUF, SC_ACCBUF, SC_PIVROW, SC_PIVCOL, SC_FREECOLS, SC_Q, SC_TQ, SC_TMP, SC_CSLOT,
   SC_FPTR, SC_FITEMS, SC_PFIRST, SC_PLEVEL, SC_PPTR, SC_PITEMS, SC_CURLOC, SC_TASKS, SC_SRCS, SC_ORDER,
-  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_COUNT
+  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_FRUSED, SC_FRTAB, SC_COUNT
 };
 typedef struct {
   void *p[SC_COUNT];
@@ -211,6 +211,24 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
  * tree of partial sums into fresh working rows (leaves keep `kind`, inner nodes
  * are plain XORs).  srcs is clobbered.  Returns the level that writes dst. */
 static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint32_t n, uint32_t level) {
+  if (n > RQB_MAX_SRCS && n <= RQB_MAX_SRCS * RQB_MAX_SRCS) {
+    /* two levels with the fewest tasks, ceil((n-1)/7): k partial sums over c = n+k-8 of the
+     * sources, then one task over the 8-k sources left and the k partial sums */
+    const uint32_t k = (n - RQB_MAX_SRCS + RQB_MAX_SRCS - 2) / (RQB_MAX_SRCS - 1), c = n + k - RQB_MAX_SRCS;
+    uint32_t part[RQB_MAX_SRCS], o = 0;
+    for (uint32_t i = 0; i < k; i++) {
+      uint32_t cnt = (c - o) / (k - i); /* spread evenly; every partial gets >= 2 sources */
+      uint32_t r = b->ws_base + b->ws_next++;
+      b_task(b, kind, r, 0, level, srcs + o, cnt);
+      part[i] = RQB_SRC(r, 1);
+      o += cnt;
+    }
+    uint32_t last[RQB_MAX_SRCS], m = 0;
+    for (uint32_t q = c; q < n; q++) last[m++] = srcs[q];
+    for (uint32_t i = 0; i < k; i++) last[m++] = part[i];
+    b_task(b, kind, dst, 0, level + 1, last, m);
+    return level + 1;
+  }
   while (n > RQB_MAX_SRCS) {
     uint32_t m = 0;
     for (uint32_t o = 0; o < n; o += RQB_MAX_SRCS) {
@@ -1060,30 +1078,116 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   end = lv;
 
   FINE(10);
-  /* D: b_top' = b_top ^ U_top z.  A row without inactive columns just goes back to
-   * its input row (no task); the others are rebuilt from the input row. */
-  for (int p = 0; p < I; p++) {
-    int r = prow[p];
-    uint32_t ns = 0;
-    uint32_t orig = r >= S + H ? (req->in_row[r - S - H] != RQB_ROW_NONE ? row0[RQB_SP_IN] + req->in_row[r - S - H] : NONE_REF)
-                               : NONE_REF;
-    for (int k = rptr[r]; k < rptr[r + 1]; k++)
-      if (col_state[cidx[k]] == 2) PUSH(ns, loc[Z + (uint32_t)col_t[cidx[k]]]);
-    if (ns == 0) {
-      loc[r] = orig;
-      continue;
-    }
-    PUSH(ns, orig);
-    uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(r), tmp, ns, lv);
-    loc[r] = WSREF(r);
-    if (e2 > end) end = e2;
+  /* Back-substitution into the peeled part, x = X^-1 (b_top ^ U_top z), one of two ways.
+   *
+   * F ("four Russians"): x_p = Y_p ^ (G z)_p with Y from phase A and G = X^-1 U_top, the
+   * bit matrix the host already holds.  G is dense (about a third of its bits are set), so
+   * the u inactive symbols are taken 8 at a time: table rows T_j[m] = XOR of the z of group j
+   * selected by the byte m (built from two 4-bit half tables, 2 levels), and every x_p is a
+   * gather of at most ceil(u/8) table rows.  Costs more sources than a second triangular
+   * solve but needs 4 levels instead of ~500 -- the solve kernel is bound by the latency of
+   * its dependency levels, not by bytes.
+   *
+   * D+E: patch b_top with U_top z and run the triangular solve again; fewer bytes, used when
+   * u is so large (K' in the tens of thousands) that F's gathers would dominate. */
+  const int ng = (U + 7) / 8;
+  static int fr_mode = -1; /* NANORQ_B200_BACKSUB = tables | triangular overrides the choice (experiments) */
+  if (fr_mode < 0) {
+    const char *e = getenv("NANORQ_B200_BACKSUB");
+    fr_mode = !e ? 0 : !strcmp(e, "tables") ? 1 : !strcmp(e, "triangular") ? 2 : 0;
   }
-  FINE(11);
-  /* E: x = X^-1 b_top' */
-  TRIANGULAR(end);
-  lv = end + (uint32_t)maxlevel + 1;
-  end = lv;
-
+  const int use_fr = I > 0 && fr_mode != 2 && (fr_mode == 1 || (size_t)ng * (size_t)I * 2 <= (size_t)nnz * 5);
+  if (use_fr) {
+    uint8_t *used8 = sc_buf(sc, SC_FRUSED, (size_t)ng * 256 + 64, 1);
+    uint32_t *tab8 = sc_buf(sc, SC_FRTAB, sizeof(uint32_t) * ((size_t)ng * 256 + (size_t)ng * 32), 0);
+    uint32_t *tab4 = tab8 + (size_t)ng * 256; /* [ng][2][16] */
+    for (int p = 0; p < I; p++) {
+      const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
+      for (int j = 0; j < ng; j++) used8[(size_t)j * 256 + g[j]] = 1;
+    }
+    for (int j = 0; j < ng; j++) {
+      uint8_t need4[2][16];
+      memset(need4, 0, sizeof(need4));
+      for (int m = 1; m < 256; m++)
+        if (used8[(size_t)j * 256 + m]) {
+          need4[0][m & 15] = 1;
+          need4[1][m >> 4] = 1;
+        }
+      for (int half = 0; half < 2; half++)
+        for (int v = 1; v < 16; v++) {
+          uint32_t *slot = &tab4[((size_t)j * 2 + half) * 16 + v];
+          *slot = NONE_REF;
+          if (!need4[half][v]) continue;
+          uint32_t ns = 0;
+          for (int bit = 0; bit < 4; bit++)
+            if (v >> bit & 1) {
+              int t = 8 * j + 4 * half + bit;
+              if (t < U) PUSH(ns, loc[Z + (uint32_t)t]);
+            }
+          if (ns == 1) {
+            *slot = tmp[0] & RQB_REF_MASK; /* a single z: no table row needed */
+          } else if (ns > 1) {
+            uint32_t r = bd.ws_base + bd.ws_next++;
+            b_task(&bd, RQB_T_XOR, r, 0, lv, tmp, ns);
+            *slot = r;
+          }
+        }
+      for (int m = 1; m < 256; m++) {
+        uint32_t *slot = &tab8[(size_t)j * 256 + m];
+        *slot = NONE_REF;
+        if (!used8[(size_t)j * 256 + m]) continue;
+        uint32_t lo = (m & 15) ? tab4[((size_t)j * 2) * 16 + (m & 15)] : NONE_REF;
+        uint32_t hi = (m >> 4) ? tab4[((size_t)j * 2 + 1) * 16 + (m >> 4)] : NONE_REF;
+        if (lo != NONE_REF && hi != NONE_REF) {
+          uint32_t pair[2] = {RQB_SRC(lo, 1), RQB_SRC(hi, 1)};
+          uint32_t r = bd.ws_base + bd.ws_next++;
+          b_task(&bd, RQB_T_XOR, r, 0, lv + 1, pair, 2);
+          *slot = r;
+        } else {
+          *slot = lo != NONE_REF ? lo : hi;
+        }
+      }
+    }
+    end = lv + 2;
+    for (int p = 0; p < I; p++) {
+      const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
+      uint32_t ns = 0;
+      for (int j = 0; j < ng; j++)
+        if (g[j]) PUSH(ns, tab8[(size_t)j * 256 + g[j]]);
+      if (ns == 0) continue; /* x_p = Y_p */
+      PUSH(ns, loc[prow[p]]);
+      uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(prow[p]), tmp, ns, lv + 2);
+      loc[prow[p]] = WSREF(prow[p]);
+      if (e2 > end) end = e2;
+    }
+    FINE(11);
+    lv = end + 1;
+    end = lv;
+  } else {
+    /* D: b_top' = b_top ^ U_top z.  A row without inactive columns just goes back to
+     * its input row (no task); the others are rebuilt from the input row. */
+    for (int p = 0; p < I; p++) {
+      int r = prow[p];
+      uint32_t ns = 0;
+      uint32_t orig = r >= S + H ? (req->in_row[r - S - H] != RQB_ROW_NONE ? row0[RQB_SP_IN] + req->in_row[r - S - H] : NONE_REF)
+                                 : NONE_REF;
+      for (int k = rptr[r]; k < rptr[r + 1]; k++)
+        if (col_state[cidx[k]] == 2) PUSH(ns, loc[Z + (uint32_t)col_t[cidx[k]]]);
+      if (ns == 0) {
+        loc[r] = orig;
+        continue;
+      }
+      PUSH(ns, orig);
+      uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(r), tmp, ns, lv);
+      loc[r] = WSREF(r);
+      if (e2 > end) end = e2;
+    }
+    FINE(11);
+    /* E: x = X^-1 b_top' */
+    TRIANGULAR(end);
+    lv = end + (uint32_t)maxlevel + 1;
+    end = lv;
+  }
   FINE(12);
   /* O: outputs.  C[col] sits in the row that pivoted on col, or in z. */
   uint32_t *cloc = sc_buf(sc, SC_CSLOT, sizeof(uint32_t) * (size_t)L, 0);

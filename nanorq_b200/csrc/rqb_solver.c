@@ -203,9 +203,9 @@ static int solver_wait(rqb_solver *s);
 static rqb_solver *g_shells;
 
 /* arena rows a fresh context gets: the fixed spaces plus room for the working rows of
- * a typical program (about 3.5 L; the arena is regrown if a program needs more) */
+ * a typical program (about 3.5 L, 6 L with the table rows of the four-Russians back-substitution; the arena is regrown if a program needs more) */
 static size_t arena_rows_wanted(uint32_t max_in, uint32_t max_out, const rqb_params *P) {
-  size_t ws = 4 * (size_t)P->L + 512;
+  size_t ws = 6 * (size_t)P->L + 512;
   const char *e = getenv("NANORQ_B200_WS_RESERVE"); /* tests: start small to exercise the regrowth */
   if (e && *e) ws = (size_t)strtoul(e, NULL, 10);
   return (size_t)max_in + max_out + (size_t)P->L + 1 + ws;
