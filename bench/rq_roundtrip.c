@@ -41,7 +41,7 @@ typedef struct {
 } rt_config;
 
 typedef struct {
-  double wall_s;   /* start barrier -> last worker done (payload generation and verification excluded) */
+  double wall_s;   /* first worker out of the start barrier -> last worker done (payload generation and verification excluded) */
   double t_gen;    /* sums over blocks of the time inside ...   nanorq_generate_symbols */
   double t_emit;   /*                                           nanorq_encode (all symbols sent) */
   double t_add;    /*                                           nanorq_decoder_new + add_symbol  */
@@ -75,7 +75,7 @@ typedef struct {
   pthread_mutex_t *mu;
   pthread_barrier_t *bar;
   rt_result acc;
-  double t_done;
+  double t_start, t_done;
 } worker;
 
 static int take(worker *w) {
@@ -94,6 +94,7 @@ static void *work(void *arg) {
   uint32_t *tags = malloc(max_pk * sizeof(uint32_t));
   memset(pk, 0, max_pk * T); /* fault the packet buffer in before the clock starts */
   pthread_barrier_wait(w->bar);
+  w->t_start = now_s();
   for (int b; (b = take(w)) >= 0;) {
     uint32_t rs = (c->seed + 0x9e3779b9u * (uint32_t)(b + 1)) | 1u;
     const uint32_t thresh = (uint32_t)(c->loss * 4294967296.0 > 4294967295.0 ? 4294967295.0 : c->loss * 4294967296.0);
@@ -193,10 +194,11 @@ int rq_roundtrip_run(const rt_config *cfg, rt_result *res) {
     pthread_create(&th[k], NULL, work, &ws[k]);
   }
   pthread_barrier_wait(&bar);
-  double t0 = now_s(), t_end = t0;
+  double t0 = now_s(), t_end = 0.0;
   for (int k = 0; k < nt; k++) {
     pthread_join(th[k], NULL);
-    if (ws[k].t_done > t_end) t_end = ws[k].t_done;
+    if (ws[k].t_start < t0) t0 = ws[k].t_start; /* first worker out of the barrier ... */
+    if (ws[k].t_done > t_end) t_end = ws[k].t_done; /* ... to the last one done */
     res->t_gen += ws[k].acc.t_gen;
     res->t_emit += ws[k].acc.t_emit;
     res->t_add += ws[k].acc.t_add;

@@ -417,16 +417,23 @@ int rqb_stream_create(void **s) {
   return 0;
 }
 int rqb_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
-// How a host thread waits for its stream (NANORQ_B200_WAIT = yield | spin | block):
-//   yield (default)  poll cudaStreamQuery and sched_yield() between polls: as prompt as
-//                    spinning when every thread has a core, and a waiting thread gives its
-//                    core away when there are more worker threads than cores;
-//   spin             cudaStreamSynchronize (busy-waits);
-//   block            a blocking-sync event: the thread sleeps until the interrupt.  Measured
-//                    on the B200 hosts the wake-up costs ~0.5-1 ms, as long as a whole
-//                    K=4096 solve, so this is only for hosts that must not burn cycles.
-int rqb_stream_sync(void *s) {
-  static thread_local cudaEvent_t ev[64];
+// ---------------------------------------------------------------- waiting
+// A host thread waits for its stream by watching a word in pinned host memory that a
+// one-thread kernel at the end of the stream's queue sets (rqb_stream_wait_flag): no
+// driver call while waiting, so a dozen waiting threads do not fight over the driver's
+// lock with the threads that are launching work (polling cudaStreamQuery did: a 1.4 MB
+// cudaMemcpyAsync took 3.5 ms at K=1024 with 20 threads).  The waiter spins briefly and
+// then yields its core between looks, which is as prompt as spinning when every thread
+// has a core and lets another worker run when there are more threads than cores.
+// NANORQ_B200_WAIT = flag (default) | spin (cudaStreamSynchronize) | block (blocking-sync
+// event: the thread sleeps; the wake-up costs ~0.5-1 ms on the B200 hosts, as long as a
+// whole K=4096 solve).
+__global__ void rqb_flag_kernel(volatile uint32_t *flag, uint32_t seq) {
+  __threadfence_system();
+  *flag = seq;
+}
+
+static int wait_mode() {
   static std::atomic<int> mode{-1};
   int m = mode.load(std::memory_order_relaxed);
   if (m < 0) {
@@ -436,26 +443,42 @@ int rqb_stream_sync(void *s) {
     if (e && !strcmp(e, "block")) m = 2;
     mode.store(m, std::memory_order_relaxed);
   }
-  if (m == 0) {
-    for (unsigned spins = 0;; spins++) {
-      cudaError_t q = cudaStreamQuery((cudaStream_t)s);
-      if (q == cudaSuccess) return 0;
-      if (q != cudaErrorNotReady) return fail(q, "cudaStreamQuery");
-      if (spins < 64) {
-        for (int k = 0; k < 32; k++) __builtin_ia32_pause();
-      } else {
-        sched_yield();
-      }
-    }
-  }
+  return m;
+}
+
+int rqb_stream_sync(void *s) {
+  static thread_local cudaEvent_t ev[64];
   int dev = 0;
-  if (m == 1 || cudaGetDevice(&dev) != cudaSuccess || dev >= 64) {
+  if (wait_mode() != 2 || cudaGetDevice(&dev) != cudaSuccess || dev >= 64) {
     CK(cudaStreamSynchronize((cudaStream_t)s));
     return 0;
   }
   if (!ev[dev]) CK(cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming));
   CK(cudaEventRecord(ev[dev], (cudaStream_t)s));
   CK(cudaEventSynchronize(ev[dev]));
+  return 0;
+}
+
+// flag: a 32-bit word in pinned host memory owned by the caller; *seq is the last value
+// handed out for it.  Returns when everything queued on the stream so far has run.
+int rqb_stream_wait_flag(void *s, uint32_t *flag, uint32_t *seq) {
+  if (wait_mode() != 0) return rqb_stream_sync(s);
+  const uint32_t want = ++*seq;
+  rqb_flag_kernel<<<1, 1, 0, (cudaStream_t)s>>>(flag, want);
+  g_launches++;
+  CK(cudaGetLastError());
+  volatile uint32_t *f = flag;
+  for (unsigned spins = 0; *f != want; spins++) {
+    if (spins < 256) {
+      for (int k = 0; k < 16; k++) __builtin_ia32_pause();
+    } else {
+      sched_yield();
+      if ((spins & 0xfff) == 0) { /* a failed launch would never set the flag: look for errors now and then */
+        cudaError_t q = cudaStreamQuery((cudaStream_t)s);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(q, "stream failed while waiting");
+      }
+    }
+  }
   return 0;
 }
 int rqb_dev_sync(void) { CK(cudaDeviceSynchronize()); return 0; }

@@ -46,6 +46,8 @@ int rqb_host_free(void *p);
 int rqb_stream_create(void **s);
 int rqb_stream_destroy(void *s);
 int rqb_stream_sync(void *s);
+/* wait for the stream through a flag word in pinned host memory (see rqb_device.cu) */
+int rqb_stream_wait_flag(void *s, uint32_t *flag, uint32_t *seq);
 int rqb_dev_sync(void);
 int rqb_copy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int rqb_copy_d2h(void *dst, const void *src, size_t bytes, void *stream);

@@ -1091,10 +1091,11 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * D+E: patch b_top with U_top z and run the triangular solve again; fewer bytes, used when
    * u is so large (K' in the tens of thousands) that F's gathers would dominate. */
   const int ng = (U + 7) / 8;
-  static int fr_mode = -1; /* NANORQ_B200_BACKSUB = tables | triangular overrides the choice (experiments) */
+  static int fr_mode = -1, fr_bits = 8; /* NANORQ_B200_BACKSUB = tables | tables4 | triangular overrides the choice (experiments) */
   if (fr_mode < 0) {
     const char *e = getenv("NANORQ_B200_BACKSUB");
-    fr_mode = !e ? 0 : !strcmp(e, "tables") ? 1 : !strcmp(e, "triangular") ? 2 : 0;
+    if (e && !strcmp(e, "tables4")) fr_bits = 4;
+    fr_mode = !e ? 0 : !strncmp(e, "tables", 6) ? 1 : !strcmp(e, "triangular") ? 2 : 0;
   }
   const int use_fr = I > 0 && fr_mode != 2 && (fr_mode == 1 || (size_t)ng * (size_t)I * 2 <= (size_t)nnz * 5);
   if (use_fr) {
@@ -1138,6 +1139,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
         if (!used8[(size_t)j * 256 + m]) continue;
         uint32_t lo = (m & 15) ? tab4[((size_t)j * 2) * 16 + (m & 15)] : NONE_REF;
         uint32_t hi = (m >> 4) ? tab4[((size_t)j * 2 + 1) * 16 + (m >> 4)] : NONE_REF;
+        if (fr_bits == 4) continue;
         if (lo != NONE_REF && hi != NONE_REF) {
           uint32_t pair[2] = {RQB_SRC(lo, 1), RQB_SRC(hi, 1)};
           uint32_t r = bd.ws_base + bd.ws_next++;
@@ -1152,6 +1154,12 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     for (int p = 0; p < I; p++) {
       const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
       uint32_t ns = 0;
+      if (fr_bits == 4) {
+        for (int j = 0; j < ng; j++) {
+          if (g[j] & 15) PUSH(ns, tab4[((size_t)j * 2) * 16 + (g[j] & 15)]);
+          if (g[j] >> 4) PUSH(ns, tab4[((size_t)j * 2 + 1) * 16 + (g[j] >> 4)]);
+        }
+      } else
       for (int j = 0; j < ng; j++)
         if (g[j]) PUSH(ns, tab8[(size_t)j * 256 + g[j]]);
       if (ns == 0) continue; /* x_p = Y_p */

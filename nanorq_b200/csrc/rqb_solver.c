@@ -173,6 +173,8 @@ struct rqb_solver {
   struct rqb_solver *next_shell;
   void *stream, *ev0, *ev1, *ev2, *ev3;
   uint8_t *h_in, *h_sym; /* pinned: staging rows of the input space, mirror of the emitted symbols */
+  uint32_t *h_flag;      /* pinned word the stream sets when it has drained (rqb_stream_wait_flag) */
+  uint32_t flag_seq;
   /* every row of the block lives in ONE device arena (rqb_program.h):
    * [IN: max_in | SYM: max_out | C: L | ZERO: 1 | WS: working rows, grown on demand] */
   uint8_t *d_arena;
@@ -231,6 +233,7 @@ static void solver_release(rqb_solver *s) { /* really free everything */
   pool_put(s->h_in, (size_t)s->in_cap * s->pitch, 1);
   pool_put(s->d_arena, s->arena_cap, 0);
   pool_put(s->h_sym, (size_t)s->out_cap * s->pitch, 1);
+  pool_put(s->h_flag, 64, 1);
   pool_put(s->d_isi, (size_t)s->out_cap * 4, 0);
   free(s->h_isi);
   pool_put(s->d_pages, s->d_pages_cap, 0);
@@ -250,18 +253,18 @@ void rqb_solver_destroy(rqb_solver *s) {
   if (!s) return;
   if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
   s->plan = NULL;
-  if (s->busy || s->batch_owner) { /* nothing queued may outlive the owner's use of the buffers */
-    int cur = rqb_dev_get();
-    if (cur != s->dev) rqb_dev_set(s->dev);
-    solver_wait(s);
-  }
+  /* Work may still be queued on the stream (an encoder whose repair symbols were never
+   * asked for): the context is parked as it is -- every buffer that work touches belongs
+   * to the context -- and whoever takes it out of the free list waits first. */
   if (s->broken) {
     solver_release(s);
     return;
   }
-  pthread_mutex_lock(&g_shell_mu);
-  s->next_shell = g_shells;
-  g_shells = s;
+  s->next_shell = NULL;
+  pthread_mutex_lock(&g_shell_mu); /* appended at the tail: the list is oldest-first */
+  rqb_solver **pp = &g_shells;
+  while (*pp) pp = &(*pp)->next_shell;
+  *pp = s;
   pthread_mutex_unlock(&g_shell_mu);
 }
 
@@ -306,7 +309,17 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
       if (c->dev != dev || c->T != T || c->in_cap < max_in || c->out_cap < max_out) continue;
       if (c->arena_cap < arena_rows_wanted(max_in, max_out, &P) * c->pitch) continue;
       if ((size_t)c->in_cap > (size_t)max_in + max_in / 4 + 64 || (size_t)c->out_cap > (size_t)max_out + max_out / 4 + 64) continue;
-      if (!best || c->in_cap + c->out_cap < (*best)->in_cap + (*best)->out_cap) best = pp;
+      /* an idle context before one with work still queued (oldest first: most likely done);
+       * among idle ones the tightest fit */
+      const int c_busy = c->busy || c->batch_owner != NULL;
+      if (!best) {
+        best = pp;
+      } else {
+        const rqb_solver *b = *best;
+        const int b_busy = b->busy || b->batch_owner != NULL;
+        if (b_busy && !c_busy) best = pp;
+        else if (b_busy == c_busy && !c_busy && c->in_cap + c->out_cap < b->in_cap + b->out_cap) best = pp;
+      }
     }
     if (best) {
       s = *best;
@@ -325,8 +338,13 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     s->cur_pages = NULL;
     s->n_out_last = 0;
     s->next_shell = NULL;
-    s->batch_owner = NULL;
     if (bind_dev(s->dev)) return dev_fail(0, "rqb_solver_create bind");
+    if ((s->busy || s->batch_owner) && solver_wait(s)) { /* the previous owner left work queued */
+      s->broken = 1;
+      rqb_solver_destroy(s);
+      return RQB_E_NODEVICE;
+    }
+    s->batch_owner = NULL;
     if (solver_layout(s)) {
       s->broken = 1;
       rqb_solver_destroy(s);
@@ -354,6 +372,8 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   e = e ? e : pool_get((void **)&s->h_in, (size_t)s->in_cap * s->pitch, 1);
   e = e ? e : pool_get((void **)&s->d_arena, s->arena_cap, 0);
   e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->out_cap * s->pitch, 1);
+  e = e ? e : pool_get((void **)&s->h_flag, 64, 1);
+  if (!e) *s->h_flag = s->flag_seq = 0;
   e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->out_cap * 4, 0);
   /* small control blocks are sent from PAGEABLE memory on purpose: cudaMemcpyAsync
    * stages a pageable source before it returns, so these buffers may be rewritten
@@ -382,7 +402,7 @@ static int solver_wait(rqb_solver *s) {
     DEV(rqb_stream_sync(s->batch_owner->stream));
   }
   s->batch_owner = NULL;
-  DEV(rqb_stream_sync(s->stream));
+  DEV(rqb_stream_wait_flag(s->stream, s->h_flag, &s->flag_seq));
   s->busy = 0;
   s->pages_pending = 0;
   return 0;
@@ -427,7 +447,7 @@ static int ensure_cap(rqb_solver *s, void **buf, size_t *cap, size_t need, int p
     *buf = NULL;
     *cap = 0;
   }
-  need += need / 8; /* programs of one block size differ a little from block to block: do not regrow for each */
+  need += need / 4; /* programs of one block size differ a little from block to block: do not regrow for each */
   DEV(pool_get(buf, need, pinned));
   *cap = pool_class(need);
   return 0;
@@ -495,8 +515,15 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   s->plan = p;
   s->plan_shared = 0;
   size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
-  rc = ensure_cap(s, (void **)&s->d_pages, &s->d_pages_cap, pb, 0);
-  rc = rc ? rc : ensure_cap(s, (void **)&s->h_pages, &s->h_pages_cap, pb, 1);
+  /* room for the largest program this block size is likely to see (measured: ~300 bytes of
+   * program per intermediate symbol), so that in steady state no thread allocates pinned
+   * or device memory: those calls take milliseconds under the driver's global lock and
+   * stall every other thread's launches */
+  size_t want = pb > (size_t)400 * (size_t)s->P.L ? pb : (size_t)400 * (size_t)s->P.L;
+  if (pb > s->d_pages_cap || pb > s->h_pages_cap) {
+    rc = ensure_cap(s, (void **)&s->d_pages, &s->d_pages_cap, want, 0);
+    rc = rc ? rc : ensure_cap(s, (void **)&s->h_pages, &s->h_pages_cap, want, 1);
+  }
   if (rc) return rc;
   /* the pages go through pinned memory so that the copy is truly asynchronous; the
    * staging buffer may be rewritten by the next plan only after this copy has run */
