@@ -7,6 +7,7 @@ writes profiles/<round>_launches.csv          the per-launch device times (ncu l
        profiles/<round>_launch_shares.json    share of the step per kernel
        profiles/<round>_solve_ncu.json        key metrics of rqb_solve_kernel (per launch)
        profiles/<round>_rowops_ncu.json       key metrics of rqb_rowops_kernel
+       profiles/<round>_aux_ncu.json          key metrics of rqb_lt_kernel / rqb_gather_rows_kernel (tools/aux_kernels.py)
        profiles/<round>_solve_traffic.json    DRAM bytes per launch (bench.py's roofline.traffic)
 """
 import csv
@@ -79,7 +80,7 @@ def main():
                    "note": "per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes",
                    "kernels": shares}, open(os.path.join(PROF, rnd + "_launch_shares.json"), "w"), indent=1)
         print(json.dumps(shares, indent=1))
-    for name in ("solve", "rowops"):
+    for name in ("solve", "rowops", "aux"):
         rep = os.path.join(OUT, "prof_%s.ncu-rep" % name)
         if not os.path.exists(rep):
             continue
