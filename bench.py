@@ -290,6 +290,10 @@ def run_own(args, rank, world, local_rank):
     traffic_file = os.path.join(ROOT, "profiles", "r01_solve_traffic.json")
     if os.path.exists(traffic_file):
         roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        if roofline["traffic"]:
+            # what the kernel really moves through HBM (ncu, same command) per second of measured launch time
+            roofline["traffic_gbs"] = roofline["traffic"] / avg_launch_s / 1e9
+            roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
 
     # ---- row-axpy microbenchmark (oaxpy, 3*T bytes per op) on a matrix >> L2
     row_axpy = None
@@ -315,13 +319,14 @@ def run_own(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through nanorq.h (bench/rq_roundtrip.c)
-    rt_so = os.path.join(ROOT, "nanorq_b200", "librq_roundtrip.so")
+    rt_so = os.path.join(nb.api.LIB_DIR, "librq_roundtrip.so")
     # 1.25 worker threads per host core: a thread that waits for its block's solve yields its core
     threads = max(1, min(args.threads or (5 * (os.cpu_count() or 1)) // (4 * world), 64))
     for w in range(0 if args.skip_e2e else max(args.warmup, 3)):
-        roundtrip(rt_so, min(NB, 2 * threads), threads, 900 + w)
+        roundtrip(rt_so, NB, threads, 900 + w)  # full-size steps: every worker gets its contexts and buffers
     barrier()
     nb.host_profile(reset=True)
+    slow0 = nb.slow_path_counters()
     h0, d0 = nb.transfer_bytes()
     l1 = nb.kernel_launches()
     parts, t_e2e = np.zeros(4), 0.0
@@ -342,6 +347,9 @@ def run_own(args, rank, world, local_rank):
            "gpu_launches": e2e_launches,
            "phase_seconds_summed_over_threads": dict(zip(("generate_symbols", "encode_emit", "add_symbol", "repair_block"),
                                                          [float(x) for x in parts]))}
+    if e2e is not None:
+        # allocations / arena regrowths / new contexts inside the timed e2e steps: must be all zero in steady state
+        e2e["slow_path_events"] = {k: v - slow0[k] for k, v in nb.slow_path_counters().items()}
     if e2e is not None and host_prof is not None:
         e2e["host_profile_seconds_summed_over_threads"] = {k: round(v, 4) for k, v in host_prof.items()}
 

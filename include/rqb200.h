@@ -44,6 +44,11 @@ unsigned long long rqb_kernel_launches(void);
 /* bytes copied host->device / device->host by this library so far */
 void rqb_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
 
+/* slow-path events so far: {fresh pinned allocations, fresh device allocations, arena
+ * regrowths, solver contexts created}.  Each takes the driver's global lock for
+ * milliseconds; in steady state the counters must stay flat. */
+void rqb_slow_path_counters(unsigned long long out[4]);
+
 /* host-side time accounting of the nanorq.h layer (enabled by the environment
  * variable NANORQ_B200_PROFILE=1; off by default).  seconds[k] = time summed over
  * all threads in slot k, names from rqb_host_profile_name(k) (NULL past the end). */
@@ -108,7 +113,9 @@ int rqb_solver_fetch_syms_async(rqb_solver *s, uint32_t first, uint32_t n);
 int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch);
 /* pinned host mirror of the emitted symbols (valid after fetch with dst == NULL) */
 const uint8_t *rqb_solver_sym_mirror(rqb_solver *s);
-/* device time of the last rqb_solver_run in milliseconds (CUDA events) */
+/* device time of the last rqb_solver_run in milliseconds (CUDA events); needs
+ * rqb_solver_set_timing(s, 1) before the run (off by default: two driver calls per block) */
+void rqb_solver_set_timing(rqb_solver *s, int on);
 int rqb_solver_last_kernel_ms(rqb_solver *s, float *ms);
 
 typedef struct {
@@ -172,9 +179,19 @@ int rqb_rowops_apply_dev(rqb_matrix *m, const rqb_oplist *l, int repeats, float 
 /* replay a reference-format schedule: ops applied in the order of
  * precode_matrix_apply_sched (lib/precode.c:23-32) followed by the two row
  * permutations of precode_matrix_intermediate (lib/precode.c:379-389).
- * The host only levelises the op list; every row operation runs on the device. */
+ * The host only orders the op list by its dependencies; every row operation runs on
+ * the device.  rqb_schedule_replay turns the schedule into ONE launch of the solve
+ * kernel (dependency levels inside the kernel, accumulations into one destination merged
+ * into gathers); rqb_schedule_replay_stepwise is the literal form, one launch of the
+ * batched row-op kernel per dependency level.  Same bytes either way. */
 int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long mark0, long mark1,
                         const int *di, size_t rows, const int *c, size_t cols, float *ms_device);
+/* host only: the program rqb_schedule_replay runs, over an arena [nrows matrix rows,
+ * updated in place | nrows gathered rows | ZERO row]; free with rqb_plan_blob_free */
+int rqb_schedule_plan_blob(size_t nrows, const rqb_op *ops, size_t nops, long mark0, long mark1, const int *di,
+                           size_t rows, const int *c, size_t cols, rqb_plan_blob *out);
+int rqb_schedule_replay_stepwise(rqb_matrix *m, const rqb_op *ops, size_t nops, long mark0, long mark1,
+                                 const int *di, size_t rows, const int *c, size_t cols, float *ms_device);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,9 @@ from .api import (  # noqa: F401
     lib,
     lt_row_indices,
     plan_blob,
+    schedule_plan_blob,
     set_device,
+    slow_path_counters,
     transfer_bytes,
     SYM_ADDED,
     SYM_DUP,

@@ -10,7 +10,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnanorq_b200.so")
+# NANORQ_B200_LIBDIR: load another build of the library (A/B measurements of two builds in one GPU session)
+LIB_DIR = os.environ.get("NANORQ_B200_LIBDIR", _HERE)
+LIB_PATH = os.path.join(LIB_DIR, "libnanorq_b200.so")
 
 SYM_DUP, SYM_IGN, SYM_ADDED, SYM_ERR = 2, 1, 0, -1
 NO_ROW = 0xFFFFFFFF
@@ -108,6 +110,7 @@ def lib():
     sig("rqb_set_device", C.c_int, C.c_int)
     sig("rqb_kernel_launches", C.c_ulonglong)
     sig("rqb_transfer_bytes", None, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
+    sig("rqb_slow_path_counters", None, C.POINTER(C.c_ulonglong * 4))
     sig("rqb_host_profile", None, C.POINTER(C.c_double), C.c_int)
     sig("rqb_host_profile_name", C.c_char_p, C.c_int)
     sig("rqb_host_profile_reset", None)
@@ -132,6 +135,7 @@ def lib():
     sig("rqb_solver_fetch_c", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
     sig("rqb_solver_sym_mirror", vp, vp)
     sig("rqb_solver_last_kernel_ms", C.c_int, vp, C.POINTER(C.c_float))
+    sig("rqb_solver_set_timing", None, vp, C.c_int)
     sig("rqb_solver_get_stats", C.c_int, vp, C.POINTER(SolverStats))
     sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
     sig("rqb_solver_run_batch_on", C.c_int, C.POINTER(vp), C.c_int, vp)
@@ -147,8 +151,11 @@ def lib():
     sig("rqb_ops_upload", C.c_int, C.POINTER(vp), vp, sz)
     sig("rqb_ops_free", None, vp)
     sig("rqb_rowops_apply_dev", C.c_int, vp, vp, C.c_int, C.POINTER(C.c_float))
-    sig("rqb_schedule_replay", C.c_int, vp, vp, sz, C.c_long, C.c_long, C.POINTER(C.c_int), sz,
-        C.POINTER(C.c_int), sz, C.POINTER(C.c_float))
+    sig("rqb_schedule_plan_blob", C.c_int, sz, vp, sz, C.c_long, C.c_long, C.POINTER(C.c_int), sz,
+        C.POINTER(C.c_int), sz, C.POINTER(PlanBlob))
+    for name in ("rqb_schedule_replay", "rqb_schedule_replay_stepwise"):
+        sig(name, C.c_int, vp, vp, sz, C.c_long, C.c_long, C.POINTER(C.c_int), sz,
+            C.POINTER(C.c_int), sz, C.POINTER(C.c_float))
     _lib = L
     return L
 
@@ -163,15 +170,16 @@ EXPORTED_SYMBOLS = [
     "nanorq_repair_block", "ioctx_from_file", "ioctx_mmap_file", "ioctx_from_mem",
     "rqb_last_error", "rqb_device_count", "rqb_set_device", "rqb_kernel_launches", "rqb_transfer_bytes",
     "rqb_solver_mark", "rqb_solver_marked_ms", "rqb_solver_run_batch_on",
-    "rqb_host_profile", "rqb_host_profile_name", "rqb_host_profile_reset",
+    "rqb_host_profile", "rqb_host_profile_name", "rqb_host_profile_reset", "rqb_slow_path_counters",
     "rqb_block_params_init", "rqb_lt_row_indices", "rqb_solver_create", "rqb_solver_create_ex",
     "rqb_solver_destroy", "rqb_release_cached", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
     "rqb_solver_plan", "rqb_solver_plan_encode", "rqb_solver_run", "rqb_solver_emit",
     "rqb_solver_sync", "rqb_solver_fetch_syms", "rqb_solver_fetch_c", "rqb_solver_fetch_syms_async", "rqb_solver_sym_mirror",
-    "rqb_solver_last_kernel_ms", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_plan_blob_build",
+    "rqb_solver_last_kernel_ms", "rqb_solver_set_timing", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_plan_blob_build",
     "rqb_plan_blob_free", "rqb_matrix_create", "rqb_matrix_destroy", "rqb_matrix_pitch",
     "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
+    "rqb_schedule_replay_stepwise", "rqb_schedule_plan_blob",
 ]
 
 
@@ -207,6 +215,13 @@ def host_profile(reset=False):
     if reset:
         lib().rqb_host_profile_reset()
     return {n: out[k] for k, n in enumerate(names)}
+
+
+def slow_path_counters():
+    """{pinned allocations, device allocations, arena regrowths, contexts created} so far"""
+    out = (C.c_ulonglong * 4)()
+    lib().rqb_slow_path_counters(C.byref(out))
+    return dict(zip(("alloc_pinned", "alloc_device", "arena_regrow", "contexts_new"), [int(x) for x in out]))
 
 
 def _check(rc, what):
@@ -295,6 +310,24 @@ def plan_blob(K_params, req):
         "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(),
         "stats": b.stats.as_dict(),
     }
+    lib().rqb_plan_blob_free(C.byref(b))
+    return 0, out
+
+
+def schedule_plan_blob(nrows, ops, mark0, mark1, di, c):
+    """Host-only: the one-launch program of rqb_schedule_replay for a reference-format schedule."""
+    assert ops.dtype == OP_DTYPE
+    di = np.ascontiguousarray(di, dtype=np.int32)
+    c = np.ascontiguousarray(c, dtype=np.int32)
+    b = PlanBlob()
+    rc = lib().rqb_schedule_plan_blob(nrows, ops.ctypes.data, len(ops), mark0, mark1,
+                                      di.ctypes.data_as(C.POINTER(C.c_int)), len(di),
+                                      c.ctypes.data_as(C.POINTER(C.c_int)), len(c), C.byref(b))
+    if rc != 0:
+        return rc, None
+    out = {"n_ws_rows": b.n_ws_rows, "n_pages": b.n_pages, "page_bytes": b.page_bytes, "row0": list(b.row0),
+           "zero_row": b.zero_row, "n_rows": b.n_rows,
+           "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(), "stats": b.stats.as_dict()}
     lib().rqb_plan_blob_free(C.byref(b))
     return 0, out
 
@@ -419,6 +452,7 @@ class Solver:
         _check(lib().rqb_solver_create_ex(C.byref(h), K, K_params or K, T, self.max_in, self.max_out),
                "rqb_solver_create")
         self.h = h
+        lib().rqb_solver_set_timing(h, 1)  # tests and tools read last_kernel_ms()
         self.pitch = lib().rqb_solver_pitch(h)
         buf = (C.c_uint8 * (self.max_in * self.pitch)).from_address(lib().rqb_solver_staging(h))
         self.staging = np.frombuffer(buf, dtype=np.uint8).reshape(self.max_in, self.pitch)
@@ -549,12 +583,13 @@ class Matrix:
         _check(lib().rqb_rowops_apply_dev(self.h, oplist, repeats, C.byref(ms)), "rqb_rowops_apply_dev")
         return ms.value
 
-    def schedule_replay(self, ops, mark0, mark1, di, c):
+    def schedule_replay(self, ops, mark0, mark1, di, c, stepwise=False):
         assert ops.dtype == OP_DTYPE
         di = np.ascontiguousarray(di, dtype=np.int32)
         c = np.ascontiguousarray(c, dtype=np.int32)
         ms = C.c_float()
-        _check(lib().rqb_schedule_replay(self.h, ops.ctypes.data, len(ops), mark0, mark1,
+        fn = lib().rqb_schedule_replay_stepwise if stepwise else lib().rqb_schedule_replay
+        _check(fn(self.h, ops.ctypes.data, len(ops), mark0, mark1,
                                          di.ctypes.data_as(C.POINTER(C.c_int)), len(di),
                                          c.ctypes.data_as(C.POINTER(C.c_int)), len(c), C.byref(ms)),
                "rqb_schedule_replay")

@@ -464,8 +464,7 @@ int rqb_stream_sync(void *s) {
 int rqb_stream_wait_flag(void *s, uint32_t *flag, uint32_t *seq) {
   if (wait_mode() != 0) return rqb_stream_sync(s);
   const uint32_t want = ++*seq;
-  rqb_flag_kernel<<<1, 1, 0, (cudaStream_t)s>>>(flag, want);
-  g_launches++;
+  rqb_flag_kernel<<<1, 1, 0, (cudaStream_t)s>>>(flag, want); /* a signal, not counted in rqb_dev_launch_count */
   CK(cudaGetLastError());
   volatile uint32_t *f = flag;
   for (unsigned spins = 0; *f != want; spins++) {

@@ -47,6 +47,7 @@
 
 #include "rfc6330_tables.h"
 #include "rqb_gf256.h"
+#include "rqb_device.h"
 #include "rqb_program.h"
 
 /* ------------------------------------------------------------------ utils */
@@ -1258,4 +1259,124 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   plan->st.t_emit = t4 - t3;
   *out = plan;
   return 0;
+}
+
+
+/* ------------------------------------------- program from a reference schedule
+ * Turns an already ordered sequence of reference-format row operations
+ * (sched_op, include/sched.h:6-10, in the order precode_matrix_apply_sched applies
+ * them, lib/precode.c:23-32) followed by a row gather (the two permutations of
+ * precode_matrix_intermediate, lib/precode.c:379-389) into ONE device program for
+ * the solve kernel, instead of one launch per dependency level:
+ *   - ops are levelised by their true dependencies (an op needs the last write of
+ *     its source and of its destination; it must not overtake a pending read of
+ *     its destination);
+ *   - successive accumulations into one destination whose sources were all ready
+ *     in time are MERGED into one gather task of up to 8 sources (the reference
+ *     reads and writes the destination once per op) -- legal because GF(256)
+ *     addition commutes and nobody reads the destination in between;
+ *   - the gather runs as a last level into a second half of the arena.
+ * Rows: the matrix occupies arena rows [base, base+nrows), the gathered result goes
+ * to [out_base, out_base+nrows); zero_row is an all-zero row (XOR list padding). */
+typedef struct {
+  uint32_t dst, level;
+  uint8_t n, gf, closed;
+  uint32_t src[RQB_MAX_SRCS]; /* row | beta << 24 */
+} stask;
+
+int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const uint32_t *gather_map, uint32_t base,
+                           uint32_t out_base, uint32_t zero_row, rqb_plan **out) {
+  pthread_once(&tables_once, tables_build);
+  const rqb_rowop *ops = (const rqb_rowop *)ops_v;
+  *out = NULL;
+  if ((uint64_t)out_base + nrows > RQB_MAX_ROWS || (uint64_t)base + nrows > RQB_MAX_ROWS) return -4;
+  stask *t = malloc(sizeof(stask) * (nops ? nops : 1));
+  uint32_t *lw = calloc((size_t)nrows + 1, 4), *lr = calloc((size_t)nrows + 1, 4);
+  int64_t *open = malloc(sizeof(int64_t) * ((size_t)nrows + 1));
+  for (uint32_t r = 0; r < nrows; r++) open[r] = -1;
+  size_t nt = 0;
+  uint32_t maxlevel = 0;
+  int rc = 0;
+  for (size_t q = 0; q < nops && !rc; q++) {
+    const uint32_t i = ops[q].i, j = ops[q].j;
+    uint32_t beta = ops[q].beta;
+    if (i >= nrows || (beta && j >= nrows)) {
+      rc = -1;
+      break;
+    }
+    if (beta == 0 || i == j) { /* oscal (multiplier in j; < 2 is a no-op, oblas_avx.c:94-95) or a row added to itself */
+      uint32_t mult = beta == 0 ? (j & 0xffu) : (beta ^ 1u); /* x ^ b*x = (1^b)*x */
+      if (beta == 0 && mult < 2) continue;
+      if (open[i] >= 0) t[open[i]].closed = 1;
+      open[i] = -1;
+      uint32_t lvl = (lw[i] > lr[i] ? lw[i] : lr[i]) + 1;
+      stask *k = &t[nt++];
+      k->dst = i; k->level = lvl; k->n = 1; k->gf = 1; k->closed = 1;
+      k->src[0] = RQB_SRC(base + i, mult);
+      lw[i] = lvl;
+      if (lvl > maxlevel) maxlevel = lvl;
+      continue;
+    }
+    if (open[j] >= 0) t[open[j]].closed = 1; /* j is read: later accumulations into j start a new task */
+    open[j] = -1;
+    int64_t o = open[i];
+    if (o >= 0 && !t[o].closed && lw[j] < t[o].level && t[o].n < RQB_MAX_SRCS) {
+      stask *k = &t[o];
+      k->src[k->n++] = RQB_SRC(base + j, beta);
+      if (beta != 1) k->gf = 1;
+      if (lr[j] < k->level) lr[j] = k->level;
+      continue;
+    }
+    uint32_t lvl = lw[i] > lw[j] ? lw[i] : lw[j];
+    if (lr[i] > lvl) lvl = lr[i];
+    lvl++;
+    if (o >= 0) t[o].closed = 1;
+    stask *k = &t[nt];
+    k->dst = i; k->level = lvl; k->n = 2; k->gf = beta != 1; k->closed = 0;
+    k->src[0] = RQB_SRC(base + i, 1);
+    k->src[1] = RQB_SRC(base + j, beta);
+    open[i] = (int64_t)nt++;
+    lw[i] = lvl;
+    if (lr[j] < lvl) lr[j] = lvl;
+    if (lvl > maxlevel) maxlevel = lvl;
+  }
+  if (!rc) {
+    scratch_t *sc = sc_get();
+    builder bd;
+    memset(&bd, 0, sizeof(bd));
+    bd.sc = sc;
+    for (size_t k = 0; k < nt; k++) b_task(&bd, t[k].gf ? RQB_T_GF : RQB_T_XOR, base + t[k].dst, 0, t[k].level, t[k].src, t[k].n);
+    for (uint32_t k = 0; k < nrows; k++) {
+      uint32_t src = RQB_SRC(base + gather_map[k], 1);
+      if (gather_map[k] >= nrows) {
+        rc = -1;
+        break;
+      }
+      b_task(&bd, RQB_T_XOR, out_base + k, 0, maxlevel + 1, &src, 1);
+    }
+    if (!rc) {
+      rqb_plan *plan = plan_acquire();
+      size_t tot_levels = 0;
+      rc = write_pages(&bd, plan, zero_row, &tot_levels);
+      if (rc) {
+        rqb_plan_free(plan);
+      } else {
+        memset(&plan->st, 0, sizeof(plan->st));
+        plan->st.n_levels = (int)tot_levels;
+        plan->st.n_tasks = (int)bd.nt;
+        plan->st.n_pages = (int)plan->n_pages;
+        plan->st.n_srcs = bd.tot_x;
+        plan->st.n_gf_srcs = bd.tot_gf;
+        plan->n_ws_rows = 0;
+        plan->n_rows = out_base + nrows;
+        plan->zero_row = zero_row;
+        *out = plan;
+      }
+    }
+  }
+  free(t);
+  free(lw);
+  free(lr);
+  free(open);
+  return rc;
 }

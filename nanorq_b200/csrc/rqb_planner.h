@@ -63,6 +63,11 @@ typedef struct rqb_plan {
 int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out);
 void rqb_plan_free(rqb_plan *p);
 
+/* one device program from an ordered sequence of reference-format row operations
+ * (rqb_rowop[nops]) followed by a row gather; see rqb_planner.c */
+int rqb_plan_from_schedule(const void *ops, size_t nops, uint32_t nrows, const uint32_t *gather_map, uint32_t base,
+                           uint32_t out_base, uint32_t zero_row, rqb_plan **out);
+
 int rqb_params_init(int K, rqb_params *P);
 /* host-side Tuple / index helpers over the built-in tables */
 int rqb_host_lt_indices(const rqb_params *P, uint32_t X, uint32_t *out);

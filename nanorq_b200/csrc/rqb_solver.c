@@ -114,6 +114,17 @@ static size_t pool_class(size_t bytes) {
   return round_up(bytes, (size_t)1 << 20);
 }
 
+/* slow-path events (each one takes the driver's global lock for milliseconds): fresh
+ * pinned / device allocations, arena regrowths, contexts created.  In steady state all
+ * of them must stay flat; rqb_slow_path_counters lets a benchmark check that. */
+static _Atomic unsigned long long g_cnt_alloc_pinned, g_cnt_alloc_dev, g_cnt_regrow, g_cnt_ctx_new;
+void rqb_slow_path_counters(unsigned long long out[4]) {
+  out[0] = g_cnt_alloc_pinned;
+  out[1] = g_cnt_alloc_dev;
+  out[2] = g_cnt_regrow;
+  out[3] = g_cnt_ctx_new;
+}
+
 static int pool_get(void **out, size_t bytes, int pinned) {
   size_t cls = pool_class(bytes);
   int dev = pinned ? -1 : rqb_dev_get();
@@ -129,6 +140,7 @@ static int pool_get(void **out, size_t bytes, int pinned) {
     }
   }
   pthread_mutex_unlock(&g_pool_mu);
+  if (pinned) g_cnt_alloc_pinned++; else g_cnt_alloc_dev++;
   return pinned ? rqb_host_malloc(out, cls) : rqb_dev_malloc(out, cls);
 }
 
@@ -184,6 +196,8 @@ struct rqb_solver {
   /* current program */
   rqb_plan *plan; /* owned unless shared */
   int plan_shared, has_c, timed;
+  int want_timing;       /* record CUDA events around the solve launch (rqb_solver_set_timing) */
+  uint32_t zero_row_set; /* arena row cleared as the ZERO row, +1 (0 = none yet) */
   uint8_t *d_pages, *h_pages; /* device copy / pinned staging of the program pages */
   size_t d_pages_cap, h_pages_cap;
   const uint8_t *cur_pages; /* device pointer actually used (own or cached) */
@@ -205,9 +219,9 @@ static int solver_wait(rqb_solver *s);
 static rqb_solver *g_shells;
 
 /* arena rows a fresh context gets: the fixed spaces plus room for the working rows of
- * a typical program (about 3.5 L, 6 L with the table rows of the four-Russians back-substitution; the arena is regrown if a program needs more) */
+ * a typical program (about 3.5 L, up to 6 L with the table rows of the back-substitution; 8 L reserved; the arena is regrown if a program needs more) */
 static size_t arena_rows_wanted(uint32_t max_in, uint32_t max_out, const rqb_params *P) {
-  size_t ws = 6 * (size_t)P->L + 512;
+  size_t ws = 8 * (size_t)P->L + 1024;
   const char *e = getenv("NANORQ_B200_WS_RESERVE"); /* tests: start small to exercise the regrowth */
   if (e && *e) ws = (size_t)strtoul(e, NULL, 10);
   return (size_t)max_in + max_out + (size_t)P->L + 1 + ws;
@@ -220,6 +234,8 @@ static int solver_layout(rqb_solver *s) {
   s->row0[RQB_SP_C] = s->max_in + s->max_out;
   s->zero_row = s->row0[RQB_SP_C] + (uint32_t)s->P.L;
   s->row0[RQB_SP_WS] = s->zero_row + 1;
+  if (s->zero_row_set == s->zero_row + 1) return 0; /* same layout as this context's last owner: still zero */
+  s->zero_row_set = s->zero_row + 1;
   s->busy = 1;
   return rqb_dev_memset(s->d_arena + (size_t)s->zero_row * s->pitch, 0, s->pitch, s->stream);
 }
@@ -334,7 +350,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     s->max_in = max_in;
     s->max_out = max_out;
     s->plan = NULL;
-    s->plan_shared = s->has_c = s->timed = 0;
+    s->plan_shared = s->has_c = s->timed = s->want_timing = 0;
     s->cur_pages = NULL;
     s->n_out_last = 0;
     s->next_shell = NULL;
@@ -353,6 +369,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     *out = s;
     return 0;
   }
+  g_cnt_ctx_new++;
   s = calloc(1, sizeof(*s));
   s->K = K;
   s->Kparams = Kparams;
@@ -464,7 +481,8 @@ static int solver_set_args(rqb_solver *s) {
     /* the program needs more working rows than the arena has: move the fixed spaces
      * (uploaded symbols included) into a larger one */
     uint8_t *bigger = NULL;
-    size_t cap = pool_class(need + need / 8);
+    size_t cap = pool_class(need + need / 4);
+    g_cnt_regrow++;
     int w = solver_wait(s);
     if (w) return w;
     DEV(pool_get((void **)&bigger, cap, 0));
@@ -474,6 +492,7 @@ static int solver_set_args(rqb_solver *s) {
     pool_put(s->d_arena, s->arena_cap, 0);
     s->d_arena = bigger;
     s->arena_cap = cap;
+    /* the ZERO row sits below the working rows and was copied with the fixed spaces */
   }
   rqb_solve_args *a = s->h_args;
   memset(a, 0, sizeof(*a));
@@ -603,12 +622,16 @@ int rqb_solver_run(rqb_solver *s) {
   if (!s->plan) return RQB_E_ARG;
   BIND(s->dev);
   s->busy = 1;
-  DEV(rqb_event_record(s->ev0, s->stream));
+  if (s->want_timing) DEV(rqb_event_record(s->ev0, s->stream));
   DEV(rqb_launch_solve(s->d_args, 1, s->h_args->width, s->stream));
-  DEV(rqb_event_record(s->ev1, s->stream));
-  s->timed = 1;
+  if (s->want_timing) DEV(rqb_event_record(s->ev1, s->stream));
+  s->timed = s->want_timing;
   return 0;
 }
+
+/* CUDA events around every solve launch of this solver (for rqb_solver_last_kernel_ms);
+ * off by default: two more driver calls per block matter at wire rate */
+void rqb_solver_set_timing(rqb_solver *s, int on) { s->want_timing = on != 0; }
 
 /* time a region of work queued on this solver's stream with CUDA events */
 int rqb_solver_mark(rqb_solver *s, int end) {
@@ -643,10 +666,10 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   }
   own->busy = 1;
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
-  DEV(rqb_event_record(own->ev0, own->stream));
+  if (own->want_timing) DEV(rqb_event_record(own->ev0, own->stream));
   DEV(rqb_launch_solve(d, n, h[0].width, own->stream));
-  DEV(rqb_event_record(own->ev1, own->stream));
-  own->timed = 1;
+  if (own->want_timing) DEV(rqb_event_record(own->ev1, own->stream));
+  own->timed = own->want_timing;
   return 0;
 }
 
@@ -884,27 +907,144 @@ int rqb_rowops_apply(rqb_matrix *m, const rqb_op *ops, size_t n) {
 }
 
 /* ------------------------------------------- reference-schedule replay */
-int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, long m1, const int *di,
-                        size_t rows, const int *c, size_t cols, float *ms_device) {
-  if (rows > m->rows || cols > m->rows || m0 < -1 || m1 < 0 || (size_t)m1 > nops || m0 >= (long)nops)
+/* the applied sequence of precode_matrix_apply_sched (lib/precode.c:23-32) and the two
+ * cycle-walk permutations (lib/precode.c:3-13,381-386) composed into one gather map */
+static int replay_prepare(size_t nr, const rqb_op *ops, size_t nops, long m0, long m1, const int *di,
+                          size_t rows, const int *c, size_t cols, rqb_rowop **seq_out, size_t *napp_out,
+                          uint32_t **map_out) {
+  if (rows > nr || cols > nr || m0 < -1 || m1 < 0 || (size_t)m1 > nops || m0 >= (long)nops)
     return RQB_E_ARG;
-  /* 1. the applied sequence of precode_matrix_apply_sched (lib/precode.c:23-32) */
   size_t napp = nops + 2 * (size_t)(m0 + 1), k = 0;
   rqb_rowop *seq = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
   for (long q = 0; q < m1; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
   for (long q = m0; q >= 0; q--) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
   for (long q = m1; q < (long)nops; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
   for (long q = 0; q <= m0; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
-  /* 2. levelise: an op runs after every earlier op that wrote one of its rows or
-   *    read its destination; ops of one level are then mutually independent */
+  for (size_t q = 0; q < napp; q++)
+    if (seq[q].i >= nr || (seq[q].beta && seq[q].j >= nr)) {
+      free(seq);
+      return RQB_E_ARG;
+    }
+  uint32_t *map = malloc(4 * nr);
+  for (size_t r = 0; r < nr; r++) map[r] = (uint32_t)r;
+  for (int pass = 0; pass < 2; pass++) {
+    size_t n = pass ? cols : rows;
+    int *P = malloc(sizeof(int) * (n ? n : 1));
+    memcpy(P, pass ? c : di, sizeof(int) * n);
+    for (size_t i = 0; i < n; i++) {
+      size_t at = i;
+      while (P[at] >= 0) {
+        uint32_t t = map[i];
+        map[i] = map[(size_t)P[at]];
+        map[(size_t)P[at]] = t;
+        int nx = P[at];
+        P[at] = -1;
+        at = (size_t)nx;
+      }
+    }
+    free(P);
+  }
+  *seq_out = seq;
+  *napp_out = napp;
+  *map_out = map;
+  return 0;
+}
+
+/* host only: the program rqb_schedule_replay would run, for a matrix of nrows rows laid out
+ * [rows | gathered rows | ZERO] (tests run it on the CPU interpreter) */
+int rqb_schedule_plan_blob(size_t nrows, const rqb_op *ops, size_t nops, long m0, long m1, const int *di, size_t rows,
+                           const int *c, size_t cols, rqb_plan_blob *out) {
+  rqb_rowop *seq = NULL;
+  uint32_t *map = NULL;
+  size_t napp = 0;
+  memset(out, 0, sizeof(*out));
+  int rc = replay_prepare(nrows, ops, nops, m0, m1, di, rows, c, cols, &seq, &napp, &map);
+  if (rc) return rc;
+  rqb_plan *p = NULL;
+  rc = rqb_plan_from_schedule(seq, napp, (uint32_t)nrows, map, 0, (uint32_t)nrows, (uint32_t)(2 * nrows), &p);
+  free(seq);
+  free(map);
+  if (rc) return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
+  out->n_pages = p->n_pages;
+  out->page_bytes = RQB_PAGE_BYTES;
+  out->row0[RQB_SP_IN] = 0;                     /* the matrix rows, updated in place  */
+  out->row0[RQB_SP_SYM] = (uint32_t)nrows;      /* (no emitted symbols)               */
+  out->row0[RQB_SP_C] = (uint32_t)nrows;        /* the gathered result                */
+  out->zero_row = (uint32_t)(2 * nrows);
+  out->row0[RQB_SP_WS] = out->zero_row + 1;
+  out->n_rows = out->zero_row + 1;
+  out->pages = p->pages;
+  out->opaque = p;
+  fill_stats(p, &out->stats);
+  return 0;
+}
+
+/* ONE launch: the schedule becomes a program for the solve kernel (rqb_plan_from_schedule:
+ * dependency levels inside the kernel, accumulations merged into gathers).  The matrix is
+ * copied into a scratch arena [rows | gathered rows | ZERO], replayed there and copied back. */
+int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, long m1, const int *di,
+                        size_t rows, const int *c, size_t cols, float *ms_device) {
+  BIND(m->dev);
+  rqb_rowop *seq = NULL;
+  uint32_t *map = NULL;
+  size_t napp = 0;
+  int rc = replay_prepare(m->rows, ops, nops, m0, m1, di, rows, c, cols, &seq, &napp, &map);
+  if (rc) return rc;
+  const size_t nr = m->rows;
+  rqb_plan *plan = NULL;
+  rc = rqb_plan_from_schedule(seq, napp, (uint32_t)nr, map, 0, (uint32_t)nr, (uint32_t)(2 * nr), &plan);
+  free(seq);
+  free(map);
+  if (rc) {
+    snprintf(g_err, sizeof(g_err), "rqb_plan_from_schedule failed (%d)", rc);
+    return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
+  }
+  uint8_t *arena = NULL, *d_pages = NULL;
+  rqb_solve_args *d_args = NULL, h_args;
+  const size_t pb = (size_t)plan->n_pages * RQB_PAGE_BYTES;
+  int e = rqb_dev_malloc((void **)&arena, (2 * nr + 1) * m->pitch);
+  e = e ? e : rqb_dev_malloc((void **)&d_pages, pb);
+  e = e ? e : rqb_dev_malloc((void **)&d_args, sizeof(h_args));
+  memset(&h_args, 0, sizeof(h_args));
+  h_args.base = arena;
+  h_args.pages = d_pages;
+  h_args.pitch = (uint32_t)m->pitch;
+  h_args.n_pages = plan->n_pages;
+  h_args.width = (uint32_t)round_up(m->T, 16);
+  e = e ? e : rqb_copy_h2d(d_pages, plan->pages, pb, m->stream); /* pageable source: staged before the call returns */
+  e = e ? e : rqb_copy_h2d(d_args, &h_args, sizeof(h_args), m->stream);
+  e = e ? e : rqb_dev_memset(arena + 2 * nr * m->pitch, 0, m->pitch, m->stream);
+  e = e ? e : rqb_event_record(m->ev0, m->stream);
+  e = e ? e : rqb_copy_d2d(arena, m->d, nr * m->pitch, m->stream);
+  e = e ? e : rqb_launch_solve(d_args, 1, h_args.width, m->stream);
+  e = e ? e : rqb_copy_d2d(m->d, arena + nr * m->pitch, nr * m->pitch, m->stream);
+  e = e ? e : rqb_event_record(m->ev1, m->stream);
+  e = e ? e : rqb_stream_sync(m->stream);
+  if (!e && ms_device) e = rqb_event_elapsed_ms(m->ev0, m->ev1, ms_device);
+  if (arena) rqb_dev_free(arena);
+  if (d_pages) rqb_dev_free(d_pages);
+  if (d_args) rqb_dev_free(d_args);
+  rqb_plan_free(plan);
+  if (e) return dev_fail(e, "rqb_schedule_replay");
+  return 0;
+}
+
+/* The literal form: every dependency level of the op list is one launch of the batched
+ * row-op kernel (oaxpy/oaddrow/oscal as they are), then the out-of-place gather. */
+int rqb_schedule_replay_stepwise(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, long m1, const int *di,
+                                 size_t rows, const int *c, size_t cols, float *ms_device) {
+  BIND(m->dev);
+  rqb_rowop *seq = NULL;
+  uint32_t *map = NULL;
+  size_t napp = 0;
+  int rc = replay_prepare(m->rows, ops, nops, m0, m1, di, rows, c, cols, &seq, &napp, &map);
+  if (rc) return rc;
+  /* levelise: an op runs after every earlier op that wrote one of its rows or
+   * read its destination; ops of one level are then mutually independent */
   uint32_t *lw = calloc(m->rows, 4), *lr = calloc(m->rows, 4), *lev = malloc(4 * (napp ? napp : 1));
   uint32_t nlev = 0;
   for (size_t q = 0; q < napp; q++) {
     uint32_t i = seq[q].i, l = lw[i] > lr[i] ? lw[i] : lr[i];
-    if (i >= m->rows || (seq[q].beta && seq[q].j >= m->rows)) {
-      free(seq); free(lw); free(lr); free(lev);
-      return RQB_E_ARG;
-    }
     if (seq[q].beta) {
       uint32_t j = seq[q].j;
       if (lw[j] > l) l = lw[j];
@@ -927,28 +1067,7 @@ int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, 
     for (size_t q = 0; q < napp; q++) sorted[cur[lev[q]]++] = seq[q];
     free(cur);
   }
-  /* 3. the two cycle-walk permutations (lib/precode.c:3-13,381-386) composed into one gather map */
   size_t nr = m->rows;
-  uint32_t *map = malloc(4 * nr);
-  for (size_t r = 0; r < nr; r++) map[r] = (uint32_t)r;
-  for (int pass = 0; pass < 2; pass++) {
-    size_t n = pass ? cols : rows;
-    int *P = malloc(sizeof(int) * (n ? n : 1));
-    memcpy(P, pass ? c : di, sizeof(int) * n);
-    for (size_t i = 0; i < n; i++) {
-      size_t at = i;
-      while (P[at] >= 0) {
-        uint32_t t = map[i];
-        map[i] = map[(size_t)P[at]];
-        map[(size_t)P[at]] = t;
-        int nx = P[at];
-        P[at] = -1;
-        at = (size_t)nx;
-      }
-    }
-    free(P);
-  }
-  /* 4. device: one launch per level, then the gather */
   rqb_rowop *d_ops = NULL;
   uint32_t *d_map = NULL;
   uint8_t *d_tmp = NULL;
@@ -970,6 +1089,6 @@ int rqb_schedule_replay(rqb_matrix *m, const rqb_op *ops, size_t nops, long m0, 
   if (d_map) rqb_dev_free(d_map);
   if (d_tmp) rqb_dev_free(d_tmp);
   free(seq); free(lw); free(lr); free(lev); free(start); free(sorted); free(map);
-  if (e) return dev_fail(e, "rqb_schedule_replay");
+  if (e) return dev_fail(e, "rqb_schedule_replay_stepwise");
   return 0;
 }

@@ -43,9 +43,22 @@ static uint8_t *row_ptr(spaces *sp, uint32_t row, int *rc) {
  * the spaces IN, SYM, C, WS; zero_row; n_rows in total.
  * returns 0 ok, 10 = intra-level hazard, 11 = malformed, 12 = misaligned, 13 = too many sources,
  * 14 = a task writes the input space or the ZERO row, 15 = an XOR list is not padded with the ZERO row */
+int rqb_interp_run_ex(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, uint32_t n_pages, const uint8_t *pages,
+                      const uint8_t *in, size_t in_rows, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_rows,
+                      size_t c_pitch, uint8_t *sym_out, size_t sym_rows, size_t sym_pitch, int in_writable);
+
 int rqb_interp_run(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, uint32_t n_pages, const uint8_t *pages,
                    const uint8_t *in, size_t in_rows, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_rows,
                    size_t c_pitch, uint8_t *sym_out, size_t sym_rows, size_t sym_pitch) {
+  return rqb_interp_run_ex(row0, zero_row, n_rows, n_pages, pages, in, in_rows, in_pitch, T, c_out, c_rows, c_pitch,
+                           sym_out, sym_rows, sym_pitch, 0);
+}
+
+/* in_writable: programs made from a reference schedule update the matrix rows (the
+ * input space) in place; solve programs never write their inputs */
+int rqb_interp_run_ex(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, uint32_t n_pages, const uint8_t *pages,
+                      const uint8_t *in, size_t in_rows, size_t in_pitch, size_t T, uint8_t *c_out, size_t c_rows,
+                      size_t c_pitch, uint8_t *sym_out, size_t sym_rows, size_t sym_pitch, int in_writable) {
   spaces sp;
   memset(&sp, 0, sizeof(sp));
   if (row0[RQB_SP_IN] != 0 || row0[RQB_SP_SYM] < in_rows || row0[RQB_SP_C] < row0[RQB_SP_SYM] + sym_rows ||
@@ -77,7 +90,7 @@ int rqb_interp_run(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, uin
       for (uint32_t k = 0; k < lh->n_tasks && !rc; k++) {
         const rqb_task *t = &tasks[k];
         uint32_t cnt = t->kind == RQB_T_SCAN ? t->nsrc : 1u;
-        if (t->dst < row0[RQB_SP_SYM] || t->dst == zero_row) { rc = 14; break; }
+        if ((!in_writable && t->dst < row0[RQB_SP_SYM]) || t->dst == zero_row) { rc = 14; break; }
         if (t->kind == RQB_T_SCAN && t->dst < row0[RQB_SP_WS]) { rc = 11; break; }
         for (uint32_t q = 0; q < cnt; q++) {
           uint32_t ref = t->dst + q;

@@ -120,7 +120,7 @@ INTERP_SO = os.path.join(ROOT, "oracle", "libplan_interp.so")
 _interp = None
 
 
-def interp_run(blob, inp, T, n_c, n_out):
+def interp_run(blob, inp, T, n_c, n_out, in_writable=False):
     """Run a plan blob (nanorq_b200.plan_blob) on the CPU interpreter.
     -> (rc, C[n_c,T], syms[n_out,T]); rc 10 = hazard inside a level, 12 = misaligned,
     13 = more than RQB_MAX_SRCS sources in a task, 14 = writes the input space / ZERO row,
@@ -129,15 +129,16 @@ def interp_run(blob, inp, T, n_c, n_out):
     if _interp is None:
         _interp = C.CDLL(INTERP_SO)
         sz = C.c_size_t
-        _interp.rqb_interp_run.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz,
-                                           u8p, sz, sz, u8p, sz, sz]
+        _interp.rqb_interp_run_ex.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz,
+                                              u8p, sz, sz, u8p, sz, sz, C.c_int]
     inp = np.ascontiguousarray(inp, dtype=np.uint8)
     row0 = np.asarray(blob["row0"], dtype=np.uint32)
     in_rows = min(inp.shape[0], int(row0[1]))  # rows past the plan's input space are never referenced
     cout = np.full((max(n_c, 1), T), 0x5A, np.uint8)
     sout = np.full((max(n_out, 1), T), 0x5A, np.uint8)
-    rc = _interp.rqb_interp_run(ptr(row0, u32p), blob["zero_row"], blob["n_rows"], blob["n_pages"], ptr(blob["pages"]),
-                                ptr(inp), in_rows, inp.strides[0], T, ptr(cout), n_c, T, ptr(sout), n_out, T)
+    rc = _interp.rqb_interp_run_ex(ptr(row0, u32p), blob["zero_row"], blob["n_rows"], blob["n_pages"],
+                                   ptr(blob["pages"]), ptr(inp), in_rows, inp.strides[0], T, ptr(cout), n_c, T,
+                                   ptr(sout), n_out, T, 1 if in_writable else 0)
     return rc, cout[:n_c], sout[:n_out]
 
 

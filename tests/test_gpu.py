@@ -248,7 +248,7 @@ def test_back_to_back_batches_on_one_stream():
 
 
 # ------------------------------------------------- reference-format replay
-@pytest.mark.parametrize("K,T", [(10, 64), (257, 48), (1024, 1280)])
+@pytest.mark.parametrize("K,T", [(10, 64), (257, 48), (1024, 1280), (4096, 1280)])
 def test_schedule_replay_of_reference_format_schedule(K, T):
     """Feed the oracle's (== reference's) sched_op list, marks and permutations to
     rqb_schedule_replay: D must become the intermediate symbols."""
@@ -261,20 +261,21 @@ def test_schedule_replay_of_reference_format_schedule(K, T):
     S = O.orc_invert(C.byref(p), 0, ptr(isi, u32p), C.byref(st))
     s = S.contents
     ops = np.zeros(s.nops, dtype=api.OP_DTYPE)
-    for k in range(s.nops):
-        ops[k] = (s.ops[k].beta, s.ops[k].i, s.ops[k].j)
-    di = np.array([s.di[k] for k in range(s.rows)], dtype=np.int32)
-    c = np.array([s.c[k] for k in range(s.cols)], dtype=np.int32)
+    C.memmove(ops.ctypes.data, s.ops, s.nops * 12)
+    di = np.ctypeslib.as_array(s.di, (s.rows,)).copy()
+    c = np.ctypeslib.as_array(s.c, (s.cols,)).copy()
     D = np.zeros((p.L, T), np.uint8)
     D[p.S + p.H:p.S + p.H + K] = src
-    m = nb.Matrix(p.L, T)
-    m.upload(D)
-    ms = m.schedule_replay(ops, s.marks[0], s.marks[1], di, c)
-    got = m.download()
-    O.orc_sched_free(S)
     want, _, _ = orc_encode(K, T, src)
-    print("replay K=%d: %.3f ms device" % (K, ms))
-    assert np.array_equal(got, want)
+    for stepwise in (False, True):  # one launch of the solve kernel / one row-op launch per dependency level
+        m = nb.Matrix(p.L, T)
+        m.upload(D)
+        ms = m.schedule_replay(ops, s.marks[0], s.marks[1], di, c, stepwise=stepwise)
+        got = m.download()
+        m.close()
+        print("replay K=%d %s: %.3f ms device" % (K, "stepwise" if stepwise else "one launch", ms))
+        assert np.array_equal(got, want)
+    O.orc_sched_free(S)
 
 
 # ------------------------------------------------------------ nanorq.h API

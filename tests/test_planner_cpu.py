@@ -148,3 +148,36 @@ def test_constructor_argument_errors():
     with pytest.raises(ValueError):
         nb.Decoder((640 << 24) | 63, 0)  # Al = 0
     assert api.tag(3, 0x01000005) == (3 << 24) | 5
+
+
+@pytest.mark.parametrize("K,T", [(10, 16), (26, 8), (257, 8), (1024, 8)])
+def test_reference_schedule_as_one_program_equals_oracle(K, T):
+    """rqb_schedule_replay's program (reference-format sched_op list -> one levelled gather
+    program, accumulations merged) run on the interpreter: the matrix becomes the
+    intermediate symbols, and the merged program has far fewer levels than ops."""
+    import ctypes as C
+    from nanorq_b200 import api
+    from oracle_lib import oracle, ptr, u32p
+    O = oracle()
+    p = orc_params(K)
+    src = kat_payload(K * T).reshape(K, T)
+    isi = np.arange(p.Kprime, dtype=np.uint32)
+    st = C.c_int()
+    S = O.orc_invert(C.byref(p), 0, ptr(isi, u32p), C.byref(st))
+    s = S.contents
+    ops = np.zeros(s.nops, dtype=api.OP_DTYPE)
+    C.memmove(ops.ctypes.data, s.ops, s.nops * 12)
+    di = np.ctypeslib.as_array(s.di, (s.rows,)).copy()
+    c = np.ctypeslib.as_array(s.c, (s.cols,)).copy()
+    rc, blob = nb.schedule_plan_blob(p.L, ops, s.marks[0], s.marks[1], di, c)
+    n_applied = s.nops + 2 * (s.marks[0] + 1)
+    O.orc_sched_free(S)
+    assert rc == 0
+    D = np.zeros((p.L, T), np.uint8)
+    D[p.S + p.H:p.S + p.H + K] = src
+    rc, cout, _ = interp_run(blob, D, T, p.L, 0, in_writable=True)
+    assert rc == 0
+    want, _, _ = orc_encode(K, T, src)
+    assert np.array_equal(cout, want)
+    assert blob["stats"]["n_tasks"] <= n_applied + p.L and blob["stats"]["n_levels"] < n_applied
+    print("K=%d: %d applied ops -> %d tasks in %d levels" % (K, n_applied, blob["stats"]["n_tasks"], blob["stats"]["n_levels"]))

@@ -44,8 +44,11 @@ try:
     D = np.zeros((sc.rows, T), np.uint8)
     D[q.S + q.H:q.S + q.H + Kr] = workload.payload(Kr, T, 2)
     m.upload(D)
+    ms = m.schedule_replay(ops, sc.marks[0], sc.marks[1], di, c, stepwise=True)
+    print("schedule replay K=%d stepwise (one row-op launch per level): %d ops, %.3f ms device" % (Kr, sc.nops, ms))
+    m.upload(D)
     ms = m.schedule_replay(ops, sc.marks[0], sc.marks[1], di, c)
-    print("schedule replay K=%d: %d ops, %.3f ms device" % (Kr, sc.nops, ms))
+    print("schedule replay K=%d as one program of the solve kernel: %.3f ms device" % (Kr, ms))
     m.close()
     oracle().orc_sched_free(S)
 except Exception as e:  # the capture of the LT kernel above is what matters
