@@ -181,3 +181,47 @@ def test_reference_schedule_as_one_program_equals_oracle(K, T):
     assert np.array_equal(cout, want)
     assert blob["stats"]["n_tasks"] <= n_applied + p.L and blob["stats"]["n_levels"] < n_applied
     print("K=%d: %d applied ops -> %d tasks in %d levels" % (K, n_applied, blob["stats"]["n_tasks"], blob["stats"]["n_levels"]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_op_list_as_one_program_equals_sequential_oracle(seed):
+    """Arbitrary reference-format op lists (axpy with beta 1 and beta > 1, oscal including the
+    no-op multipliers 0 and 1, a row added to itself, long accumulation runs, read-after-write
+    and write-after-read chains) turned into one program must equal the ops applied one by
+    one by the oracle's row kernels; plus a random final row permutation."""
+    import ctypes as C
+    from nanorq_b200 import api
+    from oracle_lib import Op, oracle
+    rng = np.random.default_rng(100 + seed)
+    nr, T, n = int(rng.integers(3, 40)), 24, int(rng.integers(1, 900))
+    D = rng.integers(0, 256, (nr, T), dtype=np.uint8)
+    ops = np.zeros(n, dtype=api.OP_DTYPE)
+    hot = rng.integers(0, nr, 3)  # a few destinations that accumulate a lot
+    for k in range(n):
+        kind = rng.random()
+        i = int(hot[rng.integers(0, 3)]) if rng.random() < 0.4 else int(rng.integers(0, nr))
+        if kind < 0.08:
+            ops[k] = (0, i, int(rng.integers(0, 256)))  # oscal, multiplier in j (0 and 1 are no-ops)
+        elif kind < 0.10:
+            ops[k] = (int(rng.integers(1, 256)), i, i)  # row added to itself
+        else:
+            ops[k] = (1 if rng.random() < 0.6 else int(rng.integers(2, 256)), i, int(rng.integers(0, nr)))
+    perm = rng.permutation(nr).astype(np.int32)
+    ident = np.arange(nr, dtype=np.int32)
+    # oracle: one op at a time, then the cycle-walk permutation of precode_matrix_permute
+    want = D.copy()
+    arr = (Op * n)()
+    for k in range(n):
+        arr[k].beta, arr[k].i, arr[k].j = int(ops["beta"][k]), int(ops["i"][k]), int(ops["j"][k])
+    oracle().orc_apply_ops(want.ctypes.data_as(C.POINTER(C.c_uint8)), T, T, arr, n)
+    P = perm.copy()
+    for i in range(nr):  # lib/precode.c:3-13
+        at = i
+        while P[at] >= 0:
+            tmp = want[i].copy(); want[i] = want[P[at]]; want[P[at]] = tmp
+            nxt = P[at]; P[at] = -1; at = nxt
+    rc, blob = nb.schedule_plan_blob(nr, ops, -1, 0, perm, ident)
+    assert rc == 0
+    rc, cout, _ = interp_run(blob, D, T, nr, 0, in_writable=True)
+    assert rc == 0
+    assert np.array_equal(cout, want)
