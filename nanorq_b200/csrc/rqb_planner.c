@@ -480,6 +480,16 @@ static void sort_by_level(int *rd, int *it, int n, int maxkey, uint64_t *tmp /* 
   }
 }
 
+/* NANORQ_B200_BACKSUB = tables | tables4 | triangular overrides the planner's choice of
+ * back-substitution (experiments); read once */
+static int g_fr_mode, g_fr_bits = 8;
+static pthread_once_t backsub_once = PTHREAD_ONCE_INIT;
+static void backsub_init(void) {
+  const char *e = getenv("NANORQ_B200_BACKSUB");
+  if (e && !strcmp(e, "tables4")) g_fr_bits = 4;
+  g_fr_mode = !e ? 0 : !strncmp(e, "tables", 6) ? 1 : !strcmp(e, "triangular") ? 2 : 0;
+}
+
 /* ---------------------------------------------------------------- planner */
 #define NONE_REF RQB_REF_NONE /* "this row is all zero / has no location" */
 
@@ -1092,12 +1102,8 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * D+E: patch b_top with U_top z and run the triangular solve again; fewer bytes, used when
    * u is so large (K' in the tens of thousands) that F's gathers would dominate. */
   const int ng = (U + 7) / 8;
-  static int fr_mode = -1, fr_bits = 8; /* NANORQ_B200_BACKSUB = tables | tables4 | triangular overrides the choice (experiments) */
-  if (fr_mode < 0) {
-    const char *e = getenv("NANORQ_B200_BACKSUB");
-    if (e && !strcmp(e, "tables4")) fr_bits = 4;
-    fr_mode = !e ? 0 : !strncmp(e, "tables", 6) ? 1 : !strcmp(e, "triangular") ? 2 : 0;
-  }
+  pthread_once(&backsub_once, backsub_init);
+  const int fr_mode = g_fr_mode, fr_bits = g_fr_bits;
   const int use_fr = I > 0 && fr_mode != 2 && (fr_mode == 1 || (size_t)ng * (size_t)I * 2 <= (size_t)nnz * 5);
   if (use_fr) {
     uint8_t *used8 = sc_buf(sc, SC_FRUSED, (size_t)ng * 256 + 64, 1);

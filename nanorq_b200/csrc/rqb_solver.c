@@ -34,16 +34,18 @@ static int dev_fail(int e, const char *what) {
 #include "rqb_hostcopy.h"
 #include "rqb_prof.h"
 static _Atomic unsigned long long g_prof_ns[RQB_PF_COUNT];
-static int g_prof_on = -1;
+static int g_prof_on;
+static pthread_once_t g_prof_once = PTHREAD_ONCE_INIT;
 static const char *const g_prof_names[RQB_PF_COUNT] = {
     "gen.load", "gen.upload", "gen.plan", "gen.run", "gen.sync", "emit.source", "emit.window", "add.create",
     "add.copy", "add.write", "repair.upload", "repair.request", "repair.plan", "repair.pages", "repair.args",
     "repair.run", "repair.fetch", "repair.write", "free"};
+static void prof_init(void) {
+  const char *e = getenv("NANORQ_B200_PROFILE");
+  g_prof_on = e && e[0] == '1';
+}
 int rqb_prof_enabled(void) {
-  if (g_prof_on < 0) {
-    const char *e = getenv("NANORQ_B200_PROFILE");
-    g_prof_on = e && e[0] == '1';
-  }
+  pthread_once(&g_prof_once, prof_init);
   return g_prof_on;
 }
 double rqb_prof_now(void) {
