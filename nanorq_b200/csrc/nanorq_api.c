@@ -12,6 +12,13 @@
 #include "rqb_hostcopy.h"
 #include "rqb_prof.h"
 
+#ifndef UPLOAD_CHUNK
+#define UPLOAD_CHUNK 512u /* rows per host->device copy queued while the block is still being read */
+#endif
+#ifndef WINDOW_DIV
+#define WINDOW_DIV 4u /* repair symbols produced per device window: K / WINDOW_DIV (32..8192) */
+#endif
+
 #define Z_MAX 256
 #define K_MAX 56403
 
@@ -207,7 +214,7 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
     b->gaps = K;
   } else {
     max_in = (uint32_t)K;
-    b->win_cap = (uint32_t)(K / 4 < 32 ? 32 : (K / 4 > 8192 ? 8192 : K / 4));
+    b->win_cap = (uint32_t)(K / WINDOW_DIV < 32 ? 32 : (K / WINDOW_DIV > 8192 ? 8192 : K / WINDOW_DIV));
     max_out = b->win_cap;
   }
   b->in_cap = max_in;
@@ -220,7 +227,6 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   return b;
 }
 
-#define UPLOAD_CHUNK 512u /* rows per host->device copy queued while the block is still being read */
 
 static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
   /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging

@@ -218,7 +218,7 @@ const uint8_t *rqb_solver_sym_mirror(rqb_solver *s) { return s->h_sym; }
  * free list and is handed out again to the next create with the same device and
  * symbol size whose rows fit. */
 static int solver_wait(rqb_solver *s);
-static rqb_solver *g_shells;
+static rqb_solver *g_shells, **g_shells_tail = &g_shells;
 
 /* arena rows a fresh context gets: the fixed spaces plus room for the working rows of
  * a typical program (about 3.5 L, up to 6 L with the table rows of the back-substitution; 8 L reserved; the arena is regrown if a program needs more) */
@@ -280,9 +280,8 @@ void rqb_solver_destroy(rqb_solver *s) {
   }
   s->next_shell = NULL;
   pthread_mutex_lock(&g_shell_mu); /* appended at the tail: the list is oldest-first */
-  rqb_solver **pp = &g_shells;
-  while (*pp) pp = &(*pp)->next_shell;
-  *pp = s;
+  *g_shells_tail = s;
+  g_shells_tail = &s->next_shell;
   pthread_mutex_unlock(&g_shell_mu);
 }
 
@@ -291,6 +290,7 @@ void rqb_release_cached(void) {
   pthread_mutex_lock(&g_shell_mu);
   rqb_solver *s = g_shells;
   g_shells = NULL;
+  g_shells_tail = &g_shells;
   pthread_mutex_unlock(&g_shell_mu);
   while (s) {
     rqb_solver *n = s->next_shell;
@@ -342,6 +342,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     if (best) {
       s = *best;
       *best = s->next_shell;
+      if (g_shells_tail == &s->next_shell) g_shells_tail = best;
     }
   }
   pthread_mutex_unlock(&g_shell_mu);

@@ -38,6 +38,8 @@ def counters():
 for w in range(3):
     run(min(nb, 2 * threads), 900 + w)
 c0 = counters()
+import resource
+ru0 = resource.getrusage(resource.RUSAGE_SELF)
 tot, parts = 0.0, [0.0] * 4
 per = []
 for s in range(steps):
@@ -46,6 +48,12 @@ for s in range(steps):
     per.append(round(2 * 8 * K * T * nb / r.wall_s / 1e9, 1))
     for k, v in enumerate((r.t_gen, r.t_emit, r.t_add, r.t_repair)):
         parts[k] += v
+ru1 = resource.getrusage(resource.RUSAGE_SELF)
+print("   CPU per block: user %.2f ms, sys %.2f ms; wall x cores per block %.2f ms (%d cores)" % (
+    1e3 * (ru1.ru_utime - ru0.ru_utime) / (nb * steps), 1e3 * (ru1.ru_stime - ru0.ru_stime) / (nb * steps),
+    1e3 * tot * (os.cpu_count() or 1) / (nb * steps), os.cpu_count() or 1),
+    "| minor faults per block %.0f, vol/invol ctx switches per block %.1f/%.1f" % (
+    (ru1.ru_minflt - ru0.ru_minflt) / (nb * steps), (ru1.ru_nvcsw - ru0.ru_nvcsw) / (nb * steps), (ru1.ru_nivcsw - ru0.ru_nivcsw) / (nb * steps)))
 print("   slow-path events during the timed steps {pinned, device, regrow, contexts}:", None if c0 is None else [a - b for a, b in zip(counters(), c0)])
 print("%s: %.1f Gbit/s (per step %s) phases ms/block %s" % (os.path.basename(libdir.rstrip("/")), 2 * 8 * K * T * nb * steps / tot / 1e9, per,
                                                        [round(1e3 * x / (nb * steps), 2) for x in parts]))
