@@ -7,6 +7,7 @@ the thin ctypes mirror of that ABI used by the tests and by bench.py.
 from .api import (  # noqa: F401
     Decoder,
     Encoder,
+    FileIO,
     Matrix,
     MemIO,
     Solver,

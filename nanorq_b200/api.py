@@ -352,6 +352,26 @@ class MemIO:
         self.close()
 
 
+class FileIO:
+    """ioctx_from_file / ioctx_mmap_file (reference lib/io.c:54,338); mode 1 = read (encoder),
+    0 = create (decoder)."""
+    ptr = None
+
+    def __init__(self, path, mode, mmap=False):
+        fn = lib().ioctx_mmap_file if mmap else lib().ioctx_from_file
+        self.ptr = fn(os.fsencode(path), mode)
+        if not self.ptr:
+            raise OSError("cannot open %r" % (path,))
+
+    def close(self):
+        if self.ptr:
+            C.cast(self.ptr, C.POINTER(_IoCtx)).contents.destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
 class _IoCtx(C.Structure):
     _fields_ = [("read", vp), ("write", vp), ("seek", vp), ("size", vp), ("tell", vp),
                 ("destroy", C.CFUNCTYPE(None, vp)), ("seekable", C.c_bool), ("writable", C.c_bool)]

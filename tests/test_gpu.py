@@ -442,3 +442,34 @@ def test_c4_eight_blocks_of_one_object_roundtrip():
     assert enc.blocks() == Z and all(enc.block_symbols(b) == K for b in range(Z))
     assert ok
     assert np.array_equal(out, payload)
+
+
+@pytest.mark.parametrize("mmap", [False, True])
+def test_api_file_and_mmap_ioctx_roundtrip(tmp_path, mmap):
+    """encode.c / decode.c style: the object is read from a file ioctx and the decoded object
+    is written through a file ioctx (stdio or mmap), ragged last symbol included."""
+    F, T = 200003, 256
+    rng = np.random.default_rng(21)
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    src_path, out_path = tmp_path / "in.bin", tmp_path / "out.bin"
+    payload.tofile(src_path)
+    enc = nb.Encoder(F, T, 0, 0, 8)  # K = Z = 0: at least 16 blocks
+    io_in = nb.FileIO(src_path, 1, mmap=mmap)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    io_out = nb.FileIO(out_path, 0, mmap=mmap)
+    assert enc.blocks() >= 16
+    for sbn in range(enc.blocks()):
+        Kb = enc.block_symbols(sbn)
+        drop = rng.random(Kb) < 0.15
+        esis = [int(e) for e in np.nonzero(~drop)[0]] + list(range(Kb, Kb + int(drop.sum()) + 2))
+        for esi in esis:
+            sym = enc.encode(esi, sbn, io_in)
+            assert sym is not None
+            assert dec.add_symbol(sym, api.tag(sbn, esi), io_out) in (nb.SYM_ADDED, nb.SYM_IGN)
+        assert dec.repair_block(io_out, sbn)
+    io_in.close()
+    io_out.close()
+    dec.close()
+    enc.close()
+    got = np.fromfile(out_path, dtype=np.uint8)
+    assert len(got) == F and np.array_equal(got, payload)
