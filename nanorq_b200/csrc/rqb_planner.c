@@ -255,7 +255,8 @@ static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + list_bytes(
 
 /* pack the tasks, level by level, into pages (a level may be split over pages:
  * its tasks are independent).  Returns 0 or a negative error. */
-static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *tot_levels) {
+static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *tot_levels, uint8_t *ext_buf,
+                       size_t ext_cap) {
   scratch_t *sc = b->sc;
   const uint32_t nl = b->max_level + 1;
   /* one stable counting sort by (level, kind, narrow/wide list): tasks that take the
@@ -264,18 +265,26 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nkeys + 2) * 4, 1);
   uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
 #define TKEY(t) ((t).level * 4 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
-  for (size_t k = 0; k < b->nt; k++) cnt[TKEY(b->tasks[k]) + 1]++;
+  size_t tot_bytes = 0;
+  for (size_t k = 0; k < b->nt; k++) {
+    cnt[TKEY(b->tasks[k]) + 1]++;
+    tot_bytes += task_bytes(&b->tasks[k]);
+  }
   for (uint32_t l = 0; l < nkeys; l++) cnt[l + 1] += cnt[l];
   for (size_t k = 0; k < b->nt; k++) order[cnt[TKEY(b->tasks[k])]++] = (uint32_t)k;
 #undef TKEY
   /* cnt[key] now holds the END of its bucket: level l spans [cnt[4l-1], cnt[4l+3]) */
   size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
-  uint8_t *pages = plan->pages;
+  /* into the caller's buffer when the program certainly fits: the tasks, a header per level
+   * (levels split over pages get one per piece) and up to 512 unused bytes at the end of a page */
+  const size_t worst = ((tot_bytes + (size_t)nl * 32) / (RQB_PAGE_BYTES - 512) + 2) * RQB_PAGE_BYTES;
+  const int ext = ext_buf && worst <= ext_cap;
+  uint8_t *pages = ext ? ext_buf : plan->own_pages;
 #define OPEN_PAGE()                                                         \
   do {                                                                      \
-    if ((npages + 1) * RQB_PAGE_BYTES > plan->pages_cap) {                  \
+    if (!ext && (npages + 1) * RQB_PAGE_BYTES > plan->pages_cap) {          \
       plan->pages_cap = (npages + 64) * 2 * RQB_PAGE_BYTES;                 \
-      pages = plan->pages = realloc(plan->pages, plan->pages_cap);          \
+      pages = plan->own_pages = realloc(plan->own_pages, plan->pages_cap);  \
     }                                                                       \
     memset(pages + npages * RQB_PAGE_BYTES, 0, RQB_PAGE_BYTES);             \
     npages++;                                                               \
@@ -337,6 +346,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
 #undef OPEN_PAGE
 #undef CLOSE_PAGE
   plan->n_pages = (uint32_t)npages;
+  plan->pages = pages;
   *tot_levels = levels;
   return 0;
 }
@@ -1228,7 +1238,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   FINE(13);
   rqb_plan *plan = plan_acquire();
   size_t tot_levels = 0;
-  rc = write_pages(&bd, plan, zero_row, &tot_levels);
+  rc = write_pages(&bd, plan, zero_row, &tot_levels, req->pages_buf, req->pages_buf_cap);
   if (rc) {
     rqb_plan_free(plan);
     return rc;
@@ -1363,7 +1373,7 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
     if (!rc) {
       rqb_plan *plan = plan_acquire();
       size_t tot_levels = 0;
-      rc = write_pages(&bd, plan, zero_row, &tot_levels);
+      rc = write_pages(&bd, plan, zero_row, &tot_levels, NULL, 0);
       if (rc) {
         rqb_plan_free(plan);
       } else {

@@ -29,6 +29,9 @@ typedef struct {
   const uint32_t *out_isi; /* [n_out] internal symbol ids                                   */
   uint32_t in_rows;        /* rows the arena reserves for the input space  (> every in_row) */
   uint32_t sym_rows;       /* rows the arena reserves for emitted symbols  (>= n_out)       */
+  uint8_t *pages_buf;      /* optional: write the program here (e.g. pinned memory the DMA    */
+  size_t pages_buf_cap;    /* engine reads) instead of the plan's own buffer; if it is too     */
+                           /* small the plan's buffer is used (plan->pages tells which)        */
 } rqb_plan_request;
 
 typedef struct {
@@ -50,8 +53,9 @@ typedef struct rqb_plan {
   uint32_t n_rows;     /* arena rows the program addresses: row0[WS] + n_ws_rows */
   uint32_t zero_row;   /* the all-zero row (the solver clears it, nothing writes it) */
   uint32_t n_pages;
-  uint8_t *pages;      /* n_pages * RQB_PAGE_BYTES                              */
-  size_t pages_cap;    /* bytes allocated behind pages (plans are recycled)     */
+  uint8_t *pages;      /* n_pages * RQB_PAGE_BYTES: own_pages or the request's pages_buf */
+  uint8_t *own_pages;  /* the plan's own buffer (plans are recycled)            */
+  size_t pages_cap;    /* bytes allocated behind own_pages                      */
   struct rqb_plan *next_free;
   uint32_t n_c_rows;   /* rows written to c_out (L or 0)                        */
   uint32_t n_out;

@@ -524,6 +524,22 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   pr.out_isi = req->out_isi;
   pr.in_rows = s->max_in;
   pr.sym_rows = s->max_out;
+  /* the planner writes the program straight into this solver's pinned page buffer (no copy of
+   * ~1 MB per block); the buffer must not still be the source of the previous program's upload */
+  {
+    size_t want = (size_t)400 * (size_t)s->P.L; /* measured: ~300 bytes of program per intermediate symbol */
+    if (s->h_pages_cap < want || s->d_pages_cap < want) {
+      int rc0 = ensure_cap(s, (void **)&s->d_pages, &s->d_pages_cap, want, 0);
+      rc0 = rc0 ? rc0 : ensure_cap(s, (void **)&s->h_pages, &s->h_pages_cap, want, 1);
+      if (rc0) return rc0;
+    }
+    if (s->pages_pending) {
+      int w = solver_wait(s);
+      if (w) return w;
+    }
+  }
+  pr.pages_buf = s->h_pages;
+  pr.pages_buf_cap = s->h_pages_cap < s->d_pages_cap ? s->h_pages_cap : s->d_pages_cap;
   rqb_plan *p = NULL;
   PF_T0;
   int rc = rqb_plan_build(&pr, &p);
@@ -537,23 +553,13 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   s->plan = p;
   s->plan_shared = 0;
   size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
-  /* room for the largest program this block size is likely to see (measured: ~300 bytes of
-   * program per intermediate symbol), so that in steady state no thread allocates pinned
-   * or device memory: those calls take milliseconds under the driver's global lock and
-   * stall every other thread's launches */
-  size_t want = pb > (size_t)400 * (size_t)s->P.L ? pb : (size_t)400 * (size_t)s->P.L;
-  if (pb > s->d_pages_cap || pb > s->h_pages_cap) {
+  if (p->pages != s->h_pages) { /* the program did not fit the pinned buffer: grow it and copy */
+    size_t want = pb + pb / 4;
     rc = ensure_cap(s, (void **)&s->d_pages, &s->d_pages_cap, want, 0);
     rc = rc ? rc : ensure_cap(s, (void **)&s->h_pages, &s->h_pages_cap, want, 1);
+    if (rc) return rc;
+    memcpy(s->h_pages, p->pages, pb);
   }
-  if (rc) return rc;
-  /* the pages go through pinned memory so that the copy is truly asynchronous; the
-   * staging buffer may be rewritten by the next plan only after this copy has run */
-  if (s->pages_pending) {
-    int w = solver_wait(s);
-    if (w) return w;
-  }
-  memcpy(s->h_pages, p->pages, pb);
   s->pages_pending = 1;
   s->busy = 1;
   DEV(rqb_copy_h2d(s->d_pages, s->h_pages, pb, s->stream));
@@ -582,7 +588,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
       in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
     }
     for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
-    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out};
+    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0};
     rqb_plan *p = NULL;
     int rc = rqb_plan_build(&pr, &p);
     free(isi);
@@ -752,7 +758,7 @@ int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out)
   for (int k = 0; k < P.Kprime + req->overhead; k++)
     if (req->in_row[k] != RQB_NO_ROW && req->in_row[k] >= in_rows) in_rows = req->in_row[k] + 1;
   rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi,
-                         in_rows, req->n_out ? req->n_out : 1};
+                         in_rows, req->n_out ? req->n_out : 1, NULL, 0};
   rqb_plan *p = NULL;
   int rc = rqb_plan_build(&pr, &p);
   if (rc == 1) return RQB_NEED_MORE;
