@@ -16,7 +16,7 @@
 #define UPLOAD_CHUNK 512u /* rows per host->device copy queued while the block is still being read */
 #endif
 #ifndef WINDOW_DIV
-#define WINDOW_DIV 4u /* repair symbols produced per device window: K / WINDOW_DIV (32..8192) */
+#define WINDOW_DIV 8u /* repair symbols produced per device window: K / WINDOW_DIV (32..8192) */
 #endif
 
 #define Z_MAX 256

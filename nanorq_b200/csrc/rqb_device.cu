@@ -191,6 +191,31 @@ __device__ __noinline__ void task_gf(const Rows R, const uint32_t *sp, uint32_t 
   R.st(dst, acc);
 }
 
+// TAB: row[dst] = row[src0] ^ XOR_j row[tab_base + 256*j + b_j] over the non-zero bytes b_j of
+// one row of the bit matrix G (the back-substitution x = Y ^ G z through 8-bit XOR tables).
+// Eight table rows are requested at a time; a zero byte selects the ZERO row, so the loads
+// need no predicates.
+__device__ __noinline__ void task_tab(const Rows R, const uint32_t *sp, uint32_t nbytes, uint32_t dst, uint32_t src0,
+                                      uint32_t tab_base, uint32_t zero_row) {
+  uint4 acc = R.ld(src0);
+  for (uint32_t j0 = 0; j0 < nbytes; j0 += 8) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(sp + j0 / 4); // bytes j0 .. j0+7 (the list is zero-padded)
+    uint32_t row[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t b = ((k < 4 ? w.x : w.y) >> (8 * (k & 3))) & 0xffu;
+      row[k] = b ? tab_base + ((j0 + k) << 8) + b : zero_row;
+    }
+    uint4 v0 = R.ld(row[0]), v1 = R.ld(row[1]), v2 = R.ld(row[2]), v3 = R.ld(row[3]);
+    uint4 v4 = R.ld(row[4]), v5 = R.ld(row[5]), v6 = R.ld(row[6]), v7 = R.ld(row[7]);
+    acc.x ^= xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+    acc.y ^= xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+    acc.z ^= xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+    acc.w ^= xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+  }
+  R.st(dst, acc);
+}
+
 __global__ void __launch_bounds__(kSolveThreads, kSolveMinCtas)
 rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -230,7 +255,7 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
     const uint32_t n_levels = reinterpret_cast<const rqb_page_hdr *>(page)->n_levels;
     uint32_t off = sizeof(rqb_page_hdr);
     for (uint32_t lv = 0; lv < n_levels; lv++) {
-      const uint4 lh = *reinterpret_cast<const uint4 *>(page + off); // n_tasks, next_off
+      const uint4 lh = *reinterpret_cast<const uint4 *>(page + off); // n_tasks, next_off, tab_base, zero_row
       const uint4 *tasks = reinterpret_cast<const uint4 *>(page + off + sizeof(rqb_level_hdr));
       if (active) {
         for (uint32_t t = grp; t < lh.x; t += kTaskGroups) {
@@ -257,6 +282,8 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
               acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
             }
             R.st(th.y, acc);
+          } else if (kind == RQB_T_TAB) {
+            task_tab(R, sp, nsrc, th.y, th.w, lh.z, lh.w);
           } else if (kind == RQB_T_SCAN) {
             task_scan(R, sp, nsrc, th.y);
           } else {

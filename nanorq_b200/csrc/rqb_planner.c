@@ -167,6 +167,7 @@ static void *sc_grow(scratch_t *sc, int id, size_t bytes) {
 /* ------------------------------------------------------ program builder */
 typedef struct {
   uint32_t dst, src_at, level;
+  uint32_t extra; /* TAB: src0 */
   uint16_t nsrc;
   uint8_t kind, aux;
 } ptask;
@@ -179,6 +180,7 @@ typedef struct {
   size_t ns;
   uint32_t ws_base; /* arena row of working row 0 */
   uint32_t ws_next; /* next unused working row */
+  uint32_t tab_base; /* first row of the XOR tables of the back-substitution */
   uint32_t max_level;
   size_t tot_x, tot_gf, tot_h;
 } builder;
@@ -193,6 +195,7 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
   t->nsrc = (uint16_t)n;
   t->kind = (uint8_t)kind;
   t->aux = (uint8_t)aux;
+  t->extra = 0;
   if (kind == RQB_T_GF) {
     if (n) memcpy(b->srcs + b->ns, srcs, (size_t)n * sizeof(uint32_t));
   } else { /* XOR and SCAN sources are bare row numbers */
@@ -206,6 +209,28 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
     b->tot_h += n;
   else
     b->tot_x += n;
+}
+
+/* TAB task: row[dst] = row[src0] ^ XOR_j table row (j, bytes[j]); the nbytes bytes go where
+ * other tasks keep their source list */
+static void b_tab(builder *b, uint32_t dst, uint32_t src0, uint32_t level, const uint8_t *bytes, uint32_t nbytes) {
+  const uint32_t words = (nbytes + 3) / 4;
+  b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
+  b->srcs = sc_grow(b->sc, SC_SRCS, (b->ns + words + 1) * sizeof(uint32_t));
+  ptask *t = &b->tasks[b->nt++];
+  t->dst = dst;
+  t->src_at = (uint32_t)b->ns;
+  t->level = level;
+  t->extra = src0;
+  t->nsrc = (uint16_t)nbytes;
+  t->kind = RQB_T_TAB;
+  t->aux = 0;
+  b->srcs[b->ns + words - 1] = 0;
+  memcpy(b->srcs + b->ns, bytes, nbytes);
+  b->ns += words;
+  if (level > b->max_level) b->max_level = level;
+  for (uint32_t k = 0; k < nbytes; k++) b->tot_x += bytes[k] != 0;
+  b->tot_x += 1;
 }
 
 /* row[dst] = sum of n sources that all exist before `level`: one task, or a
@@ -249,6 +274,7 @@ static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint3
 /* bytes of a task's source list in the page: XOR lists are padded to 4 or 8 entries */
 static size_t list_bytes(const ptask *t) {
   if (t->kind == RQB_T_XOR) return t->nsrc <= 4 ? 16 : 32;
+  if (t->kind == RQB_T_TAB) return ((size_t)t->nsrc + 15) & ~(size_t)15;
   return ((size_t)t->nsrc * 4 + 15) & ~(size_t)15;
 }
 static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + list_bytes(t); }
@@ -261,10 +287,10 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   const uint32_t nl = b->max_level + 1;
   /* one stable counting sort by (level, kind, narrow/wide list): tasks that take the
    * same path through the kernel sit together inside a level */
-  const uint32_t nkeys = nl * 4;
+  const uint32_t nkeys = nl * 5;
   uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nkeys + 2) * 4, 1);
   uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
-#define TKEY(t) ((t).level * 4 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
+#define TKEY(t) ((t).level * 5 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
   size_t tot_bytes = 0;
   for (size_t k = 0; k < b->nt; k++) {
     cnt[TKEY(b->tasks[k]) + 1]++;
@@ -273,7 +299,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   for (uint32_t l = 0; l < nkeys; l++) cnt[l + 1] += cnt[l];
   for (size_t k = 0; k < b->nt; k++) order[cnt[TKEY(b->tasks[k])]++] = (uint32_t)k;
 #undef TKEY
-  /* cnt[key] now holds the END of its bucket: level l spans [cnt[4l-1], cnt[4l+3]) */
+  /* cnt[key] now holds the END of its bucket: level l spans [cnt[5l-1], cnt[5l+4]) */
   size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
   /* into the caller's buffer when the program certainly fits: the tasks, a header per level
    * (levels split over pages get one per piece) and up to 512 unused bytes at the end of a page */
@@ -297,7 +323,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
     cur = 0;                                                                                      \
   } while (0)
   for (uint32_t l = 0; l < nl; l++) {
-    size_t lo = l ? cnt[4 * l - 1] : 0, hi = cnt[4 * l + 3];
+    size_t lo = l ? cnt[5 * l - 1] : 0, hi = cnt[5 * l + 4];
     if (lo == hi) continue;
     size_t idx = lo;
     while (idx < hi) {
@@ -319,12 +345,14 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
       size_t n = j - idx;
       lh->n_tasks = (uint32_t)n;
       lh->next_off = (uint32_t)(cur + need);
+      lh->tab_base = b->tab_base;
+      lh->zero_row = zero_row;
       rqb_task *dst = (rqb_task *)(page + cur + sizeof(rqb_level_hdr));
       uint32_t soff = (uint32_t)(cur + sizeof(rqb_level_hdr) + n * sizeof(rqb_task));
       for (size_t k = 0; k < n; k++) {
         const ptask *t = &b->tasks[order[idx + k]];
         size_t sb = list_bytes(t);
-        memcpy(page + soff, b->srcs + t->src_at, (size_t)t->nsrc * 4);
+        memcpy(page + soff, b->srcs + t->src_at, t->kind == RQB_T_TAB ? (size_t)t->nsrc : (size_t)t->nsrc * 4);
         if (t->kind == RQB_T_XOR)
           for (size_t q = t->nsrc; q < sb / 4; q++) ((uint32_t *)(page + soff))[q] = zero_row;
         dst[k].src_off = soff;
@@ -332,7 +360,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
         dst[k].nsrc = t->nsrc;
         dst[k].kind = t->kind;
         dst[k].aux = t->aux;
-        dst[k].pad = 0;
+        dst[k].pad = t->extra;
         soff += (uint32_t)sb;
       }
       cur += need;
@@ -490,13 +518,12 @@ static void sort_by_level(int *rd, int *it, int n, int maxkey, uint64_t *tmp /* 
   }
 }
 
-/* NANORQ_B200_BACKSUB = tables | tables4 | triangular overrides the planner's choice of
+/* NANORQ_B200_BACKSUB = tables | triangular overrides the planner's choice of
  * back-substitution (experiments); read once */
-static int g_fr_mode, g_fr_bits = 8;
+static int g_fr_mode;
 static pthread_once_t backsub_once = PTHREAD_ONCE_INIT;
 static void backsub_init(void) {
   const char *e = getenv("NANORQ_B200_BACKSUB");
-  if (e && !strcmp(e, "tables4")) g_fr_bits = 4;
   g_fr_mode = !e ? 0 : !strncmp(e, "tables", 6) ? 1 : !strcmp(e, "triangular") ? 2 : 0;
 }
 
@@ -1104,8 +1131,8 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * F ("four Russians"): x_p = Y_p ^ (G z)_p with Y from phase A and G = X^-1 U_top, the
    * bit matrix the host already holds.  G is dense (about a third of its bits are set), so
    * the u inactive symbols are taken 8 at a time: table rows T_j[m] = XOR of the z of group j
-   * selected by the byte m (built from two 4-bit half tables, 2 levels), and every x_p is a
-   * gather of at most ceil(u/8) table rows.  Costs more sources than a second triangular
+   * selected by the byte m (built from two 4-bit half tables, 2 levels), and every x_p is ONE
+   * table-gather task (RQB_T_TAB) of at most ceil(u/8) table rows.  Costs more sources than a second triangular
    * solve but needs 4 levels instead of ~500 -- the solve kernel is bound by the latency of
    * its dependency levels, not by bytes.
    *
@@ -1113,77 +1140,53 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * u is so large (K' in the tens of thousands) that F's gathers would dominate. */
   const int ng = (U + 7) / 8;
   pthread_once(&backsub_once, backsub_init);
-  const int fr_mode = g_fr_mode, fr_bits = g_fr_bits;
+  const int fr_mode = g_fr_mode;
   const int use_fr = I > 0 && fr_mode != 2 && (fr_mode == 1 || (size_t)ng * (size_t)I * 2 <= (size_t)nnz * 5);
   if (use_fr) {
+    /* table rows sit at fixed positions, tab_base + 256*j + m, so that a TAB task needs
+     * nothing but the bytes of its row of G; only the entries some row uses (and the two
+     * half-table entries they are made of) are computed */
     uint8_t *used8 = sc_buf(sc, SC_FRUSED, (size_t)ng * 256 + 64, 1);
-    uint32_t *tab8 = sc_buf(sc, SC_FRTAB, sizeof(uint32_t) * ((size_t)ng * 256 + (size_t)ng * 32), 0);
-    uint32_t *tab4 = tab8 + (size_t)ng * 256; /* [ng][2][16] */
+    const uint32_t tab0 = bd.ws_next;
+    bd.tab_base = bd.ws_base + tab0;
+    bd.ws_next += (uint32_t)ng * 256u;
     for (int p = 0; p < I; p++) {
       const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
       for (int j = 0; j < ng; j++) used8[(size_t)j * 256 + g[j]] = 1;
     }
     for (int j = 0; j < ng; j++) {
-      uint8_t need4[2][16];
-      memset(need4, 0, sizeof(need4));
+      uint8_t *use = used8 + (size_t)j * 256;
       for (int m = 1; m < 256; m++)
-        if (used8[(size_t)j * 256 + m]) {
-          need4[0][m & 15] = 1;
-          need4[1][m >> 4] = 1;
-        }
-      for (int half = 0; half < 2; half++)
-        for (int v = 1; v < 16; v++) {
-          uint32_t *slot = &tab4[((size_t)j * 2 + half) * 16 + v];
-          *slot = NONE_REF;
-          if (!need4[half][v]) continue;
-          uint32_t ns = 0;
-          for (int bit = 0; bit < 4; bit++)
-            if (v >> bit & 1) {
-              int t = 8 * j + 4 * half + bit;
-              if (t < U) PUSH(ns, loc[Z + (uint32_t)t]);
-            }
-          if (ns == 1) {
-            *slot = tmp[0] & RQB_REF_MASK; /* a single z: no table row needed */
-          } else if (ns > 1) {
-            uint32_t r = bd.ws_base + bd.ws_next++;
-            b_task(&bd, RQB_T_XOR, r, 0, lv, tmp, ns);
-            *slot = r;
-          }
+        if (use[m] == 1 && (m & 15) && (m >> 4)) { /* made of the half-table entries m&15 and m&0xf0 */
+          if (!use[m & 15]) use[m & 15] = 2;
+          if (!use[m & 0xf0]) use[m & 0xf0] = 2;
         }
       for (int m = 1; m < 256; m++) {
-        uint32_t *slot = &tab8[(size_t)j * 256 + m];
-        *slot = NONE_REF;
-        if (!used8[(size_t)j * 256 + m]) continue;
-        uint32_t lo = (m & 15) ? tab4[((size_t)j * 2) * 16 + (m & 15)] : NONE_REF;
-        uint32_t hi = (m >> 4) ? tab4[((size_t)j * 2 + 1) * 16 + (m >> 4)] : NONE_REF;
-        if (fr_bits == 4) continue;
-        if (lo != NONE_REF && hi != NONE_REF) {
-          uint32_t pair[2] = {RQB_SRC(lo, 1), RQB_SRC(hi, 1)};
-          uint32_t r = bd.ws_base + bd.ws_next++;
-          b_task(&bd, RQB_T_XOR, r, 0, lv + 1, pair, 2);
-          *slot = r;
-        } else {
-          *slot = lo != NONE_REF ? lo : hi;
+        if (!use[m]) continue;
+        const uint32_t row = bd.tab_base + (uint32_t)j * 256u + (uint32_t)m;
+        if ((m & 15) && (m >> 4)) {
+          uint32_t pair[2] = {bd.tab_base + (uint32_t)j * 256u + (uint32_t)(m & 15),
+                              bd.tab_base + (uint32_t)j * 256u + (uint32_t)(m & 0xf0)};
+          b_task(&bd, RQB_T_XOR, row, 0, lv + 1, pair, 2);
+        } else { /* a half-table entry: up to 4 of the z themselves */
+          uint32_t ns = 0;
+          for (int bit = 0; bit < 8; bit++)
+            if (m >> bit & 1) {
+              int t = 8 * j + bit;
+              if (t < U) PUSH(ns, loc[Z + (uint32_t)t]);
+            }
+          b_task(&bd, RQB_T_XOR, row, 0, lv, tmp, ns);
         }
       }
     }
     end = lv + 2;
     for (int p = 0; p < I; p++) {
       const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
-      uint32_t ns = 0;
-      if (fr_bits == 4) {
-        for (int j = 0; j < ng; j++) {
-          if (g[j] & 15) PUSH(ns, tab4[((size_t)j * 2) * 16 + (g[j] & 15)]);
-          if (g[j] >> 4) PUSH(ns, tab4[((size_t)j * 2 + 1) * 16 + (g[j] >> 4)]);
-        }
-      } else
-      for (int j = 0; j < ng; j++)
-        if (g[j]) PUSH(ns, tab8[(size_t)j * 256 + g[j]]);
-      if (ns == 0) continue; /* x_p = Y_p */
-      PUSH(ns, loc[prow[p]]);
-      uint32_t e2 = b_tree(&bd, RQB_T_XOR, WSREF(prow[p]), tmp, ns, lv + 2);
+      int any = 0;
+      for (int j = 0; j < ng; j++) any |= g[j];
+      if (!any) continue; /* x_p = Y_p */
+      b_tab(&bd, WSREF(prow[p]), loc[prow[p]] != NONE_REF ? loc[prow[p]] : zero_row, lv + 2, g, (uint32_t)ng);
       loc[prow[p]] = WSREF(prow[p]);
-      if (e2 > end) end = e2;
     }
     FINE(11);
     lv = end + 1;

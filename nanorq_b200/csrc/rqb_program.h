@@ -53,8 +53,15 @@ enum rqb_task_kind {
   RQB_T_XOR = 0, /* row[dst] = XOR row[src_k]              nsrc <= RQB_MAX_SRCS (0 => zero row);
                     the list holds 4 (nsrc <= 4) or 8 entries, padded with the ZERO row            */
   RQB_T_GF = 1,  /* row[dst] = XOR beta_k * row[src_k]     nsrc <= RQB_MAX_SRCS                 */
-  RQB_T_SCAN = 2 /* alpha-scan over nsrc entries, see below                                    */
+  RQB_T_SCAN = 2, /* alpha-scan over nsrc entries, see below                                   */
+  RQB_T_TAB = 3   /* table gather, see below                                                   */
 };
+
+/* TAB (the back-substitution x = Y ^ G z through 8-bit XOR tables, rqb_planner.c phase F):
+ *     row[dst] = row[src0] ^ XOR_{j < nsrc, b_j != 0} row[tab_base + 256*j + b_j]
+ * src0 is the task's `pad` word, the "source list" holds the nsrc bytes b_j (one row of the
+ * bit matrix G, 8 inactive symbols per byte), tab_base and the ZERO row come from the level
+ * header.  A third of the program bytes of three gather tasks per row. */
 
 /* SCAN (restates the structure of precode_matrix_make_HDPC, lib/precode.c:60-83:
  * column j = alpha * column j+1 plus two ones, i.e. HDPC*C is a Horner scheme
@@ -69,7 +76,7 @@ typedef struct {
   uint16_t nsrc;
   uint8_t kind;
   uint8_t aux;
-  uint32_t pad;
+  uint32_t pad;     /* TAB: the row src0                                                    */
 } rqb_task; /* 16 bytes: one 128-bit shared-memory load */
 
 /* page := rqb_page_hdr, then levels back to back (each 16-byte aligned)
@@ -82,7 +89,8 @@ typedef struct {
 typedef struct {
   uint32_t n_tasks;
   uint32_t next_off; /* byte offset (from page start) of the next level */
-  uint32_t pad[2];
+  uint32_t tab_base; /* first row of the XOR tables (TAB tasks)         */
+  uint32_t zero_row; /* the all-zero row                                */
 } rqb_level_hdr;
 
 #define RQB_MAX_H 16u /* HDPC rows, RFC 6330 table 2: H <= 16 */

@@ -104,7 +104,7 @@ int rqb_interp_run_ex(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, 
       for (uint32_t k = 0; k < lh->n_tasks && !rc; k++) {
         const rqb_task *t = &tasks[k];
         const uint32_t *s32 = (const uint32_t *)(page + t->src_off);
-        if (t->src_off + (size_t)t->nsrc * 4 > RQB_PAGE_BYTES) { rc = 11; break; }
+        if (t->kind != RQB_T_TAB && t->src_off + (size_t)t->nsrc * 4 > RQB_PAGE_BYTES) { rc = 11; break; }
         if (t->src_off % 16) { rc = 12; break; }
         switch (t->kind) {
           case RQB_T_XOR:
@@ -126,6 +126,27 @@ int rqb_interp_run_ex(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, 
               if (STAMP(ref) == level_id && OWNER(ref) != k) rc = 10;
               for (size_t b = 0; b < T; b++) tmp[b] ^= gmul(src[b], beta);
             }
+            if (!rc) memcpy(row_ptr(&sp, t->dst, &rc), tmp, T);
+            break;
+          }
+          case RQB_T_TAB: { /* row[dst] = row[src0] ^ XOR_j table row (j, byte j), bytes where the list would be */
+            if (t->src_off + (((size_t)t->nsrc + 15) & ~(size_t)15) > RQB_PAGE_BYTES) { rc = 11; break; }
+            const uint8_t *bytes = (const uint8_t *)s32;
+            const uint8_t *src = row_ptr(&sp, t->pad, &rc);
+            if (!src) break;
+            if (STAMP(t->pad) == level_id && OWNER(t->pad) != k) rc = 10;
+            if (lh->zero_row != zero_row) rc = 11;
+            memcpy(tmp, src, T);
+            for (uint32_t q = 0; q < t->nsrc && !rc; q++) {
+              if (!bytes[q]) continue;
+              uint32_t ref = lh->tab_base + 256u * q + bytes[q];
+              const uint8_t *tr = row_ptr(&sp, ref, &rc);
+              if (!tr) break;
+              if (STAMP(ref) == level_id) rc = 10;
+              for (size_t b = 0; b < T; b++) tmp[b] ^= tr[b];
+            }
+            for (uint32_t q = t->nsrc; q < ((t->nsrc + 15u) & ~15u); q++)
+              if (bytes[q]) rc = 15; /* the kernel reads the list in 8-byte pieces: padding must be zero */
             if (!rc) memcpy(row_ptr(&sp, t->dst, &rc), tmp, T);
             break;
           }
