@@ -117,7 +117,7 @@ enum {
   SC_PCOL, SC_UCOL, SC_STK1, SC_STK2, SC_LEVEL, SC_G, SC_LOWROWS, SC_SB, SC_TB, SC_XPTR, SC_XIDX, SC_SH,
   SC_HB1, SC_HB2, SC_YBUF, SC_ACCBUF, SC_PIVROW, SC_PIVCOL, SC_FREECOLS, SC_Q, SC_TQ, SC_TMP, SC_CSLOT,
   SC_FPTR, SC_FITEMS, SC_PFIRST, SC_PLEVEL, SC_PPTR, SC_PITEMS, SC_CURLOC, SC_TASKS, SC_SRCS, SC_ORDER,
-  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_FRUSED, SC_FRTAB, SC_COUNT
+  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_FRUSED, SC_FRTAB, SC_CINFO, SC_COUNT
 };
 typedef struct {
   void *p[SC_COUNT];
@@ -381,7 +381,14 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
 
 /* ------------------------------------------------------------ bit helpers */
 static inline void bits_xor(uint64_t *a, const uint64_t *b, int w) {
-  for (int k = 0; k < w; k++) a[k] ^= b[k];
+  switch (w) { /* rows of the bit matrices are a few words long: no loop for the common sizes */
+    case 4: a[3] ^= b[3]; /* fall through */
+    case 3: a[2] ^= b[2]; /* fall through */
+    case 2: a[1] ^= b[1]; /* fall through */
+    case 1: a[0] ^= b[0]; return;
+    default:
+      for (int k = 0; k < w; k++) a[k] ^= b[k];
+  }
 }
 static inline int bit_get(const uint64_t *a, int k) { return (int)(a[k >> 6] >> (k & 63)) & 1; }
 static inline void bit_flip(uint64_t *a, int k) { a[k >> 6] ^= (uint64_t)1 << (k & 63); }
@@ -488,7 +495,7 @@ static const base_matrix *base_get(const rqb_params *P) {
 /* sort the n pairs (rd[k], it[k]) by rd ascending, stable.  Short lists by insertion;
  * long ones (LDPC rows carry ~90 terms) by an 8-bit LSD radix over the level. */
 static void sort_by_level(int *rd, int *it, int n, int maxkey, uint64_t *tmp /* 2n */) {
-  if (n <= 20) {
+  if (n <= 40) {
     for (int a = 1; a < n; a++) {
       int lv = rd[a], q = it[a], j = a;
       while (j > 0 && rd[j - 1] > lv) {
@@ -705,6 +712,10 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   int *pptr = sc_buf(sc, SC_PPTR, sizeof(int) * ((size_t)nnz / 2 + 9), 0);
   int *pitems = sc_buf(sc, SC_PITEMS, sizeof(int) * ((size_t)nnz * 2 + 64), 0);
   int nparts = 0, npitems = 0, maxlevel = 0;
+  /* one word per column instead of three arrays: >= 0 peeled at that position, < 0 inactive
+   * with index ~value */
+  int *cinfo = sc_buf(sc, SC_CINFO, sizeof(int) * (size_t)L, 0);
+  for (int c = 0; c < L; c++) cinfo[c] = col_state[c] == 1 ? col_pos[c] : ~col_t[c];
   {
     int nf = 0;
     int *it = sc_buf(sc, SC_TMP, sizeof(int) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
@@ -716,12 +727,11 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       uint64_t *g = G + (size_t)p * uw;
       pfirst[p] = nparts;
       for (int k = rptr[r]; k < rptr[r + 1]; k++) {
-        int c = cidx[k];
-        if (col_state[c] == 2) {
-          bit_flip(g, col_t[c]);
-        } else if (c != pcol[p]) {
-          int q = col_pos[c];
-          if (q >= p) return -3; /* cannot happen: would contradict the peeling invariant */
+        const int q = cinfo[cidx[k]];
+        if (q < 0) {
+          bit_flip(g, ~q);
+        } else if (q != p) {
+          if (q > p) return -3; /* cannot happen: would contradict the peeling invariant */
           bits_xor(g, G + (size_t)q * uw, uw);
           rd[cnt] = level[q];
           it[cnt++] = q;
@@ -791,11 +801,10 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       uint64_t *s = Sb + (size_t)m * uw;
       xptr[m] = nx;
       for (int k = rptr[r]; k < rptr[r + 1]; k++) {
-        int c = cidx[k];
-        if (col_state[c] == 2) {
-          bit_flip(s, col_t[c]);
+        const int q = cinfo[cidx[k]];
+        if (q < 0) {
+          bit_flip(s, ~q);
         } else {
-          int q = col_pos[c];
           xidx[nx++] = q;
           bits_xor(s, G + (size_t)q * uw, uw);
         }
