@@ -473,3 +473,15 @@ def test_api_file_and_mmap_ioctx_roundtrip(tmp_path, mmap):
     enc.close()
     got = np.fromfile(out_path, dtype=np.uint8)
     assert len(got) == F and np.array_equal(got, payload)
+
+
+@pytest.mark.parametrize("K,T,loss,oh", [(1, 64, 0.0, 0), (1, 8, 1.0, 2), (2, 16, 0.5, 2), (3, 24, 0.4, 1), (9, 40, 0.5, 2),
+                                         (12, 65528, 0.3, 1), (11, 65528, 0.0, 0)])
+def test_api_roundtrip_extreme_block_shapes(K, T, loss, oh):
+    """The smallest blocks (K = 1..9 are all padded to K' = 10) and the largest symbols
+    (T = 65528, 512 column slices per block) through the public API."""
+    F = K * T - (T // 2 if K > 1 else 0)  # ragged last symbol
+    ok, payload, out, packets, enc = api_roundtrip(F, T, K, 0, loss, oh, seed=K + T)
+    if not ok:
+        pytest.skip("singular pattern (tiny block, few extra symbols)")
+    assert np.array_equal(out, payload)
