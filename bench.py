@@ -274,7 +274,9 @@ def run_own(args, rank, world, local_rank):
     avg_launch_s = ms / 1e3 / launches
     achieved = alg_per_launch / avg_launch_s / 1e9
     compulsory = NB * (K * T + consts["L"] * T + 512 * T) + sum((K + 0) * T + len(c[0]) * T for c in checks)
-    roofline = {"bound": "hbm", "kernel": "rqb_solve_kernel (batched, grid = 10 column slices x blocks)", "achieved": achieved,
+    slice_bytes = nb.lib().rqb_batch_slice_bytes(NB, T)
+    roofline = {"bound": "hbm", "kernel": "rqb_solve_kernel (batched, grid = %d column slices of %d bytes x %d blocks)" % (
+                    -(-T // slice_bytes), slice_bytes, NB), "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
                 "compulsory_bytes_per_step": compulsory,
@@ -392,7 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--blocks", type=int, default=118,
-                    help="source blocks per GPU per step (59 blocks x 10 column slices fill the 148 x 4 resident CTA slots once)")
+                    help="source blocks per GPU per step (118 blocks x 5 column slices of 256 bytes fill the 148 x 4 resident CTA slots once)")
     ap.add_argument("--threads", type=int, default=0, help="host threads for the e2e arm (default: cores / ranks)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")

@@ -131,6 +131,9 @@ int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 /* run several solvers' pending programs as ONE kernel launch (gridDim.y = n);
  * all must share T and device.  Asynchronous on solvers[0]'s stream. */
 int rqb_solver_run_batch(rqb_solver **solvers, int n);
+/* bytes of every symbol one CTA owns (64, 128 or 256) in a launch over nblocks blocks of
+ * T-byte symbols: wide slices for big batches, narrow ones for a block on its own */
+int rqb_batch_slice_bytes(int nblocks, size_t T);
 /* same, on the stream of `owner` (so that several batches queue behind each other) */
 int rqb_solver_run_batch_on(rqb_solver **solvers, int n, rqb_solver *owner);
 /* CUDA-event timing of whatever is queued on this solver's stream between

@@ -137,6 +137,7 @@ def lib():
     sig("rqb_solver_last_kernel_ms", C.c_int, vp, C.POINTER(C.c_float))
     sig("rqb_solver_set_timing", None, vp, C.c_int)
     sig("rqb_solver_get_stats", C.c_int, vp, C.POINTER(SolverStats))
+    sig("rqb_batch_slice_bytes", C.c_int, C.c_int, sz)
     sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
     sig("rqb_solver_run_batch_on", C.c_int, C.POINTER(vp), C.c_int, vp)
     sig("rqb_plan_blob_build", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.POINTER(PlanBlob))
@@ -175,7 +176,7 @@ EXPORTED_SYMBOLS = [
     "rqb_solver_destroy", "rqb_release_cached", "rqb_solver_staging", "rqb_solver_pitch", "rqb_solver_upload",
     "rqb_solver_plan", "rqb_solver_plan_encode", "rqb_solver_run", "rqb_solver_emit",
     "rqb_solver_sync", "rqb_solver_fetch_syms", "rqb_solver_fetch_c", "rqb_solver_fetch_syms_async", "rqb_solver_sym_mirror",
-    "rqb_solver_last_kernel_ms", "rqb_solver_set_timing", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_plan_blob_build",
+    "rqb_solver_last_kernel_ms", "rqb_solver_set_timing", "rqb_solver_get_stats", "rqb_solver_run_batch", "rqb_batch_slice_bytes", "rqb_plan_blob_build",
     "rqb_plan_blob_free", "rqb_matrix_create", "rqb_matrix_destroy", "rqb_matrix_pitch",
     "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",

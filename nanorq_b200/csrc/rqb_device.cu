@@ -45,8 +45,11 @@ static constexpr int kSolveThreads = RQB_SOLVE_THREADS;
 #define RQB_SOLVE_MIN_CTAS 4 /* 64 registers per thread: 4 CTAs = 1024 threads per SM (measured +18 % over 3) */
 #endif
 static constexpr int kSolveMinCtas = RQB_SOLVE_MIN_CTAS;       // CTAs per SM the register budget allows
-static constexpr int kLanesPerTask = RQB_SLICE_BYTES / 16;     // 8 lanes x 16 bytes
-static constexpr int kTaskGroups = kSolveThreads / kLanesPerTask;
+// The column slice a CTA owns is a launch-time choice (template parameter kLanes = lanes of
+// 16 bytes per task): 8 lanes = 128-byte slices is the default; 16 lanes = 256-byte slices for
+// big batches (the thin levels of the triangular solve keep more of the CTA's lanes busy and
+// every barrier covers twice the bytes); 4 lanes = 64-byte slices when only a few blocks are
+// in flight (twice the CTAs for the fat levels).
 static constexpr int kRingStages = 4;
 static constexpr uint32_t kRingBytes = kRingStages * RQB_PAGE_BYTES;
 static constexpr uint32_t kSolveSmem = kRingBytes + 128;       // ring + mbarriers
@@ -216,12 +219,16 @@ __device__ __noinline__ void task_tab(const Rows R, const uint32_t *sp, uint32_t
   R.st(dst, acc);
 }
 
+template <int kLanes>
 __global__ void __launch_bounds__(kSolveThreads, kSolveMinCtas)
 rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
+  constexpr int kLanesPerTask = kLanes;
+  constexpr int kTaskGroups = kSolveThreads / kLanes;
+  constexpr uint32_t kSliceBytes = 16u * kLanes;
   extern __shared__ __align__(128) uint8_t smem[];
   const rqb_solve_args &a = args_list[blockIdx.y];
   const uint32_t width = a.width;
-  const uint32_t col0 = blockIdx.x * RQB_SLICE_BYTES;
+  const uint32_t col0 = blockIdx.x * kSliceBytes;
   if (col0 >= width) return; // whole CTA leaves: no barrier is skipped by a subset
   uint8_t *ring = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);
@@ -552,10 +559,48 @@ int rqb_event_elapsed_ms(void *start, void *stop, float *ms) {
   return 0;
 }
 
+// slice width for a launch: NANORQ_B200_SLICE = 64 | 128 | 256 forces one (experiments); otherwise
+// wide slices once 128-byte slices would fill the GPU about twice over, narrow ones when
+// 128-byte slices would leave most SMs without a CTA
+static int pick_slice_lanes(int nblocks, uint32_t max_width) {
+  static std::atomic<int> forced{-1};
+  int f = forced.load(std::memory_order_relaxed);
+  if (f < 0) {
+    const char *e = getenv("NANORQ_B200_SLICE");
+    f = e ? atoi(e) / 16 : 0;
+    if (f != 4 && f != 8 && f != 16) f = 0;
+    forced.store(f, std::memory_order_relaxed);
+  }
+  if (f) return f;
+  static std::atomic<int> sm_count{0}; /* one driver query per process (the GPUs of a box are alike) */
+  int sms = sm_count.load(std::memory_order_relaxed);
+  if (sms <= 0) {
+    sms = rqb_dev_sm_count();
+    if (sms <= 0) sms = 148;
+    sm_count.store(sms, std::memory_order_relaxed);
+  }
+  /* measured on B200, K=4096, T=1280 (Gbit/s encode+decode at 30 / 59 / 118 blocks per launch):
+   * 64-byte slices 787 / 1123 / 1153, 128-byte 966 / 1396 / 1452, 256-byte 723 / 1192 / 1636;
+   * one block alone: 0.43 / 0.57 / 0.89 ms */
+  const long ctas128 = (long)nblocks * ((max_width + 127) / 128);
+  if (ctas128 >= 7L * sms) return 16;
+  if (ctas128 * 2 <= sms) return 4;
+  return 8;
+}
+
+int rqb_solve_slice_bytes(int nblocks, uint32_t max_width) { return 16 * pick_slice_lanes(nblocks, max_width); }
+
 int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, void *stream) {
   if (nblocks <= 0 || max_width == 0) return 0;
-  dim3 grid((max_width + RQB_SLICE_BYTES - 1) / RQB_SLICE_BYTES, (unsigned)nblocks);
-  rqb_solve_kernel<<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
+  const int lanes = pick_slice_lanes(nblocks, max_width);
+  const uint32_t slice = 16u * (uint32_t)lanes;
+  dim3 grid((max_width + slice - 1) / slice, (unsigned)nblocks);
+  if (lanes == 16)
+    rqb_solve_kernel<16><<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
+  else if (lanes == 4)
+    rqb_solve_kernel<4><<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
+  else
+    rqb_solve_kernel<8><<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
   g_launches++;
   CK(cudaGetLastError());
   return 0;

@@ -66,6 +66,8 @@ int rqb_event_elapsed_ms(void *start, void *stop, float *ms);
 /* launches ONE kernel over nblocks source blocks (gridDim.y); args_dev is a
  * device array of rqb_solve_args; max_width is the maximum over the batch */
 int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, void *stream);
+/* column slice (bytes per CTA: 64, 128 or 256) rqb_launch_solve picks for such a launch */
+int rqb_solve_slice_bytes(int nblocks, uint32_t max_width);
 
 /* LT combine (decode_row, lib/nanorq.c:184-204): out[k] = XOR of the
  * intermediate symbols selected by Tuple[K', isi[k]]; tuples are generated on

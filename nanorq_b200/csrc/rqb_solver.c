@@ -682,6 +682,8 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   return 0;
 }
 
+int rqb_batch_slice_bytes(int nblocks, size_t T) { return rqb_solve_slice_bytes(nblocks, (uint32_t)round_up(T, 16)); }
+
 int rqb_solver_run_batch(rqb_solver **sv, int n) {
   if (n <= 0) return RQB_E_ARG;
   if (n == 1) return rqb_solver_run(sv[0]);
