@@ -124,7 +124,7 @@ typedef struct {
   double t_matrix, t_peel, t_dense, t_emit; /* host seconds per planning phase */
   uint32_t n_ws_rows; /* working rows the program uses in HBM */
   int n_parts;        /* partial sums scheduled off the critical path */
-  int slice_bytes;    /* column slice one CTA owns */
+  int slice_bytes;    /* default column slice one CTA owns (see rqb_batch_slice_bytes) */
 } rqb_solver_stats;
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 

@@ -3,9 +3,10 @@
  * All rows of a source block (received symbols, working rows, intermediate
  * symbols, emitted symbols) live in HBM, row-major, one pitch.  Row operations
  * are column-local (reference: deps/oblas/oblas_avx.c:62-73 works byte by byte),
- * so the block is cut into column slices of RQB_SLICE_BYTES and every CTA
- * replays the same program on its own slice with no inter-CTA traffic; its
- * working set (slice width x rows) is what stays hot in L1/L2.
+ * so the block is cut into column slices (64, 128 or 256 bytes, chosen per
+ * launch: the program does not depend on the width) and every CTA replays the
+ * same program on its own slice with no inter-CTA traffic; its working set
+ * (slice width x rows) is what stays hot in L1/L2.
  *
  * The program is a linear stream of fixed-size PAGES (staged into shared memory
  * by TMA bulk copies, see rqb_device.cu).  A page holds whole LEVELS; all tasks
@@ -33,7 +34,7 @@
 #include <stdint.h>
 
 #define RQB_PAGE_BYTES 8192u /* multiple of 16 (TMA bulk copy granularity) */
-#define RQB_SLICE_BYTES 128u /* column slice per CTA: one cache line per (task, source) */
+#define RQB_SLICE_BYTES 128u /* default column slice per CTA (rqb_device.cu picks 64 / 128 / 256 per launch) */
 #define RQB_MAX_SRCS 8u      /* sources per XOR/GF task (the kernel keeps them all in flight) */
 #define RQB_ROW_NONE 0xFFFFFFFFu
 
