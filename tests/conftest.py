@@ -10,14 +10,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def pytest_configure(config):
-    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """Build the product library and the test-side oracle if they are stale
+    """Register the marker and build the product library and the test-side oracle if they
+    are stale -- before collection, because test modules query the library at import time
     (both builds are incremental and take seconds; nvcc cross-compiles on CPU)."""
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
     from nanorq_b200 import build as b
     b.build()
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    yield
