@@ -9,7 +9,8 @@
  *   1. build A (LDPC + LT rows; HDPC rows are handled in closed form);
  *   2. peel: order i (row, column) pairs so the peeled part X is unit lower
  *      triangular, inactivating columns when only degree-2 rows are left
- *      (same idea as precode_matrix_precond, lib/precode.c:176-203);
+ *      (same idea as precode_matrix_precond, lib/precode.c:176-203), but rows with one
+ *      column left are taken breadth-first, which halves the dependency depth of X;
  *   3. bit-matrix work on the host only (never on symbol data):
  *        G      = X^-1 * U_top            (i x u bits)
  *        Schur  = U_low - X_low * G       (binary rows: bits; HDPC rows: GF(256),
