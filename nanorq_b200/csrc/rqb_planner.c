@@ -615,7 +615,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   int *ucol = sc_buf(sc, SC_UCOL, sizeof(int) * (size_t)L, 0);
   int *stk1 = sc_buf(sc, SC_STK1, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
   int *stk2 = sc_buf(sc, SC_STK2, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
-  int n1 = 0, n2 = 0, ni = 0, nu = 0, h1 = 0;
+  int n1 = 0, n2 = 0, ni = 0, nu = 0, h1 = 0, h2 = 0;
   for (int r = 0; r < R; r++) row_pos[r] = -1;
   for (int c = 0; c < L; c++) col_pos[c] = col_t[c] = -1;
   for (int c = W; c < L; c++) { /* the P permanently inactive columns */
@@ -645,8 +645,8 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       }
     }
     if (r < 0)
-      while (n2 > 0) {
-        int cand = stk2[--n2];
+      while (h2 < n2) {
+        int cand = stk2[h2++];
         if (row_pos[cand] < 0 && deg[cand] == 2) {
           r = cand;
           break;
