@@ -182,7 +182,7 @@ def build_blocks(nb_mod, nblocks, seed0):
         while True:
             esis = workload.received_esis(K, drop, OVERHEAD, extra)
             assert len(esis) - (K - int(drop.sum())) <= n_rep_emit
-            req, missing = nb_mod.SolveRequest.for_decoder(K, esis)
+            req, missing = nb_mod.SolveRequest.for_decoder(K, esis, want_c=False)  # as nanorq_repair_block does
             d = nb_mod.Solver(K, T, max_in=len(esis), max_out=len(missing))
             if d.plan(req) == 0:
                 break

@@ -265,7 +265,7 @@ class SolveRequest:
         return SolveRequest(k, np.where(k < K, k, NO_ROW), 0, want_c, out_isi)
 
     @staticmethod
-    def for_decoder(K, esis, K_params=None):
+    def for_decoder(K, esis, K_params=None, want_c=True):
         """Row placement of nanorq_decoder_add_symbol / nanorq_repair_block
         (reference lib/nanorq.c:478-509,527-565) for symbols that arrived in the
         order `esis` and were staged in that order (staging row = arrival index).
@@ -296,7 +296,8 @@ class SolveRequest:
         for x, (e, k) in enumerate(reps[len(missing):]):
             isi[p.Kprime + x] = e + pad
             in_row[p.Kprime + x] = k
-        return SolveRequest(isi, in_row, oh, True, missing), missing
+        # want_c=False is what nanorq_repair_block asks for: only the missing symbols come back
+        return SolveRequest(isi, in_row, oh, want_c, missing), missing
 
 
 def plan_blob(K_params, req):

@@ -1199,8 +1199,11 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       int any = 0;
       for (int j = 0; j < ng; j++) any |= g[j];
       if (!any) continue; /* x_p = Y_p */
-      b_tab(&bd, WSREF(prow[p]), loc[prow[p]] != NONE_REF ? loc[prow[p]] : zero_row, lv + 2, g, (uint32_t)ng);
-      loc[prow[p]] = WSREF(prow[p]);
+      /* an encoder keeps C: x_p is the intermediate symbol of column pcol[p], written straight to
+       * its row of the C space (no copy task later) */
+      const uint32_t xdst = req->want_c ? row0[RQB_SP_C] + (uint32_t)pcol[p] : WSREF(prow[p]);
+      b_tab(&bd, xdst, loc[prow[p]] != NONE_REF ? loc[prow[p]] : zero_row, lv + 2, g, (uint32_t)ng);
+      loc[prow[p]] = xdst;
     }
     FINE(11);
     lv = end + 1;
@@ -1237,6 +1240,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   if (req->want_c)
     for (int c = 0; c < L; c++) {
       uint32_t ns = 0;
+      if (cloc[c] == row0[RQB_SP_C] + (uint32_t)c) continue; /* already written in place */
       PUSH(ns, cloc[c]);
       b_task(&bd, RQB_T_XOR, row0[RQB_SP_C] + (uint32_t)c, 0, lv, tmp, ns);
     }

@@ -18,7 +18,7 @@ print("K=%d T=%d encode: first %.3f ms, median of rest %.3f ms, levels %d tasks 
     K, T, ms[0], float(np.median(ms[1:])), st["n_levels"], st["n_tasks"], 1e6 * float(np.median(ms[1:])) / st["n_levels"]))
 drop = workload.loss_pattern(K, 0.1, 3)
 esis = workload.received_esis(K, drop, 0)
-req, missing = nb.SolveRequest.for_decoder(K, esis)
+req, missing = nb.SolveRequest.for_decoder(K, esis, want_c=False)  # as nanorq_repair_block does
 d = nb.Solver(K, T, max_in=len(esis), max_out=len(missing))
 d.staging[:len(esis), :T] = 7
 d.upload(0, len(esis))
