@@ -1,6 +1,6 @@
 #!/bin/bash
 # under gpurun: compare the back-substitution variants (kernel arm + single-block latency)
-for m in triangular tables tables4; do
+for m in triangular tables; do
   export NANORQ_B200_BACKSUB=$m
   echo "== $m"
   python tools/kernel_latency.py 4096 1280 12
