@@ -430,6 +430,7 @@ typedef struct base_matrix {
   int *rptr; /* S + H + K' + 1 */
   int *cidx;
   int *deg;  /* S + H + K' */
+  uint8_t *hb1, *hb2; /* K'+S each: the HDPC rows that get a one in column j (lib/precode.c:68-81) */
   struct base_matrix *next;
 } base_matrix;
 static base_matrix *g_base[64];
@@ -486,6 +487,15 @@ static const base_matrix *base_get(const rqb_params *P) {
     }
     for (int r = 0; r < rows; r++)
       for (int k = rptr[r]; k < rptr[r + 1]; k++) m->deg[r] += (cidx[k] < W);
+    const int n = Kp + S;
+    m->hb1 = calloc((size_t)n + 1, 1);
+    m->hb2 = calloc((size_t)n + 1, 1);
+    for (int j = 0; j + 1 < n; j++) {
+      uint32_t b1 = rqb_rand(rqb_rand_v, (uint32_t)j + 1, 6, (uint32_t)H);
+      uint32_t b2 = (b1 + rqb_rand(rqb_rand_v, (uint32_t)j + 1, 7, (uint32_t)H - 1) + 1) % (uint32_t)H;
+      m->hb1[j] = (uint8_t)b1;
+      m->hb2[j] = (uint8_t)b2;
+    }
     m->next = *slot;
     *slot = m;
   }
@@ -825,15 +835,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    * (lib/precode.c:60-83)  =>  sum_j HDPC[h][j] v_j = alpha^h y_{n-1} ^ sum_{j<=n-2, h in b(j)} y_j
    * with y_j = alpha*y_{j-1} ^ v_j.  Here v_j is the u-vector of column j: row q of G if the
    * column is peeled at q (its symbol is Y_q ^ G_q z), the unit vector if inactive. */
-  uint8_t *hb1 = sc_buf(sc, SC_HB1, (size_t)n, 0);
-  uint8_t *hb2 = sc_buf(sc, SC_HB2, (size_t)n, 0);
-  for (int j = 0; j + 1 < n; j++) {
-    uint32_t b1 = rqb_rand(rqb_rand_v, (uint32_t)j + 1, 6, (uint32_t)H);
-    uint32_t b2 = (b1 + rqb_rand(rqb_rand_v, (uint32_t)j + 1, 7, (uint32_t)H - 1) + 1) % (uint32_t)H;
-    hb1[j] = (uint8_t)b1;
-    hb2[j] = (uint8_t)b2;
-  }
-  hb1[n - 1] = hb2[n - 1] = 0;
+  const uint8_t *hb1 = bm->hb1, *hb2 = bm->hb2; /* the two HDPC rows of every column: per K', cached */
   const int uq = uw * 8; /* u64 words per byte-row of padded width 64*uw */
   uint8_t *Sh = sc_buf(sc, SC_SH, (size_t)H * (size_t)uq * 8, 1);
   uint64_t *ybuf = sc_buf(sc, SC_YBUF, (size_t)uq * 8, 1);
