@@ -72,12 +72,22 @@ int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32
 /* K_params selects K' (the reference uses block 0's parameters for every block of
  * an object, lib/nanorq.c:289,372, so a shorter block may be padded further) */
 int rqb_solver_create_ex(rqb_solver **out, int K, int K_params, size_t T, uint32_t max_in, uint32_t max_out);
-/* destroy waits for the solver's queued work, then keeps the context (stream,
- * pinned and device buffers) for the next create of the same shape: CUDA object
- * creation is too slow for blocks that come and go at wire rate.
- * rqb_release_cached() really frees every kept context. */
+/* destroy never blocks: the context (stream, events, pinned and device buffers) is parked
+ * as it is -- work may still be queued on its stream -- for the next create of the same
+ * shape, because CUDA object creation is too slow for blocks that come and go at wire rate;
+ * whoever takes a parked context waits for its stream first.  Parked contexts and pooled
+ * buffers count against a byte limit (default 8 GiB, NANORQ_B200_CACHE_MB or
+ * rqb_set_cache_limit); beyond it the oldest parked contexts are handed back to the driver
+ * (cudaFree / cudaFreeHost).  The cache of encoder programs is limited to 48 entries (LRU).
+ * rqb_release_cached() hands EVERYTHING cached back: parked contexts, pooled buffers, cached
+ * encoder programs (host and device copies), recycled plan objects and per-K' matrices; it
+ * must not run concurrently with other calls into the library. */
 void rqb_solver_destroy(rqb_solver *s);
 void rqb_release_cached(void);
+void rqb_set_cache_limit(size_t bytes);
+void rqb_cache_stats(size_t *cached_bytes, size_t *limit_bytes);
+/* free / total memory of the library's default device (cudaMemGetInfo) */
+int rqb_device_mem_info(size_t *free_bytes, size_t *total_bytes);
 /* pinned host staging area for the input rows: max_in rows of rqb_solver_pitch bytes */
 uint8_t *rqb_solver_staging(rqb_solver *s);
 size_t rqb_solver_pitch(const rqb_solver *s);
@@ -129,7 +139,10 @@ typedef struct {
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 
 /* run several solvers' pending programs as ONE kernel launch (gridDim.y = n);
- * all must share T and device.  Asynchronous on solvers[0]'s stream. */
+ * all must share T and device.  Asynchronous on solvers[0]'s stream.  Ordering across the
+ * members' own streams is kept on the device with events: the launch waits for whatever a
+ * member had queued (uploads), and anything a member queues afterwards (fetch, emit, upload,
+ * a later run) waits for the launch -- callers need no extra synchronisation. */
 int rqb_solver_run_batch(rqb_solver **solvers, int n);
 /* bytes of every symbol one CTA owns (64, 128 or 256) in a launch over nblocks blocks of
  * T-byte symbols: wide slices for big batches, narrow ones for a block on its own */

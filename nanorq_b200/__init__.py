@@ -13,6 +13,10 @@ from .api import (  # noqa: F401
     Solver,
     SolveRequest,
     block_params,
+    cache_stats,
+    device_mem_info,
+    release_cached,
+    set_cache_limit,
     device_count,
     host_profile,
     kernel_launches,

@@ -122,6 +122,9 @@ def lib():
     sig("rqb_solver_create_ex", C.c_int, C.POINTER(vp), C.c_int, C.c_int, sz, C.c_uint32, C.c_uint32)
     sig("rqb_solver_destroy", None, vp)
     sig("rqb_release_cached", None)
+    sig("rqb_set_cache_limit", None, sz)
+    sig("rqb_cache_stats", None, C.POINTER(sz), C.POINTER(sz))
+    sig("rqb_device_mem_info", C.c_int, C.POINTER(sz), C.POINTER(sz))
     sig("rqb_solver_staging", vp, vp)
     sig("rqb_solver_pitch", sz, vp)
     sig("rqb_solver_upload", C.c_int, vp, C.c_uint32, C.c_uint32)
@@ -181,6 +184,7 @@ EXPORTED_SYMBOLS = [
     "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
     "rqb_schedule_replay_stepwise", "rqb_schedule_plan_blob",
+    "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info",
 ]
 
 
@@ -216,6 +220,28 @@ def host_profile(reset=False):
     if reset:
         lib().rqb_host_profile_reset()
     return {n: out[k] for k, n in enumerate(names)}
+
+
+def release_cached():
+    lib().rqb_release_cached()
+
+
+def set_cache_limit(nbytes):
+    lib().rqb_set_cache_limit(int(nbytes))
+
+
+def cache_stats():
+    """-> (bytes parked in recycled contexts and pooled buffers, limit)"""
+    a, b = C.c_size_t(), C.c_size_t()
+    lib().rqb_cache_stats(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def device_mem_info():
+    """-> (free, total) bytes of the library's default device"""
+    a, b = C.c_size_t(), C.c_size_t()
+    _check(lib().rqb_device_mem_info(C.byref(a), C.byref(b)), "rqb_device_mem_info")
+    return a.value, b.value
 
 
 def slow_path_counters():

@@ -122,6 +122,7 @@ nanorq *nanorq_encoder_new_ex(size_t len, uint16_t T16, uint16_t K, uint16_t Z16
   size_t Zf = div_ceil(Kt, Kn);
   if (Zf == 0 || Zf > Z_MAX || div_ceil(Kt, Zf) > K_MAX) return NULL;
   nanorq *rq = calloc(1, sizeof(*rq));
+  if (!rq) return NULL;
   rq->F = len;
   rq->T = T;
   rq->Al = al;
@@ -145,9 +146,15 @@ nanorq *nanorq_decoder_new(uint64_t common, uint32_t scheme) { /* :336-376 */
   if (F == 0 || F > NANORQ_MAX_TRANSFER) return NULL;
   size_t Z = ((scheme >> 24) & 0xff) + 1, N = ((scheme >> 8) & 0xffff) + 1, Al = scheme & 0xff;
   if (Al == 0 || T < Al || T % Al != 0) return NULL;
+  /* Sub-block interleaving: the reference's encoder never produces N > 1 (gen_scheme_specific,
+   * lib/nanorq.c:78 "disable interleaving"); its decoder would walk the sub-blocks of such an OTI
+   * (:97-173), this one lays symbols out contiguously, so a foreign or corrupted N is refused
+   * rather than decoded to the wrong offsets.  With N = 1 the value of Al only has to divide T. */
+  if (N != 1) return NULL;
   size_t Kt = div_ceil(F, T);
   if (div_ceil(Kt, Z) > K_MAX) return NULL;
   nanorq *rq = calloc(1, sizeof(*rq));
+  if (!rq) return NULL;
   rq->F = F;
   rq->T = T;
   rq->Al = Al;
@@ -203,6 +210,7 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   size_t K = nanorq_block_symbols(rq, sbn);
   if (K == 0) return NULL;
   struct block *b = calloc(1, sizeof(*b));
+  if (!b) return NULL;
   b->K = (uint16_t)K;
   uint32_t max_in, max_out;
   if (rq->max_esi) { /* decoder: source slots + every repair ESI that may arrive */
@@ -211,6 +219,10 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
     max_out = (uint32_t)K;
     b->mask_words = rq->max_esi / 32 + 2;
     b->mask = calloc(b->mask_words, sizeof(uint32_t));
+    if (!b->mask) {
+      free(b);
+      return NULL;
+    }
     b->gaps = K;
   } else {
     max_in = (uint32_t)K;
@@ -302,6 +314,7 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
     uint32_t n = b->win_cap, pad = (uint32_t)rq->P.Kprime - b->K;
     if ((uint64_t)esi + n > (1u << 24)) n = (1u << 24) - esi;
     uint32_t *isi = malloc(sizeof(uint32_t) * n);
+    if (!isi) return 0;
     for (uint32_t k = 0; k < n; k++) isi[k] = esi + k + pad; /* ISI = ESI + (K'-K) :429 */
     int rc = rqb_solver_emit(b->sv, isi, n);
     free(isi);
@@ -366,8 +379,11 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
     uint32_t row = (uint32_t)rq->P.Kprime + (uint32_t)b->nrep;
     if (row >= b->in_cap) return NANORQ_SYM_ERR;
     if (b->nrep == b->rep_cap) {
-      b->rep_cap = b->rep_cap ? b->rep_cap * 2 : 256;
-      b->rep_esi = realloc(b->rep_esi, b->rep_cap * sizeof(uint32_t));
+      size_t cap = b->rep_cap ? b->rep_cap * 2 : 256;
+      uint32_t *grown = realloc(b->rep_esi, cap * sizeof(uint32_t));
+      if (!grown) return NANORQ_SYM_ERR; /* the list collected so far stays valid */
+      b->rep_esi = grown;
+      b->rep_cap = cap;
     }
     rqb_copy_stream(st + (size_t)row * b->pitch, data, rq->T); /* arrival order, like repair_bin */
     PF(RQB_PF_ADD_COPY);
@@ -402,6 +418,12 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
   size_t nlt = (size_t)Kp + overhead;
   uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);
   uint32_t *missing = malloc(sizeof(uint32_t) * gaps);
+  if (!isi || !in_row || !missing) {
+    free(isi);
+    free(in_row);
+    free(missing);
+    return false;
+  }
   size_t rep = 0, nm = 0;
   /* fill_symbol_matrix_gaps + patch_precode_matrix (:527-565): missing source rows take
    * the repair symbols in arrival order, the rest become overhead rows */

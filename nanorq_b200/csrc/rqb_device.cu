@@ -551,6 +551,28 @@ int rqb_event_create(void **e) {
   *e = (void *)ev;
   return 0;
 }
+int rqb_event_create_sync(void **e) {
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  *e = (void *)ev;
+  return 0;
+}
+int rqb_stream_wait_event(void *stream, void *event) {
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+  return 0;
+}
+int rqb_dev_mem_info(size_t *free_bytes, size_t *total_bytes) {
+  CK(cudaMemGetInfo(free_bytes, total_bytes));
+  return 0;
+}
+int rqb_host_register(void *p, size_t bytes) {
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int rqb_host_unregister(void *p) {
+  CK(cudaHostUnregister(p));
+  return 0;
+}
 int rqb_event_destroy(void *e) { CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
 int rqb_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream)); return 0; }
 int rqb_event_sync(void *e) { CK(cudaEventSynchronize((cudaEvent_t)e)); return 0; }

@@ -58,6 +58,12 @@ int rqb_copy2d_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, siz
                    size_t rows, void *stream);
 int rqb_dev_memset(void *p, int v, size_t bytes, void *stream);
 int rqb_event_create(void **e);
+int rqb_event_create_sync(void **e); /* no timing: ordering between streams only */
+int rqb_stream_wait_event(void *stream, void *event);
+int rqb_dev_mem_info(size_t *free_bytes, size_t *total_bytes);
+/* page-lock caller memory so that copies to and from it are plain DMA */
+int rqb_host_register(void *p, size_t bytes);
+int rqb_host_unregister(void *p);
 int rqb_event_destroy(void *e);
 int rqb_event_record(void *e, void *stream);
 int rqb_event_sync(void *e);

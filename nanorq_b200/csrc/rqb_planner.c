@@ -123,6 +123,7 @@ enum {
 typedef struct {
   void *p[SC_COUNT];
   size_t cap[SC_COUNT];
+  int oom; /* an allocation failed since the flag was last cleared */
 } scratch_t;
 
 static pthread_key_t sc_key;
@@ -150,7 +151,11 @@ static void *sc_buf(scratch_t *sc, int id, size_t bytes, int zero) {
     free(sc->p[id]);
     size_t cap = bytes + bytes / 2;
     sc->p[id] = malloc(cap);
-    sc->cap[id] = cap;
+    sc->cap[id] = sc->p[id] ? cap : 0;
+    if (!sc->p[id]) {
+      sc->oom = 1;
+      return NULL;
+    }
   }
   if (zero) memset(sc->p[id], 0, bytes);
   return sc->p[id];
@@ -159,7 +164,12 @@ static void *sc_buf(scratch_t *sc, int id, size_t bytes, int zero) {
 static void *sc_grow(scratch_t *sc, int id, size_t bytes) {
   if (sc->cap[id] < bytes) {
     size_t cap = bytes * 2;
-    sc->p[id] = realloc(sc->p[id], cap);
+    void *np_ = realloc(sc->p[id], cap);
+    if (!np_) {
+      sc->oom = 1;
+      return sc->p[id];
+    }
+    sc->p[id] = np_;
     sc->cap[id] = cap;
   }
   return sc->p[id];
@@ -189,6 +199,7 @@ typedef struct {
 static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, const uint32_t *srcs, uint32_t n) {
   b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
   b->srcs = sc_grow(b->sc, SC_SRCS, (b->ns + n + 1) * sizeof(uint32_t));
+  if (b->sc->oom) return; /* rqb_plan_build reports it */
   ptask *t = &b->tasks[b->nt++];
   t->dst = dst;
   t->src_at = (uint32_t)b->ns;
@@ -218,6 +229,7 @@ static void b_tab(builder *b, uint32_t dst, uint32_t src0, uint32_t level, const
   const uint32_t words = (nbytes + 3) / 4;
   b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
   b->srcs = sc_grow(b->sc, SC_SRCS, (b->ns + words + 1) * sizeof(uint32_t));
+  if (b->sc->oom) return;
   ptask *t = &b->tasks[b->nt++];
   t->dst = dst;
   t->src_at = (uint32_t)b->ns;
@@ -305,13 +317,27 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   /* into the caller's buffer when the program certainly fits: the tasks, a header per level
    * (levels split over pages get one per piece) and up to 512 unused bytes at the end of a page */
   const size_t worst = ((tot_bytes + (size_t)nl * 32) / (RQB_PAGE_BYTES - 512) + 2) * RQB_PAGE_BYTES;
-  const int ext = ext_buf && worst <= ext_cap;
+  int ext = ext_buf && worst <= ext_cap;
   uint8_t *pages = ext ? ext_buf : plan->own_pages;
 #define OPEN_PAGE()                                                         \
   do {                                                                      \
+    if (ext && (npages + 1) * RQB_PAGE_BYTES > ext_cap) {                   \
+      /* the estimate was too small for this mix of task sizes: carry on in the plan's own buffer */ \
+      if (npages * RQB_PAGE_BYTES > plan->pages_cap) {                      \
+        uint8_t *np_ = realloc(plan->own_pages, (npages + 64) * 2 * RQB_PAGE_BYTES); \
+        if (!np_) return -7;                                                \
+        plan->own_pages = np_;                                              \
+        plan->pages_cap = (npages + 64) * 2 * RQB_PAGE_BYTES;               \
+      }                                                                     \
+      memcpy(plan->own_pages, pages, npages * RQB_PAGE_BYTES);              \
+      pages = plan->own_pages;                                              \
+      ext = 0;                                                              \
+    }                                                                       \
     if (!ext && (npages + 1) * RQB_PAGE_BYTES > plan->pages_cap) {          \
+      uint8_t *np_ = realloc(plan->own_pages, (npages + 64) * 2 * RQB_PAGE_BYTES); \
+      if (!np_) return -7;                                                  \
       plan->pages_cap = (npages + 64) * 2 * RQB_PAGE_BYTES;                 \
-      pages = plan->own_pages = realloc(plan->own_pages, plan->pages_cap);  \
+      pages = plan->own_pages = np_;                                        \
     }                                                                       \
     memset(pages + npages * RQB_PAGE_BYTES, 0, RQB_PAGE_BYTES);             \
     npages++;                                                               \
@@ -412,6 +438,22 @@ static rqb_plan *plan_acquire(void) {
   return p;
 }
 
+/* really free the recycled plan objects and the per-K' matrix cache (rqb_release_cached) */
+static void base_drain(void);
+void rqb_plan_pool_drain(void) {
+  pthread_mutex_lock(&g_plans_mu);
+  rqb_plan *p = g_free_plans;
+  g_free_plans = NULL;
+  pthread_mutex_unlock(&g_plans_mu);
+  while (p) {
+    rqb_plan *n = p->next_free;
+    free(p->own_pages);
+    free(p);
+    p = n;
+  }
+  base_drain();
+}
+
 void rqb_plan_free(rqb_plan *p) {
   if (!p) return;
   pthread_mutex_lock(&g_plans_mu); /* keeps its page buffer for the next block */
@@ -503,6 +545,25 @@ static const base_matrix *base_get(const rqb_params *P) {
   return m;
 }
 
+static void base_drain(void) {
+  pthread_mutex_lock(&g_base_mu);
+  for (int k = 0; k < 64; k++) {
+    base_matrix *m = g_base[k];
+    g_base[k] = NULL;
+    while (m) {
+      base_matrix *n = m->next;
+      free(m->rptr);
+      free(m->cidx);
+      free(m->deg);
+      free(m->hb1);
+      free(m->hb2);
+      free(m);
+      m = n;
+    }
+  }
+  pthread_mutex_unlock(&g_base_mu);
+}
+
 /* sort the n pairs (rd[k], it[k]) by rd ascending, stable.  Short lists by insertion;
  * long ones (LDPC rows carry ~90 terms) by an 8-bit LSD radix over the level. */
 static void sort_by_level(int *rd, int *it, int n, int maxkey, uint64_t *tmp /* 2n */) {
@@ -562,6 +623,9 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
 #endif
   scratch_t *sc = sc_get();
   int rc = 0;
+  if (!sc) return -7;
+  sc->oom = 0;
+#define OOM_CHECK() do { if (sc->oom) return -7; } while (0)
 
   /* ---- 1. sparse matrix A, rows: [0,S) LDPC, [S,S+H) HDPC (kept empty, closed form),
    *         [S+H, R) LT rows.  Same contents as precode_matrix_gen (+patching). */
@@ -571,6 +635,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   size_t cap = (size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)nlt + 16;
   int *cidx = sc_buf(sc, SC_CIDX, cap * sizeof(int), 0);
   int *deg = sc_buf(sc, SC_DEG, (size_t)R * sizeof(int), 0); /* non-zeros in the columns [0, W) */
+  OOM_CHECK();
   {
     /* LDPC rows and the LT rows of the source symbols (ISI k in row k) are the same for
      * every block of this K': copied from the per-K' cache; only the rows of repair
@@ -605,10 +670,12 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   /* column lists */
   int *cptr = sc_buf(sc, SC_CPTR, ((size_t)L + 1) * sizeof(int), 1);
   int *ridx = sc_buf(sc, SC_RIDX, sizeof(int) * (size_t)(nnz ? nnz : 1), 0);
+  int *cur_scratch = sc_buf(sc, SC_CUR, sizeof(int) * (size_t)(S > L ? S : L), 0);
+  OOM_CHECK();
   for (int k = 0; k < nnz; k++) cptr[cidx[k] + 1]++;
   for (int c = 0; c < L; c++) cptr[c + 1] += cptr[c];
   {
-    int *cur = sc_buf(sc, SC_CUR, sizeof(int) * (size_t)(S > L ? S : L), 0);
+    int *cur = cur_scratch;
     memcpy(cur, cptr, sizeof(int) * (size_t)L);
     for (int r = 0; r < R; r++)
       for (int k = rptr[r]; k < rptr[r + 1]; k++) ridx[cur[cidx[k]]++] = r;
@@ -626,6 +693,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   int *stk1 = sc_buf(sc, SC_STK1, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
   int *stk2 = sc_buf(sc, SC_STK2, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
   int n1 = 0, n2 = 0, ni = 0, nu = 0, h1 = 0, h2 = 0;
+  OOM_CHECK();
   for (int r = 0; r < R; r++) row_pos[r] = -1;
   for (int c = 0; c < L; c++) col_pos[c] = col_t[c] = -1;
   for (int c = W; c < L; c++) { /* the P permanently inactive columns */
@@ -730,12 +798,14 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   /* one word per column instead of three arrays: >= 0 peeled at that position, < 0 inactive
    * with index ~value */
   int *cinfo = sc_buf(sc, SC_CINFO, sizeof(int) * (size_t)L, 0);
+  OOM_CHECK();
   for (int c = 0; c < L; c++) cinfo[c] = col_state[c] == 1 ? col_pos[c] : ~col_t[c];
   {
     int nf = 0;
     int *it = sc_buf(sc, SC_TMP, sizeof(int) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
     int *rd = it + ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64);
     uint64_t *sortbuf = sc_buf(sc, SC_SORT, sizeof(uint64_t) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
+    OOM_CHECK();
     pptr[0] = 0;
     for (int p = 0; p < I; p++) {
       int r = prow[p], cnt = 0;
@@ -809,6 +879,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   uint64_t *Tb = sc_buf(sc, SC_TB, (size_t)(nb ? nb : 1) * (nbw ? nbw : 1) * sizeof(uint64_t), 1);
   int *xptr = sc_buf(sc, SC_XPTR, sizeof(int) * ((size_t)nb + 1), 0);
   int *xidx = sc_buf(sc, SC_XIDX, sizeof(int) * (size_t)(nnz ? nnz : 1), 0);
+  OOM_CHECK();
   {
     int nx = 0;
     for (int m = 0; m < nb; m++) {
@@ -840,6 +911,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   uint8_t *Sh = sc_buf(sc, SC_SH, (size_t)H * (size_t)uq * 8, 1);
   uint64_t *ybuf = sc_buf(sc, SC_YBUF, (size_t)uq * 8, 1);
   uint64_t *accbuf = sc_buf(sc, SC_ACCBUF, (size_t)H * (size_t)uq * 8, 1);
+  OOM_CHECK();
   {
     for (int j = 0; j < n; j++) {
       for (int k = 0; k < uq; k++) ybuf[k] = xtime8(ybuf[k]);
@@ -872,6 +944,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   int *pivcol_of_row = sc_buf(sc, SC_PIVCOL, sizeof(int) * (size_t)(nb ? nb : 1), 0);
   int *freecols = sc_buf(sc, SC_FREECOLS, sizeof(int) * (size_t)(U ? U : 1), 0);
   int rho = 0, nfree = 0;
+  OOM_CHECK();
   for (int m = 0; m < nb; m++) pivcol_of_row[m] = -1;
   for (int t = 0; t < U; t++) {
     int pr = -1;
@@ -900,6 +973,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
    *          H x nfree system Q over GF(256) with a tracked transformation TQ (H x H) */
   uint8_t *Q = sc_buf(sc, SC_Q, (size_t)H * (size_t)(nfree ? nfree : 1), 1);
   uint8_t *TQ = sc_buf(sc, SC_TQ, (size_t)H * (size_t)H, 1);
+  OOM_CHECK();
   for (int h = 0; h < H; h++) {
     const uint8_t *row = Sh + (size_t)h * (size_t)uq * 8;
     for (int f = 0; f < nfree; f++) Q[h * nfree + f] = row[freecols[f]];
@@ -967,6 +1041,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   bd.ws_base = row0[RQB_SP_WS];
   bd.ws_next = WS_FIXED;
   uint32_t *loc = sc_buf(sc, SC_CURLOC, sizeof(uint32_t) * (size_t)WS_FIXED, 0);
+  OOM_CHECK();
   for (uint32_t s = 0; s < WS_FIXED; s++) loc[s] = NONE_REF;
   for (int k = 0; k < nlt; k++)
     if (req->in_row[k] != RQB_ROW_NONE) {
@@ -974,6 +1049,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       loc[S + H + k] = row0[RQB_SP_IN] + req->in_row[k];
     }
   uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)4 * (size_t)n + (size_t)NC + 4096), 0);
+  OOM_CHECK();
 #define WSREF(s) (row0[RQB_SP_WS] + (uint32_t)(s))
 #define PUSH(ns, ref)                                  \
   do {                                                 \
@@ -1018,6 +1094,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     if (e2 > end) end = e2;
   }
   int *cs = sc_buf(sc, SC_CS, sizeof(int) * ((size_t)NC + 1), 0);
+  OOM_CHECK();
   for (int c = 0; c <= NC; c++) cs[c] = (int)((long)n * c / NC);
   for (int c = 0; c < NC; c++) {
     uint32_t ns = 0;
@@ -1083,6 +1160,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     /* suffix[h] = sum_{c > c1} coef[c][h] * alpha^(s_c - e_c1), built backwards in O(NC*H) */
     uint8_t suf[RQB_MAX_H];
     uint8_t *gc = sc_buf(sc, SC_CSLOT, (size_t)NC * (size_t)H + 64, 0);
+    OOM_CHECK();
     memset(suf, 0, sizeof(suf));
     for (int c1 = NC - 1; c1 >= 0; c1--) {
       /* moving the reference point from e_{c1+1} (= s_{c1+2}) back to e_{c1} (= s_{c1+1}) multiplies by
@@ -1163,6 +1241,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
      * nothing but the bytes of its row of G; only the entries some row uses (and the two
      * half-table entries they are made of) are computed */
     uint8_t *used8 = sc_buf(sc, SC_FRUSED, (size_t)ng * 256 + 64, 1);
+    OOM_CHECK();
     const uint32_t tab0 = bd.ws_next;
     bd.tab_base = bd.ws_base + tab0;
     bd.ws_next += (uint32_t)ng * 256u;
@@ -1238,6 +1317,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   FINE(12);
   /* O: outputs.  C[col] sits in the row that pivoted on col, or in z. */
   uint32_t *cloc = sc_buf(sc, SC_CSLOT, sizeof(uint32_t) * (size_t)L, 0);
+  OOM_CHECK();
   for (int c = 0; c < L; c++) cloc[c] = col_state[c] == 1 ? loc[prow[col_pos[c]]] : loc[Z + (uint32_t)col_t[c]];
   if (req->want_c)
     for (int c = 0; c < L; c++) {
@@ -1256,10 +1336,13 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
 #undef PUSH
 #undef WSREF
 #undef TRIANGULAR
+#undef OOM_CHECK_UNUSED
   if ((uint64_t)row0[RQB_SP_WS] + bd.ws_next > RQB_MAX_ROWS) return -4;
 
   FINE(13);
+  OOM_CHECK();
   rqb_plan *plan = plan_acquire();
+  if (!plan) return -7;
   size_t tot_levels = 0;
   rc = write_pages(&bd, plan, zero_row, &tot_levels, req->pages_buf, req->pages_buf_cap);
   if (rc) {

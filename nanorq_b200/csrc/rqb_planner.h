@@ -66,6 +66,7 @@ typedef struct rqb_plan {
  * precode_matrix_invert returns NULL, lib/precode.c:368-370), <0 = bad request */
 int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out);
 void rqb_plan_free(rqb_plan *p);
+void rqb_plan_pool_drain(void); /* really free recycled plans and cached per-K' matrices */
 
 /* one device program from an ordered sequence of reference-format row operations
  * (rqb_rowop[nops]) followed by a row gather; see rqb_planner.c */

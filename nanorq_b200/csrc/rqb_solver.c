@@ -108,6 +108,37 @@ typedef struct pool_ent {
 } pool_ent;
 static pool_ent *g_pool;
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+/* bytes parked in the pool and in recycled solver contexts, and their limit
+ * (rqb_set_cache_limit / NANORQ_B200_CACHE_MB; default 8 GiB).  What would go over the
+ * limit is handed back to the driver instead of being kept. */
+static _Atomic size_t g_pool_bytes, g_shell_bytes;
+static _Atomic size_t g_cache_limit = (size_t)8 << 30;
+static pthread_once_t g_cache_once = PTHREAD_ONCE_INIT;
+static void cache_limit_init(void) {
+  const char *e = getenv("NANORQ_B200_CACHE_MB");
+  if (e && *e) g_cache_limit = (size_t)strtoull(e, NULL, 10) << 20;
+}
+static size_t cache_limit(void) {
+  pthread_once(&g_cache_once, cache_limit_init);
+  return g_cache_limit;
+}
+void rqb_set_cache_limit(size_t bytes) {
+  pthread_once(&g_cache_once, cache_limit_init);
+  g_cache_limit = bytes;
+}
+void rqb_cache_stats(size_t *cached_bytes, size_t *limit_bytes) {
+  if (cached_bytes) *cached_bytes = g_pool_bytes + g_shell_bytes;
+  if (limit_bytes) *limit_bytes = cache_limit();
+}
+int rqb_device_mem_info(size_t *free_bytes, size_t *total_bytes) {
+  size_t f = 0, t = 0;
+  if (rqb_dev_count() <= 0) return RQB_E_NODEVICE;
+  if (rqb_dev_get() != rqb_dev_default() && rqb_dev_set(rqb_dev_default())) return RQB_E_NODEVICE;
+  if (rqb_dev_mem_info(&f, &t)) return RQB_E_NODEVICE;
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
 
 static size_t pool_class(size_t bytes) {
   size_t c = 4096;
@@ -136,6 +167,7 @@ static int pool_get(void **out, size_t bytes, int pinned) {
     if (e->pinned == pinned && e->dev == dev && e->bytes == cls) {
       *pp = e->next;
       pthread_mutex_unlock(&g_pool_mu);
+      g_pool_bytes -= e->bytes;
       *out = e->p;
       free(e);
       return 0;
@@ -146,17 +178,46 @@ static int pool_get(void **out, size_t bytes, int pinned) {
   return pinned ? rqb_host_malloc(out, cls) : rqb_dev_malloc(out, cls);
 }
 
+/* the calling thread must be bound to the buffer's device */
+static void buf_free(void *p, int pinned) {
+  if (!p) return;
+  if (pinned) rqb_host_free(p); else rqb_dev_free(p);
+}
+
 static void pool_put(void *p, size_t bytes, int pinned) {
   if (!p) return;
-  pool_ent *e = malloc(sizeof(*e));
+  const size_t cls = pool_class(bytes);
+  pool_ent *e = g_pool_bytes + g_shell_bytes + cls > cache_limit() ? NULL : malloc(sizeof(*e));
+  if (!e) { /* over the limit (or out of memory): really free */
+    buf_free(p, pinned);
+    return;
+  }
   e->p = p;
-  e->bytes = pool_class(bytes);
+  e->bytes = cls;
   e->pinned = pinned;
   e->dev = pinned ? -1 : rqb_dev_get();
+  g_pool_bytes += cls;
   pthread_mutex_lock(&g_pool_mu);
   e->next = g_pool;
   g_pool = e;
   pthread_mutex_unlock(&g_pool_mu);
+}
+
+static void pool_drain(void) { /* hand every pooled buffer back to the driver */
+  pthread_mutex_lock(&g_pool_mu);
+  pool_ent *e = g_pool;
+  g_pool = NULL;
+  pthread_mutex_unlock(&g_pool_mu);
+  const int cur = rqb_dev_get();
+  while (e) {
+    pool_ent *n = e->next;
+    if (!e->pinned && e->dev >= 0 && rqb_dev_get() != e->dev) rqb_dev_set(e->dev);
+    buf_free(e->p, e->pinned);
+    g_pool_bytes -= e->bytes;
+    free(e);
+    e = n;
+  }
+  if (cur >= 0 && rqb_dev_get() != cur) rqb_dev_set(cur);
 }
 
 /* --------------------------------------------------- encoder plan cache
@@ -168,10 +229,44 @@ typedef struct enc_plan {
   uint32_t n_out, in_rows, sym_rows; /* the arena layout is part of the program */
   rqb_plan *plan;
   uint8_t *d_pages;
+  int refs;               /* solver contexts whose current program this is (parked ones included) */
+  unsigned long long use; /* LRU stamp */
   struct enc_plan *next;
 } enc_plan;
 static enc_plan *g_enc_plans;
 static pthread_mutex_t g_plan_mu = PTHREAD_MUTEX_INITIALIZER;
+static unsigned long long g_enc_clock;
+#define RQB_ENC_PLANS_MAX 48 /* cached encoder programs (one per K, device and window size in use) */
+
+static void enc_plan_free(enc_plan *e) { /* caller holds g_plan_mu; e is unlinked and unreferenced */
+  const int cur = rqb_dev_get();
+  if (cur != e->dev) rqb_dev_set(e->dev);
+  if (e->d_pages) rqb_dev_free(e->d_pages);
+  if (cur >= 0 && cur != e->dev) rqb_dev_set(cur);
+  rqb_plan_free(e->plan);
+  free(e);
+}
+static void enc_plan_unref(enc_plan *e) {
+  if (!e) return;
+  pthread_mutex_lock(&g_plan_mu);
+  e->refs--;
+  pthread_mutex_unlock(&g_plan_mu);
+}
+/* caller holds g_plan_mu: drop least recently used entries nobody runs until the cache is within `keep` */
+static void enc_plans_trim(int keep) {
+  for (;;) {
+    int n = 0;
+    enc_plan **victim = NULL;
+    for (enc_plan **pp = &g_enc_plans; *pp; pp = &(*pp)->next) {
+      n++;
+      if ((*pp)->refs == 0 && (!victim || (*pp)->use < (*victim)->use)) victim = pp;
+    }
+    if (n <= keep || !victim) return;
+    enc_plan *e = *victim;
+    *victim = e->next;
+    enc_plan_free(e);
+  }
+}
 
 /* ------------------------------------------------------------- solver */
 struct rqb_solver {
@@ -183,9 +278,13 @@ struct rqb_solver {
   int busy;   /* work has been queued on the stream since the last wait */
   int broken; /* a device call failed: do not recycle                    */
   int pages_pending;             /* the pinned page staging is still being copied */
-  struct rqb_solver *batch_owner; /* last batched launch ran on this solver's stream */
   struct rqb_solver *next_shell;
   void *stream, *ev0, *ev1, *ev2, *ev3;
+  /* ordering between streams for batched launches (no timing): ev_ready is recorded on this
+   * solver's stream when its uploads must precede a launch on another stream, ev_done on the
+   * launching stream after a batched kernel that works on other solvers' rows */
+  void *ev_ready, *ev_done;
+  struct enc_plan *enc; /* the cached encoder program attached to this context (reference counted) */
   uint8_t *h_in, *h_sym; /* pinned: staging rows of the input space, mirror of the emitted symbols */
   uint32_t *h_flag;      /* pinned word the stream sets when it has drained (rqb_stream_wait_flag) */
   uint32_t flag_seq;
@@ -245,48 +344,86 @@ static int solver_layout(rqb_solver *s) {
 #define ROW_PTR(s, space, k) ((s)->d_arena + ((size_t)(s)->row0[space] + (k)) * (s)->pitch)
 static pthread_mutex_t g_shell_mu = PTHREAD_MUTEX_INITIALIZER;
 
-static void solver_release(rqb_solver *s) { /* really free everything */
+static size_t solver_bytes(const rqb_solver *s) { /* pinned + device memory a context holds */
+  return (size_t)s->in_cap * s->pitch + s->arena_cap + (size_t)s->out_cap * s->pitch + s->d_pages_cap +
+         s->h_pages_cap + (size_t)s->out_cap * 4 + RQB_ARGS_BYTES;
+}
+
+static void solver_detach_plan(rqb_solver *s) {
+  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  s->plan = NULL;
+  s->plan_shared = 0;
+  if (s->enc) enc_plan_unref(s->enc);
+  s->enc = NULL;
+  s->cur_pages = NULL;
+}
+
+/* give everything back to the driver (after the stream has drained) */
+static void solver_release(rqb_solver *s) {
   int cur = rqb_dev_get();
   if (cur != s->dev) rqb_dev_set(s->dev);
   if (s->stream) rqb_stream_sync(s->stream);
-  pool_put(s->h_in, (size_t)s->in_cap * s->pitch, 1);
-  pool_put(s->d_arena, s->arena_cap, 0);
-  pool_put(s->h_sym, (size_t)s->out_cap * s->pitch, 1);
-  pool_put(s->h_flag, 64, 1);
-  pool_put(s->d_isi, (size_t)s->out_cap * 4, 0);
+  solver_detach_plan(s);
+  buf_free(s->h_in, 1);
+  buf_free(s->d_arena, 0);
+  buf_free(s->h_sym, 1);
+  buf_free(s->h_flag, 1);
+  buf_free(s->d_isi, 0);
   free(s->h_isi);
-  pool_put(s->d_pages, s->d_pages_cap, 0);
-  pool_put(s->h_pages, s->h_pages_cap, 1);
+  buf_free(s->d_pages, 0);
+  buf_free(s->h_pages, 1);
   free(s->h_args);
-  pool_put(s->d_args, RQB_ARGS_BYTES, 0);
+  buf_free(s->d_args, 0);
   if (s->ev0) rqb_event_destroy(s->ev0);
   if (s->ev1) rqb_event_destroy(s->ev1);
   if (s->ev2) rqb_event_destroy(s->ev2);
   if (s->ev3) rqb_event_destroy(s->ev3);
+  if (s->ev_ready) rqb_event_destroy(s->ev_ready);
+  if (s->ev_done) rqb_event_destroy(s->ev_done);
   if (s->stream) rqb_stream_destroy(s->stream);
   if (cur != s->dev && cur >= 0) rqb_dev_set(cur);
   free(s);
 }
 
+/* Parks the context for the next create of the same shape (it does not wait: work may still be
+ * queued on the stream -- an encoder whose repair symbols were never asked for -- every buffer
+ * that work touches belongs to the context, and whoever takes it out of the list waits first).
+ * Parked contexts count against the cache limit; the oldest ones beyond it are really freed. */
 void rqb_solver_destroy(rqb_solver *s) {
   if (!s) return;
-  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
-  s->plan = NULL;
-  /* Work may still be queued on the stream (an encoder whose repair symbols were never
-   * asked for): the context is parked as it is -- every buffer that work touches belongs
-   * to the context -- and whoever takes it out of the free list waits first. */
+  if (s->plan && !s->plan_shared) { /* an encoder program stays attached (and referenced) while queued work may read it */
+    rqb_plan_free(s->plan);
+    s->plan = NULL;
+  }
   if (s->broken) {
     solver_release(s);
     return;
   }
   s->next_shell = NULL;
+  rqb_solver *evict = NULL, **evict_tail = &evict;
   pthread_mutex_lock(&g_shell_mu); /* appended at the tail: the list is oldest-first */
   *g_shells_tail = s;
   g_shells_tail = &s->next_shell;
+  g_shell_bytes += solver_bytes(s);
+  while (g_shells && g_shells != s && g_pool_bytes + g_shell_bytes > cache_limit()) {
+    rqb_solver *old = g_shells;
+    g_shells = old->next_shell;
+    if (!g_shells) g_shells_tail = &g_shells;
+    g_shell_bytes -= solver_bytes(old);
+    old->next_shell = NULL;
+    *evict_tail = old;
+    evict_tail = &old->next_shell;
+  }
   pthread_mutex_unlock(&g_shell_mu);
+  while (evict) {
+    rqb_solver *n = evict->next_shell;
+    solver_release(evict);
+    evict = n;
+  }
 }
 
-/* free every cached solver context and pooled buffer (tests, long-lived hosts) */
+/* really free every cached solver context, pooled buffer, cached encoder program and recycled plan
+ * object (tests, long-lived hosts).  Must not run concurrently with other calls into the library. */
 void rqb_release_cached(void) {
   pthread_mutex_lock(&g_shell_mu);
   rqb_solver *s = g_shells;
@@ -295,9 +432,15 @@ void rqb_release_cached(void) {
   pthread_mutex_unlock(&g_shell_mu);
   while (s) {
     rqb_solver *n = s->next_shell;
+    g_shell_bytes -= solver_bytes(s);
     solver_release(s);
     s = n;
   }
+  pool_drain();
+  pthread_mutex_lock(&g_plan_mu);
+  enc_plans_trim(0);
+  pthread_mutex_unlock(&g_plan_mu);
+  rqb_plan_pool_drain();
 }
 
 int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32_t max_out) {
@@ -330,12 +473,12 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
       if ((size_t)c->in_cap > (size_t)max_in + max_in / 4 + 64 || (size_t)c->out_cap > (size_t)max_out + max_out / 4 + 64) continue;
       /* an idle context before one with work still queued (oldest first: most likely done);
        * among idle ones the tightest fit */
-      const int c_busy = c->busy || c->batch_owner != NULL;
+      const int c_busy = c->busy;
       if (!best) {
         best = pp;
       } else {
         const rqb_solver *b = *best;
-        const int b_busy = b->busy || b->batch_owner != NULL;
+        const int b_busy = b->busy;
         if (b_busy && !c_busy) best = pp;
         else if (b_busy == c_busy && !c_busy && c->in_cap + c->out_cap < b->in_cap + b->out_cap) best = pp;
       }
@@ -344,6 +487,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
       s = *best;
       *best = s->next_shell;
       if (g_shells_tail == &s->next_shell) g_shells_tail = best;
+      g_shell_bytes -= solver_bytes(s);
     }
   }
   pthread_mutex_unlock(&g_shell_mu);
@@ -353,18 +497,20 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     s->P = P;
     s->max_in = max_in;
     s->max_out = max_out;
-    s->plan = NULL;
-    s->plan_shared = s->has_c = s->timed = s->want_timing = 0;
-    s->cur_pages = NULL;
+    s->has_c = s->timed = s->want_timing = 0;
     s->n_out_last = 0;
     s->next_shell = NULL;
-    if (bind_dev(s->dev)) return dev_fail(0, "rqb_solver_create bind");
-    if ((s->busy || s->batch_owner) && solver_wait(s)) { /* the previous owner left work queued */
+    if (bind_dev(s->dev)) { /* the context is already out of the list: do not leak it */
+      s->broken = 1;
+      rqb_solver_destroy(s);
+      return dev_fail(0, "rqb_solver_create bind");
+    }
+    if (s->busy && solver_wait(s)) { /* the previous owner left work queued */
       s->broken = 1;
       rqb_solver_destroy(s);
       return RQB_E_NODEVICE;
     }
-    s->batch_owner = NULL;
+    solver_detach_plan(s); /* nothing queued can read the previous owner's program any more */
     if (solver_layout(s)) {
       s->broken = 1;
       rqb_solver_destroy(s);
@@ -375,6 +521,10 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   }
   g_cnt_ctx_new++;
   s = calloc(1, sizeof(*s));
+  if (!s) {
+    snprintf(g_err, sizeof(g_err), "rqb_solver_create: out of memory");
+    return RQB_E_ARG;
+  }
   s->K = K;
   s->Kparams = Kparams;
   s->T = T;
@@ -390,6 +540,8 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
   e = e ? e : rqb_event_create(&s->ev3);
   e = e ? e : rqb_event_create(&s->ev0);
   e = e ? e : rqb_event_create(&s->ev1);
+  e = e ? e : rqb_event_create_sync(&s->ev_ready);
+  e = e ? e : rqb_event_create_sync(&s->ev_done);
   e = e ? e : pool_get((void **)&s->h_in, (size_t)s->in_cap * s->pitch, 1);
   e = e ? e : pool_get((void **)&s->d_arena, s->arena_cap, 0);
   e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->out_cap * s->pitch, 1);
@@ -401,6 +553,12 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
    * for the next launch while earlier copies are still queued on the stream */
   s->h_isi = malloc((size_t)s->out_cap * 4);
   s->h_args = calloc(1, RQB_ARGS_BYTES);
+  if (!s->h_isi || !s->h_args) {
+    snprintf(g_err, sizeof(g_err), "rqb_solver_create: out of memory");
+    s->broken = 1;
+    rqb_solver_destroy(s);
+    return RQB_E_ARG;
+  }
   e = e ? e : pool_get((void **)&s->d_args, RQB_ARGS_BYTES, 0);
   e = e ? e : solver_layout(s);
   if (e) {
@@ -418,11 +576,8 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
 }
 
 static int solver_wait(rqb_solver *s) {
-  if (s->batch_owner && s->batch_owner != s) {
-    /* a batched launch on another solver's stream works on this solver's rows */
-    DEV(rqb_stream_sync(s->batch_owner->stream));
-  }
-  s->batch_owner = NULL;
+  /* a batched launch on another solver's stream that works on this solver's rows is ordered
+   * before anything queued here afterwards by ev_done (rqb_solver_run_batch_on) */
   DEV(rqb_stream_wait_flag(s->stream, s->h_flag, &s->flag_seq));
   s->busy = 0;
   s->pages_pending = 0;
@@ -554,7 +709,14 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
     snprintf(g_err, sizeof(g_err), "rqb_plan_build failed (%d)", rc);
     return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
   }
-  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  if (s->enc) { /* queued work may still read the cached encoder program */
+    int w = solver_wait(s);
+    if (w) {
+      rqb_plan_free(p);
+      return w;
+    }
+  }
+  solver_detach_plan(s);
   s->plan = p;
   s->plan_shared = 0;
   size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
@@ -588,14 +750,17 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
     const int Kp = s->P.Kprime;
     uint32_t *isi = malloc(sizeof(uint32_t) * (size_t)Kp), *in_row = malloc(sizeof(uint32_t) * (size_t)Kp);
     uint32_t *oi = malloc(sizeof(uint32_t) * (size_t)(n_rep ? n_rep : 1));
-    for (int k = 0; k < Kp; k++) {
-      isi[k] = (uint32_t)k;
-      in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
-    }
-    for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
-    rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0};
     rqb_plan *p = NULL;
-    int rc = rqb_plan_build(&pr, &p);
+    int rc = -7;
+    if (isi && in_row && oi) {
+      for (int k = 0; k < Kp; k++) {
+        isi[k] = (uint32_t)k;
+        in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
+      }
+      for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
+      rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0};
+      rc = rqb_plan_build(&pr, &p);
+    }
     free(isi);
     free(in_row);
     free(oi);
@@ -605,27 +770,44 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
       return rc == 1 ? RQB_NEED_MORE : (rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG);
     }
     e = calloc(1, sizeof(*e));
-    e->K = s->K;
-    e->Kparams = s->Kparams;
-    e->want_c = want_c;
-    e->n_out = n_rep;
-    e->in_rows = s->max_in;
-    e->sym_rows = s->max_out;
-    e->dev = s->dev;
-    e->plan = p;
     size_t pb = (size_t)p->n_pages * RQB_PAGE_BYTES;
-    int de = rqb_dev_malloc((void **)&e->d_pages, pb);
-    de = de ? de : rqb_copy_h2d(e->d_pages, p->pages, pb, s->stream);
-    de = de ? de : rqb_stream_sync(s->stream);
-    if (de) {
+    int de = e ? 0 : -1;
+    if (e) {
+      e->K = s->K;
+      e->Kparams = s->Kparams;
+      e->want_c = want_c;
+      e->n_out = n_rep;
+      e->in_rows = s->max_in;
+      e->sym_rows = s->max_out;
+      e->dev = s->dev;
+      e->plan = p;
+      de = rqb_dev_malloc((void **)&e->d_pages, pb);
+      de = de ? de : rqb_copy_h2d(e->d_pages, p->pages, pb, s->stream);
+      de = de ? de : rqb_stream_sync(s->stream);
+    }
+    if (de) { /* nothing of the half-built entry is kept */
+      if (e && e->d_pages) rqb_dev_free(e->d_pages);
+      free(e);
+      rqb_plan_free(p);
       pthread_mutex_unlock(&g_plan_mu);
       return dev_fail(de, "encoder plan upload");
     }
     e->next = g_enc_plans;
     g_enc_plans = e;
+    enc_plans_trim(RQB_ENC_PLANS_MAX);
   }
+  e->refs++;
+  e->use = ++g_enc_clock;
   pthread_mutex_unlock(&g_plan_mu);
-  if (s->plan && !s->plan_shared) rqb_plan_free(s->plan);
+  if (s->enc != e && s->enc && s->busy) { /* queued work may still read the previous program */
+    int w = solver_wait(s);
+    if (w) {
+      enc_plan_unref(e);
+      return w;
+    }
+  }
+  solver_detach_plan(s);
+  s->enc = e;
   s->plan = e->plan;
   s->plan_shared = 1;
   s->cur_pages = e->d_pages;
@@ -671,12 +853,13 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   rqb_solve_args *h = own->h_args + 1, *d = own->d_args + 1;
   for (int k = 0; k < n; k++) {
     if (!sv[k]->plan || sv[k]->T != own->T || sv[k]->dev != own->dev) return RQB_E_ARG;
-    if (sv[k] != own && sv[k]->busy) { /* its uploads must have landed */
-      int w = solver_wait(sv[k]);
-      if (w) return w;
+    if (sv[k] != own && sv[k]->busy) {
+      /* its uploads (symbols, program pages, arguments) are queued on its own stream: the launching
+       * stream waits for them on the device, the host does not */
+      DEV(rqb_event_record(sv[k]->ev_ready, sv[k]->stream));
+      DEV(rqb_stream_wait_event(own->stream, sv[k]->ev_ready));
     }
     h[k] = *sv[k]->h_args;
-    sv[k]->batch_owner = own;
   }
   own->busy = 1;
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
@@ -684,6 +867,14 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   DEV(rqb_launch_solve(d, n, h[0].width, own->stream));
   if (own->want_timing) DEV(rqb_event_record(own->ev1, own->stream));
   own->timed = own->want_timing;
+  /* whatever a member queues on its own stream from now on (fetches, emits, uploads of the next
+   * symbols, a later launch) runs after this kernel: no entry point needs to know about the batch */
+  DEV(rqb_event_record(own->ev_done, own->stream));
+  for (int k = 0; k < n; k++)
+    if (sv[k] != own) {
+      DEV(rqb_stream_wait_event(sv[k]->stream, own->ev_done));
+      sv[k]->busy = 1;
+    }
   return 0;
 }
 
