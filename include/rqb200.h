@@ -134,7 +134,10 @@ typedef struct {
   double t_matrix, t_peel, t_dense, t_emit; /* host seconds per planning phase */
   uint32_t n_ws_rows; /* working rows the program uses in HBM */
   int n_parts;        /* partial sums scheduled off the critical path */
-  int slice_bytes;    /* default column slice one CTA owns (see rqb_batch_slice_bytes) */
+  int slice_bytes;    /* column slice one CTA owns: the HBM flavour's default (see rqb_batch_slice_bytes) or the
+                         shared-memory flavour's slot width */
+  int smem;           /* 1: shared-memory flavour of the program (rows live in shared-memory slots) */
+  uint32_t n_slots, tab_bits; /* shared-memory flavour: slots per CTA, inactive symbols per XOR-table group */
 } rqb_solver_stats;
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out);
 
@@ -165,8 +168,16 @@ typedef struct {
   const uint8_t *pages;
   rqb_solver_stats stats;
   void *opaque;
+  /* shared-memory flavour of the program (rqb_program.h): rows live in n_slots slots of
+   * slice_bytes per CTA, XOR tables over tab_bits inactive symbols; smem == 0: HBM flavour */
+  int smem;
+  uint32_t slice_bytes, n_slots, tab_bits;
 } rqb_plan_blob;
 int rqb_plan_blob_build(int K_params, const rqb_solve_request *req, rqb_plan_blob *out);
+/* smem_budget: bytes of shared memory a CTA may use for row slots (0 = HBM flavour only;
+ * rqb_smem_budget() = what the solve kernel has on this build) */
+int rqb_plan_blob_build_ex(int K_params, const rqb_solve_request *req, uint32_t smem_budget, rqb_plan_blob *out);
+uint32_t rqb_smem_budget(void);
 void rqb_plan_blob_free(rqb_plan_blob *b);
 
 /* ---- batched row operations out of HBM --------------------------------- */

@@ -38,7 +38,8 @@ class SolverStats(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("i", "u", "nb", "rho", "nfree", "levels_fwd", "n_levels", "n_tasks", "n_pages")] + \
                [(n, C.c_size_t) for n in ("n_srcs", "n_gf_srcs", "n_horner", "nnz")] + \
                [(n, C.c_double) for n in ("t_matrix", "t_peel", "t_dense", "t_emit")] + \
-               [("n_ws_rows", C.c_uint32), ("n_parts", C.c_int), ("slice_bytes", C.c_int)]
+               [("n_ws_rows", C.c_uint32), ("n_parts", C.c_int), ("slice_bytes", C.c_int), ("smem", C.c_int),
+                ("n_slots", C.c_uint32), ("tab_bits", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -47,7 +48,8 @@ class SolverStats(C.Structure):
 class PlanBlob(C.Structure):
     _fields_ = [("n_ws_rows", C.c_uint32), ("n_pages", C.c_uint32), ("page_bytes", C.c_uint32),
                 ("row0", C.c_uint32 * 4), ("zero_row", C.c_uint32), ("n_rows", C.c_uint32),
-                ("pages", u8p), ("stats", SolverStats), ("opaque", vp)]
+                ("pages", u8p), ("stats", SolverStats), ("opaque", vp),
+                ("smem", C.c_int), ("slice_bytes", C.c_uint32), ("n_slots", C.c_uint32), ("tab_bits", C.c_uint32)]
 
 
 class Op(C.Structure):
@@ -144,6 +146,8 @@ def lib():
     sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
     sig("rqb_solver_run_batch_on", C.c_int, C.POINTER(vp), C.c_int, vp)
     sig("rqb_plan_blob_build", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.POINTER(PlanBlob))
+    sig("rqb_plan_blob_build_ex", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.c_uint32, C.POINTER(PlanBlob))
+    sig("rqb_smem_budget", C.c_uint32)
     sig("rqb_plan_blob_free", None, C.POINTER(PlanBlob))
     sig("rqb_matrix_create", C.c_int, C.POINTER(vp), sz, sz)
     sig("rqb_matrix_destroy", None, vp)
@@ -184,7 +188,7 @@ EXPORTED_SYMBOLS = [
     "rqb_matrix_upload", "rqb_matrix_download", "rqb_matrix_fill_random", "rqb_rowops_apply",
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
     "rqb_schedule_replay_stepwise", "rqb_schedule_plan_blob",
-    "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info",
+    "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info", "rqb_plan_blob_build_ex", "rqb_smem_budget",
 ]
 
 
@@ -326,10 +330,17 @@ class SolveRequest:
         return SolveRequest(isi, in_row, oh, want_c, missing), missing
 
 
-def plan_blob(K_params, req):
-    """Host-only: build the device program and return (rc, dict) without a GPU."""
+def smem_budget():
+    return lib().rqb_smem_budget()
+
+
+def plan_blob(K_params, req, smem=0):
+    """Host-only: build the device program and return (rc, dict) without a GPU.
+    smem: bytes of shared memory for row slots (0 = HBM flavour, True = the kernel's budget)."""
     b = PlanBlob()
-    rc = lib().rqb_plan_blob_build(K_params, C.byref(req.c), C.byref(b))
+    if smem is True:
+        smem = smem_budget()
+    rc = lib().rqb_plan_blob_build_ex(K_params, C.byref(req.c), int(smem), C.byref(b))
     if rc != 0:
         return rc, None
     out = {
@@ -337,6 +348,7 @@ def plan_blob(K_params, req):
         "row0": list(b.row0), "zero_row": b.zero_row, "n_rows": b.n_rows,
         "pages": np.ctypeslib.as_array(b.pages, (b.n_pages * b.page_bytes,)).copy(),
         "stats": b.stats.as_dict(),
+        "smem": b.smem, "slice_bytes": b.slice_bytes, "n_slots": b.n_slots, "tab_bits": b.tab_bits,
     }
     lib().rqb_plan_blob_free(C.byref(b))
     return 0, out

@@ -312,6 +312,248 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   }
 }
 
+// ------------------------------------------------- shared-memory solve kernel
+// The shared-memory flavour of the program (rqb_program.h): a CTA keeps its column slice
+// (kLanes x 16 bytes) of every live row of the block in shared-memory SLOTS for the whole
+// solve.  The received symbols are read from HBM once (LOAD tasks), every row operation of
+// the elimination runs in place on the slots -- ~30-cycle shared-memory latency per
+// dependency level instead of an L2/HBM round trip -- and only results go back to HBM, so
+// DRAM traffic is the compulsory traffic.  One CTA per SM (the slots take most of the 227 KB),
+// 512 threads = 512 / kLanes tasks at a time; program pages arrive through a 2-deep TMA ring.
+// grid = (ceil(width / (16 kLanes)), nblocks); dynamic smem = ring + barriers + n_slots * 16 kLanes.
+static constexpr int kSmemThreads = 512;
+static constexpr int kSmemRingStages = 2;
+static constexpr uint32_t kSmemRingBytes = kSmemRingStages * RQB_PAGE_BYTES;
+static constexpr uint32_t kSmemFixedBytes = kSmemRingBytes + 128; // ring + mbarriers, then the slots
+
+template <int kLanes>
+struct Slots {
+  static constexpr uint32_t kSlice = 16u * kLanes;
+  uint8_t *gbase;  // the block's HBM arena, already offset to this thread's column
+  uint32_t pitch;
+  uint32_t sbase;  // shared-space address of slot 0, already offset to this thread's lane
+  __device__ __forceinline__ uint32_t saddr(uint32_t slot) const { return sbase + slot * kSlice; }
+  __device__ __forceinline__ uint8_t *gaddr(uint32_t ref) const {
+    uint64_t p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(ref & (RQB_REF_GLOBAL - 1u)), "r"(pitch), "l"(gbase));
+    return reinterpret_cast<uint8_t *>(p);
+  }
+  __device__ __forceinline__ uint4 lds(uint32_t slot) const {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(saddr(slot))
+                 : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void sts(uint32_t slot, const uint4 &v) const {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr(slot)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+  }
+  __device__ __forceinline__ uint4 ldg(uint32_t ref) const {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(gaddr(ref))
+                 : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void stg(uint32_t ref, const uint4 &v) const {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr(ref)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+  }
+  // a mixed reference: a slot, or (bit 23) a row of the HBM arena
+  __device__ __forceinline__ uint4 ld(uint32_t ref) const { return (ref & RQB_REF_GLOBAL) ? ldg(ref) : lds(ref); }
+  __device__ __forceinline__ void st(uint32_t ref, const uint4 &v) const {
+    if (ref & RQB_REF_GLOBAL) stg(ref, v); else sts(ref, v);
+  }
+};
+
+template <int kLanes>
+__device__ __noinline__ void smem_task_gf(const Slots<kLanes> R, const uint32_t *sp, uint32_t nsrc, uint32_t dst) {
+  uint4 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    v[u] = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)u < nsrc) v[u] = R.ld(sp[u] & RQB_REF_MASK);
+  }
+  uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    if ((uint32_t)u < nsrc) {
+      const BetaPlanes bp = beta_planes(sp[u] >> 24);
+      acc.x ^= gfmul4(v[u].x, bp); acc.y ^= gfmul4(v[u].y, bp);
+      acc.z ^= gfmul4(v[u].z, bp); acc.w ^= gfmul4(v[u].w, bp);
+    }
+  }
+  R.st(dst, acc);
+}
+
+// SCAN2: y = alpha*y ^ slot[e_k]; the two HDPC accumulators of column k take y; y ends in slot `yend`
+template <int kLanes>
+__device__ __noinline__ void smem_task_scan2(const Slots<kLanes> R, const uint32_t *sp, uint32_t nsrc, uint32_t acc0,
+                                             uint32_t yend, uint32_t aux) {
+  const uint32_t H = aux & 31u;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (uint32_t h = 0; h < H; h++) R.sts(acc0 + h, zero);
+  const uint32_t n_acc = (aux & 0x80u) ? nsrc - 1 : nsrc; // the last column of the scan carries no ones
+  uint4 y = zero;
+  for (uint32_t k0 = 0; k0 < nsrc; k0 += 4) {
+    const uint4 e = *reinterpret_cast<const uint4 *>(sp + k0);
+    const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+    uint4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      x[u] = zero;
+      if (k0 + u < nsrc && (ev[u] & RQB_REF_MASK) != RQB_REF_NONE) x[u] = R.lds(ev[u] & RQB_REF_MASK);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k0 + u < nsrc) {
+        y.x = xtime4(y.x) ^ x[u].x; y.y = xtime4(y.y) ^ x[u].y;
+        y.z = xtime4(y.z) ^ x[u].z; y.w = xtime4(y.w) ^ x[u].w;
+        if (k0 + u < n_acc) {
+          const uint32_t s1 = acc0 + ((ev[u] >> 24) & 15u), s2 = acc0 + (ev[u] >> 28);
+          uint4 a1 = R.lds(s1), a2 = R.lds(s2);
+          xor4(a1, y);
+          xor4(a2, y);
+          R.sts(s1, a1);
+          R.sts(s2, a2);
+        }
+      }
+    }
+  }
+  R.sts(yend, y);
+}
+
+// TAB, in place: slot[dst] ^= XOR_j slot[tab_base + (j << bits) + v_j] over the non-zero group
+// values v_j of one row of G; the result also goes to the arena row `also` (an encoder's C row)
+template <int kLanes>
+__device__ __noinline__ void smem_task_tab(const Slots<kLanes> R, const uint32_t *sp, uint32_t ngroups, uint32_t dst,
+                                           uint32_t also, uint32_t tab_base, uint32_t bits) {
+  uint4 acc = R.lds(dst);
+  for (uint32_t j0 = 0; j0 < ngroups; j0 += 8) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(sp + j0 / 4); // bytes j0 .. j0+7 (the list is zero-padded)
+    uint32_t row[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t b = ((k < 4 ? w.x : w.y) >> (8 * (k & 3))) & 0xffu;
+      row[k] = b ? tab_base + ((j0 + k) << bits) + b : 0u; // slot 0 is all zero
+    }
+    uint4 v0 = R.lds(row[0]), v1 = R.lds(row[1]), v2 = R.lds(row[2]), v3 = R.lds(row[3]);
+    uint4 v4 = R.lds(row[4]), v5 = R.lds(row[5]), v6 = R.lds(row[6]), v7 = R.lds(row[7]);
+    acc.x ^= xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+    acc.y ^= xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+    acc.z ^= xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+    acc.w ^= xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+  }
+  R.sts(dst, acc);
+  if (also != RQB_ROW_NONE) R.stg(also, acc);
+}
+
+template <int kLanes>
+__global__ void __launch_bounds__(kSmemThreads, 1)
+rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
+  constexpr int kTaskGroups = kSmemThreads / kLanes;
+  constexpr uint32_t kSliceBytes = 16u * kLanes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const rqb_solve_args &a = args_list[blockIdx.y];
+  const uint32_t width = a.width;
+  const uint32_t col0 = blockIdx.x * kSliceBytes;
+  if (col0 >= width) return; // whole CTA leaves: no barrier is skipped by a subset
+  uint8_t *ring = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kSmemRingBytes);
+  const int tid = threadIdx.x;
+  const uint32_t n_pages = a.n_pages;
+  const uint8_t *pages = a.pages;
+  const uint32_t lane = (uint32_t)tid % kLanes, grp = (uint32_t)tid / kLanes;
+  Slots<kLanes> R;
+  R.gbase = a.base + col0 + lane * 16u;
+  R.pitch = a.pitch;
+  R.sbase = smem_u32(smem + kSmemFixedBytes) + lane * 16u;
+
+  if (tid == 0) {
+    for (int s = 0; s < kSmemRingStages; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (grp == 0) R.sts(0, make_uint4(0, 0, 0, 0)); // slot 0: the zero row
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t first = n_pages < (uint32_t)kSmemRingStages ? n_pages : (uint32_t)kSmemRingStages;
+    for (uint32_t s = 0; s < first; s++) {
+      mbar_expect_tx(&bars[s], RQB_PAGE_BYTES);
+      tma_bulk_g2s(ring + s * RQB_PAGE_BYTES, pages + (size_t)s * RQB_PAGE_BYTES, RQB_PAGE_BYTES, &bars[s]);
+    }
+  }
+  const bool active = col0 + lane * 16u < width; // the last slice of a row may be narrower
+
+  for (uint32_t pg = 0; pg < n_pages; pg++) {
+    const uint32_t st = pg % kSmemRingStages;
+    mbar_wait(&bars[st], (pg / kSmemRingStages) & 1u);
+    const uint8_t *page = ring + st * RQB_PAGE_BYTES;
+    const uint32_t n_levels = reinterpret_cast<const rqb_page_hdr *>(page)->n_levels;
+    uint32_t off = sizeof(rqb_page_hdr);
+    for (uint32_t lv = 0; lv < n_levels; lv++) {
+      const uint4 lh = *reinterpret_cast<const uint4 *>(page + off); // n_tasks, next_off, tab_base, zero_row
+      const uint4 *tasks = reinterpret_cast<const uint4 *>(page + off + sizeof(rqb_level_hdr));
+      if (active) {
+        for (uint32_t t = grp; t < lh.x; t += kTaskGroups) {
+          const uint4 th = tasks[t]; // {src_off, dst, nsrc | kind<<16 | aux<<24, pad}
+          const uint32_t nsrc = th.z & 0xffffu, kind = (th.z >> 16) & 0xffu;
+          const uint32_t *sp = reinterpret_cast<const uint32_t *>(page + th.x);
+          if (kind == RQB_T_XOR) {
+            // exactly 4 or 8 references (padded with slot 0): all loads issued before the first use
+            const uint4 i0 = *reinterpret_cast<const uint4 *>(sp);
+            uint4 v0 = R.ld(i0.x), v1 = R.ld(i0.y), v2 = R.ld(i0.z), v3 = R.ld(i0.w);
+            uint4 acc;
+            if (nsrc > 4) {
+              const uint4 i1 = *reinterpret_cast<const uint4 *>(sp + 4);
+              uint4 v4 = R.ld(i1.x), v5 = R.ld(i1.y), v6 = R.ld(i1.z), v7 = R.ld(i1.w);
+              acc.x = xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+              acc.y = xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+              acc.z = xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+              acc.w = xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+            } else {
+              acc.x = xor3(v0.x, v1.x, v2.x) ^ v3.x;
+              acc.y = xor3(v0.y, v1.y, v2.y) ^ v3.y;
+              acc.z = xor3(v0.z, v1.z, v2.z) ^ v3.z;
+              acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
+            }
+            R.st(th.y, acc);
+          } else if (kind == RQB_T_TAB) {
+            smem_task_tab<kLanes>(R, sp, nsrc, th.y, th.w, lh.z, th.z >> 24);
+          } else if (kind == RQB_T_LOAD) {
+            // slots dst.. = arena rows pad..: four loads in flight
+            for (uint32_t k = 0; k < nsrc; k += 4) {
+              uint4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++)
+                if (k + u < nsrc) v[u] = R.ldg(th.w + k + u);
+#pragma unroll
+              for (int u = 0; u < 4; u++)
+                if (k + u < nsrc) R.sts(th.y + k + u, v[u]);
+            }
+          } else if (kind == RQB_T_SCAN2) {
+            smem_task_scan2<kLanes>(R, sp, nsrc, th.y, th.w, th.z >> 24);
+          } else {
+            smem_task_gf<kLanes>(R, sp, nsrc, th.y);
+          }
+        }
+      }
+      __syncthreads();
+      off = lh.y;
+    }
+    if (n_levels == 0) __syncthreads();
+    // every thread is past its last read of this stage: refill it
+    if (tid == 0 && pg + kSmemRingStages < n_pages) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[st], RQB_PAGE_BYTES);
+      tma_bulk_g2s(ring + st * RQB_PAGE_BYTES, pages + (size_t)(pg + kSmemRingStages) * RQB_PAGE_BYTES,
+                   RQB_PAGE_BYTES, &bars[st]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LT kernel
 // one CTA per output symbol; lane 0 expands Tuple[K', isi] into row indices.
 __global__ void __launch_bounds__(128)
@@ -623,6 +865,47 @@ int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_w
     rqb_solve_kernel<4><<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
   else
     rqb_solve_kernel<8><<<grid, kSolveThreads, kSolveSmem, (cudaStream_t)stream>>>(args_dev);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+/* shared-memory flavour: every block of the launch uses the same slice width (16, 32 or 64 bytes)
+ * and at most max_slots slots */
+int rqb_smem_slot_budget_bytes(void) { return (int)(227u * 1024u - kSmemFixedBytes); }
+
+} // extern "C" (templates have C++ linkage)
+template <int kLanes>
+static int launch_smem(const rqb_solve_args *args_dev, dim3 grid, uint32_t smem_bytes, cudaStream_t stream) {
+  static std::atomic<int> configured[64];
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+    CK(cudaFuncSetAttribute(rqb_solve_smem_kernel<kLanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev < 64) configured[dev].store(1, std::memory_order_release);
+  }
+  rqb_solve_smem_kernel<kLanes><<<grid, kSmemThreads, smem_bytes, stream>>>(args_dev);
+  return 0;
+}
+extern "C" {
+
+int rqb_launch_solve_smem(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, uint32_t slice_bytes,
+                          uint32_t max_slots, void *stream) {
+  if (nblocks <= 0 || max_width == 0) return 0;
+  const uint32_t smem_bytes = kSmemFixedBytes + max_slots * slice_bytes;
+  if (smem_bytes > 227u * 1024u || (slice_bytes != 16 && slice_bytes != 32 && slice_bytes != 64)) {
+    snprintf(g_err, sizeof(g_err), "rqb_launch_solve_smem: %u slots of %u bytes do not fit", max_slots, slice_bytes);
+    return (int)cudaErrorInvalidValue;
+  }
+  dim3 grid((max_width + slice_bytes - 1) / slice_bytes, (unsigned)nblocks);
+  int e;
+  if (slice_bytes == 64)
+    e = launch_smem<4>(args_dev, grid, smem_bytes, (cudaStream_t)stream);
+  else if (slice_bytes == 32)
+    e = launch_smem<2>(args_dev, grid, smem_bytes, (cudaStream_t)stream);
+  else
+    e = launch_smem<1>(args_dev, grid, smem_bytes, (cudaStream_t)stream);
+  if (e) return e;
   g_launches++;
   CK(cudaGetLastError());
   return 0;

@@ -72,6 +72,11 @@ int rqb_event_elapsed_ms(void *start, void *stop, float *ms);
 /* launches ONE kernel over nblocks source blocks (gridDim.y); args_dev is a
  * device array of rqb_solve_args; max_width is the maximum over the batch */
 int rqb_launch_solve(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, void *stream);
+/* the shared-memory flavour of the program (rqb_program.h): all blocks of the launch use
+ * slice_bytes-wide slots (16, 32 or 64), at most max_slots of them */
+int rqb_launch_solve_smem(const rqb_solve_args *args_dev, int nblocks, uint32_t max_width, uint32_t slice_bytes,
+                          uint32_t max_slots, void *stream);
+int rqb_smem_slot_budget_bytes(void);
 /* column slice (bytes per CTA: 64, 128 or 256) rqb_launch_solve picks for such a launch */
 int rqb_solve_slice_bytes(int nblocks, uint32_t max_width);
 

@@ -118,7 +118,8 @@ enum {
   SC_PCOL, SC_UCOL, SC_STK1, SC_STK2, SC_LEVEL, SC_G, SC_LOWROWS, SC_SB, SC_TB, SC_XPTR, SC_XIDX, SC_SH,
   SC_HB1, SC_HB2, SC_YBUF, SC_ACCBUF, SC_PIVROW, SC_PIVCOL, SC_FREECOLS, SC_Q, SC_TQ, SC_TMP, SC_CSLOT,
   SC_FPTR, SC_FITEMS, SC_PFIRST, SC_PLEVEL, SC_PPTR, SC_PITEMS, SC_CURLOC, SC_TASKS, SC_SRCS, SC_ORDER,
-  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_FRUSED, SC_FRTAB, SC_CINFO, SC_COUNT
+  SC_LVLCNT, SC_CS, SC_COEF, SC_SORT, SC_FRUSED, SC_FRTAB, SC_CINFO, SC_CHFIRST, SC_CHLEVEL, SC_CHPTR,
+  SC_CHITEMS, SC_HAS, SC_NEEDED, SC_GC, SC_COUNT
 };
 typedef struct {
   void *p[SC_COUNT];
@@ -208,7 +209,7 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
   t->kind = (uint8_t)kind;
   t->aux = (uint8_t)aux;
   t->extra = 0;
-  if (kind == RQB_T_GF) {
+  if (kind == RQB_T_GF || kind == RQB_T_SCAN2) { /* the top byte carries the multiplier / the two HDPC rows */
     if (n) memcpy(b->srcs + b->ns, srcs, (size_t)n * sizeof(uint32_t));
   } else { /* XOR and SCAN sources are bare row numbers */
     for (uint32_t k = 0; k < n; k++) b->srcs[b->ns + k] = srcs[k] & RQB_REF_MASK;
@@ -217,7 +218,7 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
   if (level > b->max_level) b->max_level = level;
   if (kind == RQB_T_GF)
     b->tot_gf += n;
-  else if (kind == RQB_T_SCAN)
+  else if (kind == RQB_T_SCAN || kind == RQB_T_SCAN2)
     b->tot_h += n;
   else
     b->tot_x += n;
@@ -225,7 +226,15 @@ static void b_task(builder *b, int kind, uint32_t dst, int aux, uint32_t level, 
 
 /* TAB task: row[dst] = row[src0] ^ XOR_j table row (j, bytes[j]); the nbytes bytes go where
  * other tasks keep their source list */
+static void b_tab_ex(builder *b, uint32_t dst, uint32_t extra, int aux, uint32_t level, const uint8_t *bytes,
+                     uint32_t nbytes);
 static void b_tab(builder *b, uint32_t dst, uint32_t src0, uint32_t level, const uint8_t *bytes, uint32_t nbytes) {
+  b_tab_ex(b, dst, src0, 0, level, bytes, nbytes);
+}
+/* extra: the row src0 (HBM flavour) / the arena row that also receives the result (smem flavour);
+ * aux: bits per table group (smem flavour) */
+static void b_tab_ex(builder *b, uint32_t dst, uint32_t src0, int aux, uint32_t level, const uint8_t *bytes,
+                     uint32_t nbytes) {
   const uint32_t words = (nbytes + 3) / 4;
   b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
   b->srcs = sc_grow(b->sc, SC_SRCS, (b->ns + words + 1) * sizeof(uint32_t));
@@ -237,13 +246,35 @@ static void b_tab(builder *b, uint32_t dst, uint32_t src0, uint32_t level, const
   t->extra = src0;
   t->nsrc = (uint16_t)nbytes;
   t->kind = RQB_T_TAB;
-  t->aux = 0;
+  t->aux = (uint8_t)aux;
   b->srcs[b->ns + words - 1] = 0;
   memcpy(b->srcs + b->ns, bytes, nbytes);
   b->ns += words;
   if (level > b->max_level) b->max_level = level;
   for (uint32_t k = 0; k < nbytes; k++) b->tot_x += bytes[k] != 0;
   b->tot_x += 1;
+}
+
+/* smem flavour: slots dst .. dst+count-1 = arena rows first_row .. first_row+count-1 */
+static void b_load(builder *b, uint32_t dst, uint32_t first_row, uint32_t count, uint32_t level) {
+  b->tasks = sc_grow(b->sc, SC_TASKS, (b->nt + 1) * sizeof(ptask));
+  if (b->sc->oom) return;
+  ptask *t = &b->tasks[b->nt++];
+  t->dst = dst;
+  t->src_at = (uint32_t)b->ns;
+  t->level = level;
+  t->extra = first_row;
+  t->nsrc = (uint16_t)count;
+  t->kind = RQB_T_LOAD;
+  t->aux = 0;
+  if (level > b->max_level) b->max_level = level;
+  b->tot_x += count;
+}
+/* smem flavour: one chunk of the alpha-scan with the HDPC sums folded in (rqb_program.h) */
+static void b_scan2(builder *b, uint32_t acc_base, uint32_t yend, int aux, uint32_t level, const uint32_t *entries,
+                    uint32_t n) {
+  b_task(b, RQB_T_SCAN2, acc_base, aux, level, entries, n);
+  if (!b->sc->oom) b->tasks[b->nt - 1].extra = yend;
 }
 
 /* row[dst] = sum of n sources that all exist before `level`: one task, or a
@@ -287,6 +318,7 @@ static uint32_t b_tree(builder *b, int kind, uint32_t dst, uint32_t *srcs, uint3
 /* bytes of a task's source list in the page: XOR lists are padded to 4 or 8 entries */
 static size_t list_bytes(const ptask *t) {
   if (t->kind == RQB_T_XOR) return t->nsrc <= 4 ? 16 : 32;
+  if (t->kind == RQB_T_LOAD) return 0;
   if (t->kind == RQB_T_TAB) return ((size_t)t->nsrc + 15) & ~(size_t)15;
   return ((size_t)t->nsrc * 4 + 15) & ~(size_t)15;
 }
@@ -300,10 +332,10 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   const uint32_t nl = b->max_level + 1;
   /* one stable counting sort by (level, kind, narrow/wide list): tasks that take the
    * same path through the kernel sit together inside a level */
-  const uint32_t nkeys = nl * 5;
+  const uint32_t nkeys = nl * 8;
   uint32_t *cnt = sc_buf(sc, SC_LVLCNT, ((size_t)nkeys + 2) * 4, 1);
   uint32_t *order = sc_buf(sc, SC_ORDER, (b->nt + 1) * 4, 0);
-#define TKEY(t) ((t).level * 5 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
+#define TKEY(t) ((t).level * 8 + ((t).kind == RQB_T_XOR ? (uint32_t)((t).nsrc > 4) : (t).kind + 1u))
   size_t tot_bytes = 0;
   for (size_t k = 0; k < b->nt; k++) {
     cnt[TKEY(b->tasks[k]) + 1]++;
@@ -312,7 +344,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
   for (uint32_t l = 0; l < nkeys; l++) cnt[l + 1] += cnt[l];
   for (size_t k = 0; k < b->nt; k++) order[cnt[TKEY(b->tasks[k])]++] = (uint32_t)k;
 #undef TKEY
-  /* cnt[key] now holds the END of its bucket: level l spans [cnt[5l-1], cnt[5l+4]) */
+  /* cnt[key] now holds the END of its bucket: level l spans [cnt[8l-1], cnt[8l+7]) */
   size_t npages = 0, cur = 0, levels_in_page = 0, levels = 0;
   /* into the caller's buffer when the program certainly fits: the tasks, a header per level
    * (levels split over pages get one per piece) and up to 512 unused bytes at the end of a page */
@@ -350,7 +382,7 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
     cur = 0;                                                                                      \
   } while (0)
   for (uint32_t l = 0; l < nl; l++) {
-    size_t lo = l ? cnt[5 * l - 1] : 0, hi = cnt[5 * l + 4];
+    size_t lo = l ? cnt[8 * l - 1] : 0, hi = cnt[8 * l + 7];
     if (lo == hi) continue;
     size_t idx = lo;
     while (idx < hi) {
@@ -379,7 +411,8 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
       for (size_t k = 0; k < n; k++) {
         const ptask *t = &b->tasks[order[idx + k]];
         size_t sb = list_bytes(t);
-        memcpy(page + soff, b->srcs + t->src_at, t->kind == RQB_T_TAB ? (size_t)t->nsrc : (size_t)t->nsrc * 4);
+        if (t->kind != RQB_T_LOAD)
+          memcpy(page + soff, b->srcs + t->src_at, t->kind == RQB_T_TAB ? (size_t)t->nsrc : (size_t)t->nsrc * 4);
         if (t->kind == RQB_T_XOR)
           for (size_t q = t->nsrc; q < sb / 4; q++) ((uint32_t *)(page + soff))[q] = zero_row;
         dst[k].src_off = soff;
@@ -606,6 +639,410 @@ static void backsub_init(void) {
   g_fr_mode = !e ? 0 : !strncmp(e, "tables", 6) ? 1 : !strcmp(e, "triangular") ? 2 : 0;
 }
 
+/* ------------------------------------------------- shared-memory flavour
+ * In-place chains: a row that lives in a shared-memory slot accumulates its terms where it
+ * is, up to 7 at a time (8 sources per task, one of them the row itself), each group as early
+ * as its terms exist -- no rows for partial sums.  rd[]/it[] = level at which each term is
+ * final / the term; returns the level at which the row is final. */
+typedef struct {
+  int *first;  /* row index -> first group; rows 0..I-1 peeled positions, I..I+nb-1 residual rows */
+  int *level;  /* group -> level of its task */
+  int *ptr;    /* group -> first item */
+  int *items;  /* peeled positions */
+  int ng, nitems;
+} chains;
+
+static int chain_row(chains *ch, int *rd, int *it, int cnt, int has_self, int maxkey, uint64_t *sortbuf) {
+  if (cnt > 1) sort_by_level(rd, it, cnt, maxkey, sortbuf);
+  int prev = 0, idx = 0, cap = has_self ? (int)RQB_MAX_SRCS - 1 : (int)RQB_MAX_SRCS;
+  while (idx < cnt) {
+    const int take = cnt - idx < cap ? cnt - idx : cap;
+    const int lv = (rd[idx + take - 1] > prev ? rd[idx + take - 1] : prev) + 1;
+    ch->level[ch->ng] = lv;
+    ch->ptr[ch->ng] = ch->nitems;
+    for (int k = 0; k < take; k++) ch->items[ch->nitems++] = it[idx + k];
+    ch->ng++;
+    prev = lv;
+    idx += take;
+    cap = (int)RQB_MAX_SRCS - 1;
+  }
+  ch->ptr[ch->ng] = ch->nitems;
+  return prev;
+}
+
+/* bits [bits*j, bits*j + bits) of a bit row of uw words */
+static inline uint32_t group_val(const uint64_t *g, int uw, int j, int bits) {
+  const int off = j * bits, w = off >> 6, sh = off & 63;
+  uint64_t x = g[w] >> sh;
+  if (sh + bits > 64 && w + 1 < uw) x |= g[w + 1] << (64 - sh);
+  return (uint32_t)(x & ((1u << bits) - 1u));
+}
+
+/* what the analysis (steps 1-3 of rqb_plan_build) hands to the emitter */
+typedef struct {
+  const rqb_plan_request *req;
+  rqb_params P;
+  int oh, R, n, nlt, I, U, uw, nb, nbw, uq, nfree, maxlevel;
+  const int *rptr, *cidx, *col_pos, *col_t, *prow, *pcol, *ucol, *lowrows, *pivrow, *freecols, *qrow_of_f;
+  const uint8_t *col_state, *hb1, *hb2, *Sh, *TQ;
+  const uint64_t *G, *Sb, *Tb;
+  const chains *ch;
+  uint32_t slot_budget; /* slots a CTA can hold at the chosen slice width */
+  uint32_t row0[4];
+} plan_view;
+
+#define SM_G(row) (RQB_REF_GLOBAL | (uint32_t)(row))
+
+/* Emits the shared-memory flavour of the program (rqb_program.h).  Slots:
+ *   0                 zeros
+ *   1 + r             matrix row r (LDPC, HDPC, LT), updated in place: Y_p, r_m, r'_h, finally x_p
+ *   1 + R + t         inactive column t: r'_t, then z_t in place
+ *   1 + R + U ...     scratch, reused phase by phase: scan accumulators and y ends, partial sums
+ *                     of the GF(256) trees, then the XOR tables of the back-substitution, then the
+ *                     partial sums of long output rows
+ * Returns 0, -7 (out of memory) or -8 (does not fit the slot budget: use the HBM flavour). */
+static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n_slots_out, uint32_t *tab_bits_out) {
+  const rqb_plan_request *req = v->req;
+  const int S = v->P.S, H = v->P.H, L = v->P.L, R = v->R, U = v->U, I = v->I, n = v->n, nb = v->nb;
+  const int uw = v->uw, nbw = v->nbw, nfree = v->nfree;
+  const uint32_t SCR = 1u + (uint32_t)R + (uint32_t)U;
+  if (v->slot_budget <= SCR + 64) return -8;
+  const uint32_t scr_cap = v->slot_budget - SCR;
+#define SLOT_ROW(r) (1u + (uint32_t)(r))
+#define SLOT_Z(t) (1u + (uint32_t)R + (uint32_t)(t))
+  uint8_t *has = sc_buf(sc, SC_HAS, (size_t)SCR + 8, 1); /* the slot holds a value (otherwise: known zero) */
+  uint32_t *tmp = sc_buf(sc, SC_TMP, sizeof(uint32_t) * ((size_t)L + (size_t)nb + (size_t)4 * (size_t)n + 4096), 0);
+  uint8_t *needed = sc_buf(sc, SC_NEEDED, (size_t)L + 8, 0); /* columns whose intermediate symbol is an output term */
+  if (sc->oom) return -7;
+  uint32_t peak = SCR, sp;
+  bd->ws_base = 0; /* b_tree takes rows for partial sums from ws_base + ws_next++: scratch slots here */
+#define PUSHS(ns, slot)                                   \
+  do {                                                    \
+    uint32_t _s = (slot);                                 \
+    if (has[_s]) tmp[(ns)++] = RQB_SRC(_s, 1);            \
+  } while (0)
+
+  /* which intermediate symbols are wanted: all of them (encoder), or the terms of the outputs */
+  if (req->want_c) {
+    memset(needed, 1, (size_t)L);
+  } else {
+    memset(needed, 0, (size_t)L);
+    for (int k = 0; k < req->n_out; k++) {
+      uint32_t idx[RQB_MAX_LT_DEGREE];
+      int cnt = rqb_host_lt_indices(&v->P, req->out_isi[k], idx);
+      for (int q = 0; q < cnt; q++) needed[idx[q]] = 1;
+    }
+  }
+
+  /* level 0: the received symbols, HBM -> slots, in runs of consecutive rows */
+  for (int k = 0; k < v->nlt;) {
+    if (req->in_row[k] == RQB_ROW_NONE) {
+      k++;
+      continue;
+    }
+    if (req->in_row[k] >= req->in_rows) return -1;
+    int len = 1;
+    while (k + len < v->nlt && len < 16 && req->in_row[k + len] == req->in_row[k] + (uint32_t)len) len++;
+    if (req->in_row[k] + (uint32_t)len > req->in_rows) return -1;
+    b_load(bd, SLOT_ROW(S + H + k), SM_G(v->row0[RQB_SP_IN] + req->in_row[k]), (uint32_t)len, 0);
+    for (int q = 0; q < len; q++) has[SLOT_ROW(S + H + k + q)] = 1;
+    k += len;
+  }
+
+  /* A + B: the triangular solve Y = X^-1 b_top and the residual rows r_m = b_m ^ X_low Y, all in place */
+  uint32_t endA = (uint32_t)v->maxlevel;
+  for (int idx = 0; idx < I + nb; idx++) {
+    const int r = idx < I ? v->prow[idx] : v->lowrows[idx - I];
+    const uint32_t dst = SLOT_ROW(r);
+    for (int g = v->ch->first[idx]; g < v->ch->first[idx + 1]; g++) {
+      uint32_t ns = 0;
+      PUSHS(ns, dst);
+      const uint32_t self = ns;
+      for (int e = v->ch->ptr[g]; e < v->ch->ptr[g + 1]; e++) PUSHS(ns, SLOT_ROW(v->prow[v->ch->items[e]]));
+      if (ns == self) continue; /* nothing to add */
+      b_task(bd, RQB_T_XOR, dst, 0, (uint32_t)v->ch->level[g], tmp, ns);
+      has[dst] = 1;
+      if ((uint32_t)v->ch->level[g] > endA) endA = (uint32_t)v->ch->level[g];
+    }
+  }
+  const uint32_t lvB = (uint32_t)v->maxlevel + 1;
+  const uint32_t endB = endA > lvB ? endA : lvB;
+
+  /* alpha-scans over the columns 0..n-1 in NC chunks, HDPC sums accumulated on the way (SCAN2) */
+  int NC = n / 32;
+  if (NC > 128) NC = 128;
+  if (NC < 1) NC = 1;
+  for (;;) {
+    const uint32_t gf_tmp = (uint32_t)H * (((uint32_t)NC + (uint32_t)U + 2u + 6u) / 7u + 3u);
+    if ((uint32_t)NC * ((uint32_t)H + 1u) + gf_tmp <= scr_cap || NC == 1) break;
+    NC /= 2;
+  }
+  if ((uint32_t)NC * ((uint32_t)H + 1u) + (uint32_t)H * 8u > scr_cap) return -8;
+#define ACC(c, h) (SCR + (uint32_t)(c) * (uint32_t)H + (uint32_t)(h))
+#define YEND(c) (SCR + (uint32_t)NC * (uint32_t)H + (uint32_t)(c))
+  int *cs = sc_buf(sc, SC_CS, sizeof(int) * ((size_t)NC + 2), 0);
+  if (sc->oom) return -7;
+  for (int c = 0; c <= NC; c++) cs[c] = (int)((long)n * c / NC);
+  for (int c = 0; c < NC; c++) {
+    uint32_t ns = 0;
+    for (int j = cs[c]; j < cs[c + 1]; j++) {
+      uint32_t ref = RQB_REF_NONE;
+      if (v->col_state[j] == 1 && has[SLOT_ROW(v->prow[v->col_pos[j]])]) ref = SLOT_ROW(v->prow[v->col_pos[j]]);
+      const uint32_t h1 = j + 1 < n ? v->hb1[j] : 0u, h2 = j + 1 < n ? v->hb2[j] : 0u;
+      tmp[ns++] = ref | (h1 << 24) | (h2 << 28);
+    }
+    b_scan2(bd, ACC(c, 0), YEND(c), H | (cs[c + 1] == n ? 0x80 : 0), lvB, tmp, ns);
+  }
+  sp = SCR + (uint32_t)NC * ((uint32_t)H + 1u);
+  if (sp > peak) peak = sp;
+
+  /* C1: r'_t = XOR of the residual rows the GF(2) elimination combined for pivot column t */
+  uint32_t lvC = endB + 1, endC1 = endB;
+  for (int t = 0; t < U; t++) {
+    if (v->pivrow[t] < 0) continue;
+    const uint64_t *tb = v->Tb + (size_t)v->pivrow[t] * nbw;
+    const uint32_t dst = SLOT_Z(t);
+    uint32_t ns = 0, lv = lvC;
+    for (int m = 0; m < nb; m++) {
+      if (!bit_get(tb, m) || !has[SLOT_ROW(v->lowrows[m])]) continue;
+      tmp[ns++] = RQB_SRC(SLOT_ROW(v->lowrows[m]), 1);
+      if (ns == RQB_MAX_SRCS) {
+        b_task(bd, RQB_T_XOR, dst, 0, lv, tmp, ns);
+        has[dst] = 1;
+        if (lv > endC1) endC1 = lv;
+        lv++;
+        ns = 0;
+        tmp[ns++] = RQB_SRC(dst, 1);
+      }
+    }
+    if (ns > (has[dst] ? 1u : 0u)) {
+      b_task(bd, RQB_T_XOR, dst, 0, lv, tmp, ns);
+      has[dst] = 1;
+      if (lv > endC1) endC1 = lv;
+    }
+  }
+  /* HDPC sums: XOR the chunks' accumulators together, in place, 8 at a time */
+  uint32_t endT = endB;
+  {
+    uint32_t lv = lvC;
+    for (int stride = 1; stride < NC; stride *= 8, lv++) {
+      for (int c0 = 0; c0 < NC; c0 += stride * 8)
+        for (int h = 0; h < H; h++) {
+          uint32_t ns = 0;
+          for (int k = 0; k < 8 && c0 + k * stride < NC; k++) tmp[ns++] = RQB_SRC(ACC(c0 + k * stride, h), 1);
+          if (ns > 1) b_task(bd, RQB_T_XOR, ACC(c0, h), 0, lv, tmp, ns);
+        }
+      endT = lv;
+    }
+  }
+  uint32_t lv = (endC1 > endT ? endC1 : endT) + 1, end = lv;
+
+  /* C2: r'_h = r_h ^ sum_c Gc[h][c]*yend_c ^ sum_t beta[h][t]*r'_t (GF leaves, XOR tree); the
+   * coefficients as in the HBM flavour (see there) */
+  {
+    uint8_t *coef = sc_buf(sc, SC_COEF, (size_t)NC * (size_t)H, 1);
+    uint8_t *gc = sc_buf(sc, SC_GC, (size_t)NC * (size_t)H + 64, 0);
+    if (sc->oom) return -7;
+    for (int c = 0; c < NC; c++)
+      for (int j = cs[c]; j < cs[c + 1] && j + 1 < n; j++) {
+        uint8_t a = rqb_gf_pow2(&GF, j - cs[c] + 1);
+        coef[c * H + v->hb1[j]] ^= a;
+        coef[c * H + v->hb2[j]] ^= a;
+      }
+    uint8_t suf[RQB_MAX_H];
+    memset(suf, 0, sizeof(suf));
+    for (int c1 = NC - 1; c1 >= 0; c1--) {
+      if (c1 + 1 < NC) {
+        uint8_t a = rqb_gf_pow2(&GF, cs[c1 + 2] - cs[c1 + 1]);
+        for (int h = 0; h < H; h++) suf[h] = rqb_gf_mul(&GF, suf[h], a) ^ coef[(c1 + 1) * H + h];
+      }
+      for (int h = 0; h < H; h++)
+        gc[c1 * H + h] = rqb_gf_mul(&GF, rqb_gf_pow2(&GF, h), rqb_gf_pow2(&GF, n - cs[c1 + 1])) ^ suf[h];
+    }
+    bd->ws_next = sp;
+    for (int h = 0; h < H; h++) {
+      const uint8_t *row = v->Sh + (size_t)h * (size_t)v->uq * 8;
+      uint32_t ns = 0;
+      for (int c1 = 0; c1 < NC; c1++)
+        if (gc[c1 * H + h]) tmp[ns++] = RQB_SRC(YEND(c1), gc[c1 * H + h]);
+      for (int t = 0; t < U; t++)
+        if (v->pivrow[t] >= 0 && row[t] && has[SLOT_Z(t)]) tmp[ns++] = RQB_SRC(SLOT_Z(t), row[t]);
+      tmp[ns++] = RQB_SRC(ACC(0, h), 1);
+      uint32_t e2 = b_tree(bd, RQB_T_GF, SLOT_ROW(S + h), tmp, ns, lv);
+      has[SLOT_ROW(S + h)] = 1;
+      if (e2 > end) end = e2;
+    }
+    if (bd->ws_next > peak) peak = bd->ws_next;
+    if (peak > v->slot_budget) return -8;
+  }
+  lv = end + 1;
+  end = lv;
+  /* C3: z_f = sum_h TQ[qrow(f)][h] * r'_h */
+  for (int f = 0; f < nfree; f++) {
+    uint32_t ns = 0;
+    for (int h = 0; h < H; h++) {
+      uint8_t b = v->TQ[v->qrow_of_f[f] * H + h];
+      if (b) tmp[ns++] = RQB_SRC(SLOT_ROW(S + h), b);
+    }
+    uint32_t e2 = b_tree(bd, RQB_T_GF, SLOT_Z(v->freecols[f]), tmp, ns, lv);
+    has[SLOT_Z(v->freecols[f])] = 1;
+    if (e2 > end) end = e2;
+  }
+  if (bd->ws_next > peak) peak = bd->ws_next;
+  if (peak > v->slot_budget) return -8;
+  lv = end + 1;
+  end = lv;
+  /* C4: z_t = r'_t ^ XOR_{f: bit} z_f for the pivot columns, in place */
+  for (int t = 0; t < U; t++) {
+    if (v->pivrow[t] < 0) continue;
+    const uint64_t *ps = v->Sb + (size_t)v->pivrow[t] * uw;
+    const uint32_t dst = SLOT_Z(t);
+    uint32_t ns = 0, l2 = lv;
+    PUSHS(ns, dst);
+    for (int f = 0; f < nfree; f++) {
+      if (!bit_get(ps, v->freecols[f])) continue;
+      tmp[ns++] = RQB_SRC(SLOT_Z(v->freecols[f]), 1);
+      if (ns == RQB_MAX_SRCS) {
+        b_task(bd, RQB_T_XOR, dst, 0, l2, tmp, ns);
+        has[dst] = 1;
+        if (l2 > end) end = l2;
+        l2++;
+        ns = 0;
+        tmp[ns++] = RQB_SRC(dst, 1);
+      }
+    }
+    if (ns > (has[dst] ? 1u : 0u)) {
+      b_task(bd, RQB_T_XOR, dst, 0, l2, tmp, ns);
+      has[dst] = 1;
+      if (l2 > end) end = l2;
+    }
+  }
+  lv = end + 1;
+
+  /* F: x_p = Y_p ^ (G z)_p through XOR tables over groups of `bits` inactive symbols, the largest
+   * group size whose tables fit the scratch slots (everything that lived there is dead by now).
+   * Level lv: entries made of the z themselves (one half of the group's bits); lv+1: entries
+   * that combine a low and a high half; lv+2: one in-place TAB task per wanted row. */
+  int bits = 8;
+  while (bits > 4 && (((uint32_t)(U + bits - 1) / (uint32_t)bits) << bits) > scr_cap) bits--;
+  const int ngr = (U + bits - 1) / bits;
+  if (((uint32_t)ngr << bits) > scr_cap) return -8;
+  const uint32_t TAB = SCR;
+  bd->tab_base = TAB;
+  if (TAB + ((uint32_t)ngr << bits) > peak) peak = TAB + ((uint32_t)ngr << bits);
+  const int lo_bits = bits / 2;
+  const uint32_t lo_mask = (1u << lo_bits) - 1u, tsize = 1u << bits;
+  uint8_t *used = sc_buf(sc, SC_FRUSED, (size_t)ngr * tsize + 64, 1);
+  uint8_t *gv = sc_buf(sc, SC_FRTAB, (size_t)ngr + 64, 0);
+  if (sc->oom) return -7;
+#define GROUP_VAL(g, j) group_val((g), uw, (j), bits)
+  for (int p = 0; p < I; p++) {
+    if (!needed[v->pcol[p]]) continue;
+    const uint64_t *g = v->G + (size_t)p * uw;
+    for (int j = 0; j < ngr; j++) used[(size_t)j * tsize + GROUP_VAL(g, j)] = 1;
+  }
+  for (int j = 0; j < ngr; j++) {
+    uint8_t *use = used + (size_t)j * tsize;
+    for (uint32_t m = 1; m < tsize; m++)
+      if (use[m] == 1 && (m & lo_mask) && (m & ~lo_mask)) {
+        if (!use[m & lo_mask]) use[m & lo_mask] = 2;
+        if (!use[m & ~lo_mask]) use[m & ~lo_mask] = 2;
+      }
+    for (uint32_t m = 1; m < tsize; m++) {
+      if (!use[m]) continue;
+      const uint32_t slot = TAB + ((uint32_t)j << bits) + m;
+      if ((m & lo_mask) && (m & ~lo_mask)) {
+        uint32_t pair[2] = {TAB + ((uint32_t)j << bits) + (m & lo_mask), TAB + ((uint32_t)j << bits) + (m & ~lo_mask)};
+        b_task(bd, RQB_T_XOR, slot, 0, lv + 1, pair, 2);
+      } else { /* up to 4 of the z themselves (a z that is known zero is left out; none left: a zero row) */
+        uint32_t ns = 0;
+        for (int bit = 0; bit < bits; bit++)
+          if (m >> bit & 1) {
+            int t = bits * j + bit;
+            if (t < U) PUSHS(ns, SLOT_Z(t));
+          }
+        b_task(bd, RQB_T_XOR, slot, 0, lv, tmp, ns);
+      }
+    }
+  }
+  for (int p = 0; p < I; p++) {
+    const int col = v->pcol[p];
+    if (!needed[col]) continue;
+    const uint64_t *g = v->G + (size_t)p * uw;
+    const uint32_t slot = SLOT_ROW(v->prow[p]);
+    const uint32_t crow = req->want_c ? SM_G(v->row0[RQB_SP_C] + (uint32_t)col) : RQB_ROW_NONE;
+    int any = 0;
+    for (int j = 0; j < ngr; j++) {
+      gv[j] = (uint8_t)GROUP_VAL(g, j);
+      any |= gv[j];
+    }
+    if (!any) { /* x_p = Y_p */
+      if (req->want_c) {
+        uint32_t ns = 0;
+        PUSHS(ns, slot);
+        b_task(bd, RQB_T_XOR, crow, 0, lv + 2, tmp, ns);
+      }
+      continue;
+    }
+    if (!has[slot]) { /* Y_p is known zero: give the in-place gather a zero row to start from */
+      b_task(bd, RQB_T_XOR, slot, 0, lv, tmp, 0);
+      has[slot] = 1;
+    }
+    b_tab_ex(bd, slot, crow, bits, lv + 2, gv, (uint32_t)ngr);
+  }
+#undef GROUP_VAL
+  if (req->want_c)
+    for (int t = 0; t < U; t++) { /* the inactive symbols themselves */
+      uint32_t ns = 0;
+      PUSHS(ns, SLOT_Z(t));
+      b_task(bd, RQB_T_XOR, SM_G(v->row0[RQB_SP_C] + (uint32_t)v->ucol[t]), 0, lv + 2, tmp, ns);
+    }
+  lv += 3;
+
+  /* O: emitted symbols = LT combinations of the intermediate symbols, slots -> HBM.  Rows with
+   * more than 8 terms take scratch slots for partial sums; when those run out the next rows
+   * start two levels later and reuse them. */
+  bd->ws_next = SCR;
+  for (int k = 0; k < req->n_out; k++) {
+    uint32_t idx[RQB_MAX_LT_DEGREE];
+    int cnt = rqb_host_lt_indices(&v->P, req->out_isi[k], idx);
+    uint32_t ns = 0;
+    for (int q = 0; q < cnt; q++) {
+      const int col = (int)idx[q];
+      PUSHS(ns, v->col_state[col] == 1 ? SLOT_ROW(v->prow[v->col_pos[col]]) : SLOT_Z(v->col_t[col]));
+    }
+    if (ns > RQB_MAX_SRCS && bd->ws_next + 8u > v->slot_budget) {
+      lv += 2;
+      bd->ws_next = SCR;
+    }
+    b_tree(bd, RQB_T_XOR, SM_G(v->row0[RQB_SP_SYM] + (uint32_t)k), tmp, ns, lv);
+    if (bd->ws_next > peak) peak = bd->ws_next;
+  }
+  if (peak > v->slot_budget) return -8;
+  *n_slots_out = peak;
+  *tab_bits_out = (uint32_t)bits;
+  return sc->oom ? -7 : 0;
+#undef SLOT_ROW
+#undef SLOT_Z
+#undef ACC
+#undef YEND
+#undef PUSHS
+}
+
+/* NANORQ_B200_SMEM_MAXSLICE = 16 | 32 | 64: widest column slice of the shared-memory flavour
+ * (experiments); read once */
+static uint32_t g_smem_max_slice = 64;
+static pthread_once_t smem_once = PTHREAD_ONCE_INIT;
+static void smem_init(void) {
+  const char *e = getenv("NANORQ_B200_SMEM_MAXSLICE");
+  const int v = e ? atoi(e) : 0;
+  if (v == 16 || v == 32 || v == 64) g_smem_max_slice = (uint32_t)v;
+}
+/* arena rows below the working rows: [IN | SYM | C | ZERO] */
+static uint64_t row0_ws_rows(const rqb_plan_request *req, int L) {
+  return (uint64_t)req->in_rows + req->sym_rows + (uint64_t)L + 1u;
+}
+
 /* ---------------------------------------------------------------- planner */
 #define NONE_REF RQB_REF_NONE /* "this row is all zero / has no location" */
 
@@ -780,6 +1217,28 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   double t2 = now_s();
   FINE(5);
 
+  /* Flavour: when a CTA's shared memory can hold a column slice of every live row (the matrix
+   * rows, the inactive symbols and a scratch region for accumulators / XOR tables), the
+   * shared-memory program is emitted (rqb_program.h): the widest slice of 64, 32 or 16 bytes
+   * that fits.  Larger blocks get the HBM flavour. */
+  int smem = 0;
+  uint32_t slice = 0, slot_budget = 0;
+  if (req->smem_budget) {
+    pthread_once(&smem_once, smem_init);
+    const uint32_t fixed = 1u + (uint32_t)R + (uint32_t)U;
+    uint32_t min_scratch = 16u * (((uint32_t)U + 3u) / 4u);                 /* 4-bit tables */
+    const uint32_t scan_min = 8u * ((uint32_t)H + 1u) + (uint32_t)H * ((8u + (uint32_t)U + 8u) / 7u + 3u);
+    if (scan_min > min_scratch) min_scratch = scan_min;
+    if (min_scratch < 128u) min_scratch = 128u;
+    for (uint32_t w = g_smem_max_slice; w >= 16u; w >>= 1)
+      if ((uint64_t)(fixed + min_scratch) * w <= req->smem_budget && (uint64_t)row0_ws_rows(req, L) < RQB_REF_GLOBAL) {
+        smem = 1;
+        slice = w;
+        slot_budget = req->smem_budget / w;
+        break;
+      }
+  }
+
   /* ---- 3a. dependencies of the triangular solve, G = X^-1 U_top (bits), and the
    * schedule of each row: at most RQB_MAX_SRCS-1 terms besides the row itself;
    * longer rows get partial sums ("parts") placed at the earliest level their
@@ -798,6 +1257,14 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   /* one word per column instead of three arrays: >= 0 peeled at that position, < 0 inactive
    * with index ~value */
   int *cinfo = sc_buf(sc, SC_CINFO, sizeof(int) * (size_t)L, 0);
+  chains ch;
+  memset(&ch, 0, sizeof(ch));
+  if (smem) { /* in-place chains instead of parts: at most one group per term */
+    ch.first = sc_buf(sc, SC_CHFIRST, sizeof(int) * ((size_t)R + 2), 0);
+    ch.level = sc_buf(sc, SC_CHLEVEL, sizeof(int) * ((size_t)nnz + (size_t)R + 8), 0);
+    ch.ptr = sc_buf(sc, SC_CHPTR, sizeof(int) * ((size_t)nnz + (size_t)R + 9), 0);
+    ch.items = sc_buf(sc, SC_CHITEMS, sizeof(int) * ((size_t)nnz + 8), 0);
+  }
   OOM_CHECK();
   for (int c = 0; c < L; c++) cinfo[c] = col_state[c] == 1 ? col_pos[c] : ~col_t[c];
   {
@@ -821,6 +1288,12 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
           rd[cnt] = level[q];
           it[cnt++] = q;
         }
+      }
+      if (smem) {
+        ch.first[p] = ch.ng;
+        level[p] = chain_row(&ch, rd, it, cnt, r >= S + H && req->in_row[r - S - H] != RQB_ROW_NONE, maxlevel, sortbuf);
+        if (level[p] > maxlevel) maxlevel = level[p];
+        continue;
       }
       if (cnt <= CAPF) { /* the common case: one task, only the latest term matters */
         int mx = -1;
@@ -898,6 +1371,22 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       bit_flip(Tb + (size_t)m * nbw, m);
     }
     xptr[nb] = nx;
+  }
+  if (smem) { /* the residual rows accumulate in place as their terms become final, like the peeled ones */
+    int *it = sc_buf(sc, SC_TMP, sizeof(int) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
+    int *rd = it + ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64);
+    uint64_t *sortbuf = sc_buf(sc, SC_SORT, sizeof(uint64_t) * 2 * ((size_t)RQB_MAX_LT_DEGREE + (size_t)L + 64), 0);
+    OOM_CHECK();
+    for (int m = 0; m < nb; m++) {
+      const int r = lowrows[m], cnt = xptr[m + 1] - xptr[m];
+      for (int k = 0; k < cnt; k++) {
+        it[k] = xidx[xptr[m] + k];
+        rd[k] = level[it[k]];
+      }
+      ch.first[I + m] = ch.ng;
+      chain_row(&ch, rd, it, cnt, r >= S + H && req->in_row[r - S - H] != RQB_ROW_NONE, maxlevel, sortbuf);
+    }
+    ch.first[I + nb] = ch.ng;
   }
 
   FINE(1);
@@ -1034,10 +1523,31 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   const uint32_t zero_row = row0[RQB_SP_C] + (uint32_t)L;
   row0[RQB_SP_WS] = zero_row + 1;
   if (req->sym_rows < (uint32_t)req->n_out) return -1;
-  if ((uint64_t)row0[RQB_SP_WS] + (uint64_t)WS_FIXED + (uint64_t)nnz > RQB_MAX_ROWS) return -4;
   builder bd;
   memset(&bd, 0, sizeof(bd));
   bd.sc = sc;
+  uint32_t smem_slots = 0, smem_tab_bits = 0;
+  if (smem) {
+    plan_view v;
+    memset(&v, 0, sizeof(v));
+    v.req = req; v.P = P; v.oh = oh; v.R = R; v.n = n; v.nlt = nlt; v.I = I; v.U = U; v.uw = uw; v.nb = nb;
+    v.nbw = nbw; v.uq = uq; v.nfree = nfree; v.maxlevel = maxlevel;
+    v.rptr = rptr; v.cidx = cidx; v.col_pos = col_pos; v.col_t = col_t; v.prow = prow; v.pcol = pcol; v.ucol = ucol;
+    v.lowrows = lowrows; v.pivrow = pivrow; v.freecols = freecols; v.qrow_of_f = qrow_of_f;
+    v.col_state = col_state; v.hb1 = hb1; v.hb2 = hb2; v.Sh = Sh; v.TQ = TQ; v.G = G; v.Sb = Sb; v.Tb = Tb;
+    v.ch = &ch; v.slot_budget = slot_budget;
+    memcpy(v.row0, row0, sizeof(row0));
+    rc = emit_smem(&v, &bd, sc, &smem_slots, &smem_tab_bits);
+    if (rc == -8) { /* the estimate was too optimistic for this block: HBM flavour */
+      rqb_plan_request r2 = *req;
+      r2.smem_budget = 0;
+      return rqb_plan_build(&r2, out);
+    }
+    if (rc) return rc;
+    bd.ws_next = 0; /* no working rows in HBM */
+    goto emitted;
+  }
+  if ((uint64_t)row0[RQB_SP_WS] + (uint64_t)WS_FIXED + (uint64_t)nnz > RQB_MAX_ROWS) return -4;
   bd.ws_base = row0[RQB_SP_WS];
   bd.ws_next = WS_FIXED;
   uint32_t *loc = sc_buf(sc, SC_CURLOC, sizeof(uint32_t) * (size_t)WS_FIXED, 0);
@@ -1339,12 +1849,14 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
 #undef OOM_CHECK_UNUSED
   if ((uint64_t)row0[RQB_SP_WS] + bd.ws_next > RQB_MAX_ROWS) return -4;
 
+emitted:
   FINE(13);
   OOM_CHECK();
   rqb_plan *plan = plan_acquire();
   if (!plan) return -7;
   size_t tot_levels = 0;
-  rc = write_pages(&bd, plan, zero_row, &tot_levels, req->pages_buf, req->pages_buf_cap);
+  /* the shared-memory flavour pads its XOR lists with slot 0 */
+  rc = write_pages(&bd, plan, smem ? 0u : zero_row, &tot_levels, req->pages_buf, req->pages_buf_cap);
   if (rc) {
     rqb_plan_free(plan);
     return rc;
@@ -1361,6 +1873,10 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   plan->zero_row = zero_row;
   plan->n_c_rows = req->want_c ? (uint32_t)L : 0;
   plan->n_out = (uint32_t)req->n_out;
+  plan->smem = smem;
+  plan->slice_bytes = slice;
+  plan->n_slots = smem_slots;
+  plan->tab_bits = smem_tab_bits;
   plan->st.i = I;
   plan->st.u = U;
   plan->st.nb = nb;
@@ -1490,6 +2006,8 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
         plan->st.n_srcs = bd.tot_x;
         plan->st.n_gf_srcs = bd.tot_gf;
         plan->n_ws_rows = 0;
+        plan->smem = 0;
+        plan->slice_bytes = plan->n_slots = plan->tab_bits = 0;
         plan->n_rows = out_base + nrows;
         plan->zero_row = zero_row;
         *out = plan;

@@ -32,6 +32,9 @@ typedef struct {
   uint8_t *pages_buf;      /* optional: write the program here (e.g. pinned memory the DMA    */
   size_t pages_buf_cap;    /* engine reads) instead of the plan's own buffer; if it is too     */
                            /* small the plan's buffer is used (plan->pages tells which)        */
+  uint32_t smem_budget;    /* bytes of shared memory a CTA may use for row slots: > 0 asks for */
+                           /* the shared-memory flavour of the program (rqb_program.h) when    */
+                           /* the block's live rows fit, 0 for the HBM flavour                 */
 } rqb_plan_request;
 
 typedef struct {
@@ -58,6 +61,10 @@ typedef struct rqb_plan {
   size_t pages_cap;    /* bytes allocated behind own_pages                      */
   struct rqb_plan *next_free;
   uint32_t n_c_rows;   /* rows written to c_out (L or 0)                        */
+  int smem;            /* 1: shared-memory flavour (rows live in slots of slice_bytes)   */
+  uint32_t slice_bytes; /* smem flavour: column slice the slot budget was computed for   */
+  uint32_t n_slots;    /* smem flavour: slots a CTA needs (slot 0 = zeros)               */
+  uint32_t tab_bits;   /* smem flavour: inactive symbols per table group                 */
   uint32_t n_out;
   rqb_plan_stats st;
 } rqb_plan;

@@ -96,4 +96,35 @@ typedef struct {
 
 #define RQB_MAX_H 16u /* HDPC rows, RFC 6330 table 2: H <= 16 */
 
+/* ---------------------------------------------------------------------------
+ * The SHARED-MEMORY flavour of the program (rqb_solve_smem_kernel).
+ *
+ * For blocks whose rows fit, a CTA keeps its column slice (16, 32 or 64 bytes wide) of EVERY
+ * live row in shared memory ("slots") for the whole solve: the received symbols are read from
+ * HBM once (LOAD tasks), every row operation of the elimination runs in place on the slots,
+ * and only the results (intermediate symbols / emitted symbols) are written back -- DRAM
+ * traffic is the compulsory traffic.  Same page / level / task format; the differences:
+ *
+ *   row reference   bit 23 set   -> row (ref & 0x7FFFFF) of the block's HBM arena (IN, SYM, C);
+ *                   bit 23 clear -> shared-memory slot `ref`.  Slot 0 is all zero and never
+ *                   written (it pads XOR lists; level header zero_row = 0).
+ *   XOR / GF        as above over mixed references; a destination that accumulates lists
+ *                   itself as a source (rows are updated in place).
+ *   LOAD            slots dst .. dst+nsrc-1  =  arena rows pad .. pad+nsrc-1   (no list)
+ *   SCAN2           alpha-scan with the HDPC sums folded in (the y_j are never stored):
+ *                     y = alpha*y ^ row[ref(e_k)];  slot[dst + h1(e_k)] ^= y;  slot[dst + h2(e_k)] ^= y
+ *                   entry e = ref | h1 << 24 | h2 << 28 (the two HDPC rows that have a one in
+ *                   that column, lib/precode.c:68-81); the task first clears its H accumulator
+ *                   slots dst..dst+H-1 (H = aux & 31) and finally stores y to slot `pad`.
+ *                   aux bit 7: the last entry is the last column of the scan (no ones there).
+ *   TAB             in place: slot[dst] ^= XOR_j slot[tab_base + (j << bits) + v_j], v_j != 0;
+ *                   the list holds one byte v_j per group of `bits` = aux inactive symbols
+ *                   (4..8, whatever the slot budget allows); pad = arena reference that also
+ *                   receives the result (an encoder's row of the C space) or RQB_ROW_NONE.
+ */
+#define RQB_REF_GLOBAL 0x00800000u
+#define RQB_T_LOAD 4
+#define RQB_T_SCAN2 5
+#define RQB_SMEM_BUDGET_BYTES (227u * 1024u - 2u * RQB_PAGE_BYTES - 128u) /* slots of one CTA: 227 KB minus the page ring and its barriers */
+
 #endif

@@ -95,6 +95,19 @@ int rqb_lt_row_indices(int K, uint32_t isi, uint32_t *out) {
 }
 
 #define RQB_ARGS_BYTES 16384 /* room for 256 blocks in one batched launch */
+
+/* NANORQ_B200_FLAVOUR = hbm forces the HBM flavour of the solve program (experiments, tests);
+ * default: the shared-memory flavour whenever a block's rows fit (rqb_program.h) */
+static uint32_t g_smem_budget = RQB_SMEM_BUDGET_BYTES;
+static pthread_once_t g_flavour_once = PTHREAD_ONCE_INIT;
+static void flavour_init(void) {
+  const char *e = getenv("NANORQ_B200_FLAVOUR");
+  if (e && !strcmp(e, "hbm")) g_smem_budget = 0;
+}
+static uint32_t solver_smem_budget(void) {
+  pthread_once(&g_flavour_once, flavour_init);
+  return g_smem_budget;
+}
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 /* ------------------------------------------------------------ buffer pool
@@ -604,7 +617,10 @@ static void fill_stats(const rqb_plan *p, rqb_solver_stats *o) {
   o->t_peel = p->st.t_peel; o->t_dense = p->st.t_dense; o->t_emit = p->st.t_emit;
   o->n_ws_rows = p->n_ws_rows;
   o->n_parts = p->st.n_parts;
-  o->slice_bytes = RQB_SLICE_BYTES;
+  o->slice_bytes = p->smem ? (int)p->slice_bytes : (int)RQB_SLICE_BYTES;
+  o->smem = p->smem;
+  o->n_slots = p->n_slots;
+  o->tab_bits = p->tab_bits;
 }
 
 int rqb_solver_get_stats(const rqb_solver *s, rqb_solver_stats *out) {
@@ -660,6 +676,7 @@ static int solver_set_args(rqb_solver *s) {
   na.pitch = (uint32_t)s->pitch;
   na.n_pages = p->n_pages;
   na.width = (uint32_t)round_up(s->T, 16);
+  na.pad = p->smem ? p->n_slots : 0; /* shared-memory flavour: slots the CTA needs */
   if (!s->args_valid || memcmp(a, &na, sizeof(na))) { /* a recycled encoder context usually has them on the device already */
     *a = na;
     s->busy = 1;
@@ -698,6 +715,7 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
       if (w) return w;
     }
   }
+  pr.smem_budget = solver_smem_budget();
   pr.pages_buf = s->h_pages;
   pr.pages_buf_cap = s->h_pages_cap < s->d_pages_cap ? s->h_pages_cap : s->d_pages_cap;
   rqb_plan *p = NULL;
@@ -758,7 +776,8 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
         in_row[k] = k < s->K ? (uint32_t)k : RQB_ROW_NONE;
       }
       for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
-      rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0};
+      rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0,
+                             solver_smem_budget()};
       rc = rqb_plan_build(&pr, &p);
     }
     free(isi);
@@ -819,7 +838,10 @@ int rqb_solver_run(rqb_solver *s) {
   BIND(s->dev);
   s->busy = 1;
   if (s->want_timing) DEV(rqb_event_record(s->ev0, s->stream));
-  DEV(rqb_launch_solve(s->d_args, 1, s->h_args->width, s->stream));
+  if (s->plan->smem)
+    DEV(rqb_launch_solve_smem(s->d_args, 1, s->h_args->width, s->plan->slice_bytes, s->plan->n_slots, s->stream));
+  else
+    DEV(rqb_launch_solve(s->d_args, 1, s->h_args->width, s->stream));
   if (s->want_timing) DEV(rqb_event_record(s->ev1, s->stream));
   s->timed = s->want_timing;
   return 0;
@@ -849,22 +871,41 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   if (n <= 0 || !own) return RQB_E_ARG;
   BIND(own->dev);
   if ((size_t)(n + 1) * sizeof(rqb_solve_args) > RQB_ARGS_BYTES) return RQB_E_ARG;
-  /* entry 0 of the owner's buffer stays its own single-run argument block */
+  /* entry 0 of the owner's buffer stays its own single-run argument block.  The blocks are
+   * grouped by the flavour of their program (HBM, or shared memory with 16/32/64-byte slots):
+   * one launch per flavour present, normally one. */
   rqb_solve_args *h = own->h_args + 1, *d = own->d_args + 1;
+  int cls_n[4] = {0, 0, 0, 0}, cls_at[4];
+  uint32_t cls_slots[4] = {0, 0, 0, 0};
+#define FLAVOUR_CLASS(p) (!(p)->smem ? 0 : (p)->slice_bytes == 16 ? 1 : (p)->slice_bytes == 32 ? 2 : 3)
   for (int k = 0; k < n; k++) {
     if (!sv[k]->plan || sv[k]->T != own->T || sv[k]->dev != own->dev) return RQB_E_ARG;
+    cls_n[FLAVOUR_CLASS(sv[k]->plan)]++;
+  }
+  cls_at[0] = 0;
+  for (int c = 1; c < 4; c++) cls_at[c] = cls_at[c - 1] + cls_n[c - 1];
+  for (int k = 0; k < n; k++) {
     if (sv[k] != own && sv[k]->busy) {
       /* its uploads (symbols, program pages, arguments) are queued on its own stream: the launching
        * stream waits for them on the device, the host does not */
       DEV(rqb_event_record(sv[k]->ev_ready, sv[k]->stream));
       DEV(rqb_stream_wait_event(own->stream, sv[k]->ev_ready));
     }
-    h[k] = *sv[k]->h_args;
+    const int c = FLAVOUR_CLASS(sv[k]->plan);
+    h[cls_at[c]++] = *sv[k]->h_args;
+    if (sv[k]->plan->smem && sv[k]->plan->n_slots > cls_slots[c]) cls_slots[c] = sv[k]->plan->n_slots;
   }
+#undef FLAVOUR_CLASS
   own->busy = 1;
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
   if (own->want_timing) DEV(rqb_event_record(own->ev0, own->stream));
-  DEV(rqb_launch_solve(d, n, h[0].width, own->stream));
+  for (int c = 0, at = 0; c < 4; at += cls_n[c], c++) {
+    if (!cls_n[c]) continue;
+    if (c == 0)
+      DEV(rqb_launch_solve(d + at, cls_n[c], h[at].width, own->stream));
+    else
+      DEV(rqb_launch_solve_smem(d + at, cls_n[c], h[at].width, 8u << c, cls_slots[c], own->stream));
+  }
   if (own->want_timing) DEV(rqb_event_record(own->ev1, own->stream));
   own->timed = own->want_timing;
   /* whatever a member queues on its own stream from now on (fetches, emits, uploads of the next
@@ -948,7 +989,13 @@ int rqb_solver_fetch_c(rqb_solver *s, uint32_t first, uint32_t n, uint8_t *dst, 
 }
 
 /* ------------------------------------------------ host-only plan access */
+uint32_t rqb_smem_budget(void) { return RQB_SMEM_BUDGET_BYTES; }
+
 int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out) {
+  return rqb_plan_blob_build_ex(K, req, 0, out);
+}
+
+int rqb_plan_blob_build_ex(int K, const rqb_solve_request *req, uint32_t smem_budget, rqb_plan_blob *out) {
   rqb_params P;
   memset(out, 0, sizeof(*out));
   if (rqb_params_init(K, &P) || req->overhead < 0) return RQB_E_ARG;
@@ -956,11 +1003,15 @@ int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out)
   for (int k = 0; k < P.Kprime + req->overhead; k++)
     if (req->in_row[k] != RQB_NO_ROW && req->in_row[k] >= in_rows) in_rows = req->in_row[k] + 1;
   rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi,
-                         in_rows, req->n_out ? req->n_out : 1, NULL, 0};
+                         in_rows, req->n_out ? req->n_out : 1, NULL, 0, smem_budget};
   rqb_plan *p = NULL;
   int rc = rqb_plan_build(&pr, &p);
   if (rc == 1) return RQB_NEED_MORE;
   if (rc) return rc == -4 ? RQB_E_TOOBIG : RQB_E_ARG;
+  out->smem = p->smem;
+  out->slice_bytes = p->slice_bytes;
+  out->n_slots = p->n_slots;
+  out->tab_bits = p->tab_bits;
   out->n_ws_rows = p->n_ws_rows;
   memcpy(out->row0, p->row0, sizeof(out->row0));
   out->zero_row = p->zero_row;

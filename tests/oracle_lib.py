@@ -129,16 +129,18 @@ def interp_run(blob, inp, T, n_c, n_out, in_writable=False):
     if _interp is None:
         _interp = C.CDLL(INTERP_SO)
         sz = C.c_size_t
-        _interp.rqb_interp_run_ex.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz,
-                                              u8p, sz, sz, u8p, sz, sz, C.c_int]
+        _interp.rqb_interp_run2.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u8p, sz, sz, sz,
+                                            u8p, sz, sz, u8p, sz, sz, C.c_int, C.c_int, C.c_uint32]
     inp = np.ascontiguousarray(inp, dtype=np.uint8)
     row0 = np.asarray(blob["row0"], dtype=np.uint32)
     in_rows = min(inp.shape[0], int(row0[1]))  # rows past the plan's input space are never referenced
     cout = np.full((max(n_c, 1), T), 0x5A, np.uint8)
     sout = np.full((max(n_out, 1), T), 0x5A, np.uint8)
-    rc = _interp.rqb_interp_run_ex(ptr(row0, u32p), blob["zero_row"], blob["n_rows"], blob["n_pages"],
-                                   ptr(blob["pages"]), ptr(inp), in_rows, inp.strides[0], T, ptr(cout), n_c, T,
-                                   ptr(sout), n_out, T, 1 if in_writable else 0)
+    # both flavours of the program (rqb_program.h): blob["smem"] selects the shared-memory one
+    rc = _interp.rqb_interp_run2(ptr(row0, u32p), blob["zero_row"], blob["n_rows"], blob["n_pages"],
+                                 ptr(blob["pages"]), ptr(inp), in_rows, inp.strides[0], T, ptr(cout), n_c, T,
+                                 ptr(sout), n_out, T, 1 if in_writable else 0, int(blob.get("smem", 0)),
+                                 int(blob.get("n_slots", 0)))
     return rc, cout[:n_c], sout[:n_out]
 
 

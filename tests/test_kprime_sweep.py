@@ -58,9 +58,13 @@ def one_K(K, T, run_encode, run_decode):
     return 0
 
 
+SMEM = True  # ask for the shared-memory flavour: the planner falls back to the HBM one when the rows do not fit
+
+
 def interp_encode(K, T, src, out_isi, p):
-    rc, blob = nb.plan_blob(K, nb.SolveRequest.for_encoder(K, True, out_isi))
+    rc, blob = nb.plan_blob(K, nb.SolveRequest.for_encoder(K, True, out_isi), smem=SMEM)
     assert rc == 0
+    FLAVOURS[bool(blob["smem"])] = FLAVOURS.get(bool(blob["smem"]), 0) + 1
     rc, cout, sout = interp_run(blob, src, T, p.L, len(out_isi))
     assert rc == 0, (K, rc)
     return cout, sout
@@ -68,7 +72,7 @@ def interp_encode(K, T, src, out_isi, p):
 
 def interp_decode(K, T, esis, syms, p):
     req, missing = nb.SolveRequest.for_decoder(K, esis, want_c=False)
-    rc, blob = nb.plan_blob(K, req)
+    rc, blob = nb.plan_blob(K, req, smem=SMEM)
     if rc != 0:
         return rc, None
     rc, _, sout = interp_run(blob, syms, T, 0, len(missing))
@@ -76,14 +80,24 @@ def interp_decode(K, T, esis, syms, p):
     return 0, sout
 
 
+FLAVOURS = {}
+
+
 def test_every_kprime_on_the_interpreter():
+    global SMEM
     singular = 0
     vals = sweep_values()
     for Kp in vals:
+        SMEM = True
         singular += one_K(Kp, 8, interp_encode, interp_decode)
         if Kp <= 3000 or Kp == 56403:  # K'-1: one padding symbol, same K'
             singular += one_K(Kp - 1, 8, interp_encode, interp_decode)
-    print("%d K' values, %d singular decodes (verdicts agree)" % (len(vals), singular))
+        if Kp <= 3000:  # the HBM flavour as well where the shared-memory one is the default
+            SMEM = False
+            singular += one_K(Kp, 8, interp_encode, interp_decode)
+    print("%d K' values, %d singular decodes (verdicts agree); encode programs by flavour: %s" % (
+        len(vals), singular, {("smem" if k else "hbm"): v for k, v in FLAVOURS.items()}))
+    assert FLAVOURS.get(True, 0) > 100 and FLAVOURS.get(False, 0) > 50
 
 
 # ------------------------------------------------------------------ GPU subset

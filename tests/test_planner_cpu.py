@@ -51,15 +51,17 @@ def test_block_params_match_oracle(K):
         assert nb.lt_row_indices(K, x) == list(out[:n])
 
 
+@pytest.mark.parametrize("smem", [False, True], ids=["hbm", "smem"])
 @pytest.mark.parametrize("K,T", [(10, 64), (26, 16), (101, 24), (257, 8), (1024, 16), (4096, 8)])
-def test_encode_plan_on_interpreter_equals_oracle(K, T):
+def test_encode_plan_on_interpreter_equals_oracle(K, T, smem):
     p = orc_params(K)
     src = kat_payload(K * T).reshape(K, T)
     Cm, _, _ = orc_encode(K, T, src)
     out_isi = np.arange(K, K + 24, dtype=np.uint32) + (p.Kprime - K)
     req = nb.SolveRequest.for_encoder(K, True, out_isi)
-    rc, blob = nb.plan_blob(K, req)
+    rc, blob = nb.plan_blob(K, req, smem=smem)
     assert rc == 0
+    assert blob["smem"] == int(smem)  # every one of these blocks fits the shared-memory slots
     st = blob["stats"]
     assert st["i"] + st["u"] == p.L and st["rho"] + st["nfree"] == st["u"]
     rc, cout, sout = interp_run(blob, src, T, p.L, len(out_isi))
@@ -68,10 +70,11 @@ def test_encode_plan_on_interpreter_equals_oracle(K, T):
     assert np.array_equal(sout, np.stack([orc_lt(K, T, Cm, int(x)) for x in out_isi]))
 
 
+@pytest.mark.parametrize("smem", [False, True], ids=["hbm", "smem"])
 @pytest.mark.parametrize("K,T,loss,oh,trials", [(10, 8, 0.4, 0, 200), (26, 8, 0.5, 0, 80), (100, 16, 0.5, 0, 4),
                                                   (100, 16, 0.2, 12, 4), (257, 8, 0.3, 15, 3),
                                                   (1000, 16, 0.9, 1, 2), (1024, 32, 0.05, 2, 2), (4096, 8, 0.1, 0, 1)])
-def test_decode_plan_on_interpreter_equals_oracle_including_verdict(K, T, loss, oh, trials):
+def test_decode_plan_on_interpreter_equals_oracle_including_verdict(K, T, loss, oh, trials, smem):
     p = orc_params(K)
     singular = 0
     for seed in range(trials):
@@ -86,7 +89,7 @@ def test_decode_plan_on_interpreter_equals_oracle_including_verdict(K, T, loss, 
         req, missing = nb.SolveRequest.for_decoder(K, esis)
         if not missing:
             continue
-        rc_p, blob = nb.plan_blob(K, req)
+        rc_p, blob = nb.plan_blob(K, req, smem=smem)
         assert (rc_o == 0) == (rc_p == 0), (K, seed, rc_o, rc_p)
         if rc_o != 0:
             singular += 1
