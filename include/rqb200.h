@@ -72,6 +72,35 @@ int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32
 /* K_params selects K' (the reference uses block 0's parameters for every block of
  * an object, lib/nanorq.c:289,372, so a shorter block may be padded further) */
 int rqb_solver_create_ex(rqb_solver **out, int K, int K_params, size_t T, uint32_t max_in, uint32_t max_out);
+/* same, on CUDA device `dev` (independent source blocks shard over the GPUs of a box with no
+ * exchange between them; dev < 0 = the process-wide default of rqb_set_device) */
+int rqb_solver_create_on(rqb_solver **out, int dev, int K, int K_params, size_t T, uint32_t max_in,
+                         uint32_t max_out);
+int rqb_solver_device(const rqb_solver *s);
+/* which flavour of the solve program the planner is asked for (rqb_program.h): AUTO = the
+ * shared-memory flavour when the block's rows fit a CTA's shared memory (lowest latency for a
+ * block on its own: DRAM traffic is the compulsory traffic), HBM = always the HBM flavour
+ * (highest throughput when many blocks are launched together) */
+#define RQB_FLAVOUR_AUTO 0
+#define RQB_FLAVOUR_HBM 1
+void rqb_solver_set_flavour(rqb_solver *s, int flavour);
+/* copy n rows from CALLER memory (rows src_pitch apart, T bytes each) into input rows
+ * [first, first+n), asynchronously; plain DMA when the memory is page-locked
+ * (rqb_host_alloc / rqb_host_register), staged by the driver otherwise.  The caller's rows
+ * must stay valid until the next rqb_solver_sync (or any call that waits). */
+int rqb_solver_upload_rows(rqb_solver *s, uint32_t first, uint32_t n, const uint8_t *src, size_t src_pitch);
+/* copy rows [first, first+n) of a row space (0 = input, 1 = emitted symbols, 2 = intermediate
+ * symbols) into caller memory; wait != 0 waits for the copy */
+int rqb_solver_fetch_rows(rqb_solver *s, int space, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch,
+                          int wait);
+/* emitted-symbol row sym_row[k] = input row in_row[k], k < n, on the device (a decoder places the
+ * source symbols it received into the block image next to the recovered ones) */
+int rqb_solver_copy_in_to_sym(rqb_solver *s, const uint32_t *sym_row, const uint32_t *in_row, uint32_t n);
+/* page-locked host memory for symbol buffers: copies to and from it are DMA without a staging copy */
+void *rqb_host_alloc(size_t bytes);
+void rqb_host_release(void *p);
+int rqb_host_pin(void *p, size_t bytes);   /* page-lock memory the caller allocated */
+int rqb_host_unpin(void *p);
 /* destroy never blocks: the context (stream, events, pinned and device buffers) is parked
  * as it is -- work may still be queued on its stream -- for the next create of the same
  * shape, because CUDA object creation is too slow for blocks that come and go at wire rate;
@@ -101,6 +130,9 @@ typedef struct {
   int want_c;              /* keep the L intermediate symbols on the device              */
   uint32_t n_out;          /* symbols to emit with the solve                             */
   const uint32_t *out_isi; /* [n_out]                                                    */
+  const uint32_t *out_row; /* optional [n_out]: row of the emitted-symbol space symbol k */
+                           /* goes to (default k); lets a decoder recover straight into  */
+                           /* the block image it hands back with one copy                */
 } rqb_solve_request;
 
 /* analyse the block and stage the program on the device.  Returns RQB_NEED_MORE

@@ -10,6 +10,8 @@ from .api import (  # noqa: F401
     FileIO,
     Matrix,
     MemIO,
+    PinnedBuffer,
+    PinnedMemIO,
     Solver,
     SolveRequest,
     block_params,

@@ -31,7 +31,7 @@ class BlockParams(C.Structure):
 
 class _SolveRequest(C.Structure):
     _fields_ = [("overhead", C.c_int), ("isi", u32p), ("in_row", u32p), ("want_c", C.c_int),
-                ("n_out", C.c_uint32), ("out_isi", u32p)]
+                ("n_out", C.c_uint32), ("out_isi", u32p), ("out_row", u32p)]
 
 
 class SolverStats(C.Structure):
@@ -102,6 +102,11 @@ def lib():
     sig("nanorq_num_missing", sz, vp, C.c_uint8)
     sig("nanorq_num_repair", sz, vp, C.c_uint8)
     sig("nanorq_repair_block", C.c_bool, vp, vp, C.c_uint8)
+    # nanorq_batch.h
+    sig("ioctx_from_pinned_mem", vp, vp, sz, C.c_int)
+    sig("nanorq_encode_range", sz, vp, C.c_uint8, C.c_uint32, C.c_uint32, vp, sz, vp)
+    sig("nanorq_decoder_add_symbols", C.c_int, vp, u32p, vp, sz, sz, C.POINTER(C.c_int), vp)
+    sig("nanorq_set_devices", C.c_int, vp, C.c_int)
     # io.h
     sig("ioctx_from_file", vp, C.c_char_p, C.c_int)
     sig("ioctx_mmap_file", vp, C.c_char_p, C.c_int)
@@ -145,6 +150,16 @@ def lib():
     sig("rqb_batch_slice_bytes", C.c_int, C.c_int, sz)
     sig("rqb_solver_run_batch", C.c_int, C.POINTER(vp), C.c_int)
     sig("rqb_solver_run_batch_on", C.c_int, C.POINTER(vp), C.c_int, vp)
+    sig("rqb_solver_create_on", C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, sz, C.c_uint32, C.c_uint32)
+    sig("rqb_solver_device", C.c_int, vp)
+    sig("rqb_solver_set_flavour", None, vp, C.c_int)
+    sig("rqb_solver_upload_rows", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
+    sig("rqb_solver_fetch_rows", C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, vp, sz, C.c_int)
+    sig("rqb_solver_copy_in_to_sym", C.c_int, vp, u32p, u32p, C.c_uint32)
+    sig("rqb_host_alloc", vp, sz)
+    sig("rqb_host_release", None, vp)
+    sig("rqb_host_pin", C.c_int, vp, sz)
+    sig("rqb_host_unpin", C.c_int, vp)
     sig("rqb_plan_blob_build", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.POINTER(PlanBlob))
     sig("rqb_plan_blob_build_ex", C.c_int, C.c_int, C.POINTER(_SolveRequest), C.c_uint32, C.POINTER(PlanBlob))
     sig("rqb_smem_budget", C.c_uint32)
@@ -189,6 +204,10 @@ EXPORTED_SYMBOLS = [
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
     "rqb_schedule_replay_stepwise", "rqb_schedule_plan_blob",
     "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info", "rqb_plan_blob_build_ex", "rqb_smem_budget",
+    "ioctx_from_pinned_mem", "nanorq_encode_range", "nanorq_decoder_add_symbols", "nanorq_set_devices",
+    "rqb_solver_create_on", "rqb_solver_device", "rqb_solver_set_flavour", "rqb_solver_upload_rows",
+    "rqb_solver_fetch_rows", "rqb_solver_copy_in_to_sym", "rqb_host_alloc", "rqb_host_release", "rqb_host_pin",
+    "rqb_host_unpin",
 ]
 
 
@@ -280,13 +299,16 @@ def _u32(a):
 class SolveRequest:
     """rqb_solve_request: which LT rows exist, where their bytes are, what to emit."""
 
-    def __init__(self, isi, in_row, overhead=0, want_c=True, out_isi=()):
+    def __init__(self, isi, in_row, overhead=0, want_c=True, out_isi=(), out_row=None):
         self.isi = _u32(isi)
         self.in_row = _u32(in_row)
         self.out_isi = _u32(out_isi)
+        self.out_row = None if out_row is None else _u32(out_row)
         assert len(self.isi) == len(self.in_row)
+        assert self.out_row is None or len(self.out_row) == len(self.out_isi)
         self.c = _SolveRequest(int(overhead), self.isi.ctypes.data_as(u32p), self.in_row.ctypes.data_as(u32p),
-                               1 if want_c else 0, len(self.out_isi), self.out_isi.ctypes.data_as(u32p))
+                               1 if want_c else 0, len(self.out_isi), self.out_isi.ctypes.data_as(u32p),
+                               None if self.out_row is None else self.out_row.ctypes.data_as(u32p))
 
     @staticmethod
     def for_encoder(K, want_c=True, out_isi=()):
@@ -392,6 +414,40 @@ class MemIO:
         self.close()
 
 
+class PinnedBuffer:
+    """Page-locked host memory from rqb_host_alloc as a numpy uint8 array (`.arr`): symbol buffers
+    and payloads the GPU's copy engines reach without a staging copy."""
+
+    ptr = None
+
+    def __init__(self, nbytes):
+        self.ptr = lib().rqb_host_alloc(nbytes)
+        if not self.ptr:
+            raise RuntimeError("rqb_host_alloc failed: " + last_error())
+        self.arr = np.frombuffer((C.c_uint8 * nbytes).from_address(self.ptr), dtype=np.uint8)
+
+    def close(self):
+        if self.ptr:
+            self.arr = None
+            lib().rqb_host_release(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+class PinnedMemIO(MemIO):
+    """ioctx_from_pinned_mem (nanorq_batch.h) over a numpy uint8 array; already_pinned=False page-locks
+    it for the lifetime of the context."""
+
+    def __init__(self, arr, already_pinned=True):
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        self.arr = arr
+        self.ptr = lib().ioctx_from_pinned_mem(arr.ctypes.data, arr.size, 1 if already_pinned else 0)
+        if not self.ptr:
+            raise RuntimeError("ioctx_from_pinned_mem failed: " + last_error())
+
+
 class FileIO:
     """ioctx_from_file / ioctx_mmap_file (reference lib/io.c:54,338); mode 1 = read (encoder),
     0 = create (decoder)."""
@@ -475,6 +531,19 @@ class Encoder(_Codec):
         n = lib().nanorq_encode(self.h, out.ctypes.data, esi, sbn, io.ptr)
         return out if n == T else None
 
+    def encode_range(self, sbn, esi0, n, io, out=None):
+        """nanorq_encode_range: symbols esi0..esi0+n-1 as an (n, T) array (or into `out`, whose rows
+        may be wider than T)."""
+        T = self.symbol_size()
+        if out is None:
+            out = np.empty((n, T), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.shape[0] >= n and out.strides[1] == 1 and out.shape[1] >= T
+        got = lib().nanorq_encode_range(self.h, sbn, esi0, n, out.ctypes.data, out.strides[0], io.ptr)
+        return out[:n, :T] if got == n else None
+
+    def set_devices(self, n):
+        return lib().nanorq_set_devices(self.h, n)
+
 
 class Decoder(_Codec):
     def __init__(self, common, specific):
@@ -485,6 +554,20 @@ class Decoder(_Codec):
 
     def add_symbol(self, data, tag, io):
         return lib().nanorq_decoder_add_symbol(self.h, data.ctypes.data, tag, io.ptr)
+
+    def add_symbols(self, tags, data, io):
+        """nanorq_decoder_add_symbols: data is an (n, >=T) uint8 array (rows may be strided);
+        -> (number added or -1, per-symbol status list). `data` must stay alive until the blocks
+        it feeds are complete."""
+        tags = np.ascontiguousarray(tags, dtype=np.uint32)
+        assert data.dtype == np.uint8 and data.shape[0] >= len(tags) and data.strides[1] == 1
+        status = (C.c_int * max(1, len(tags)))()
+        rc = lib().nanorq_decoder_add_symbols(self.h, tags.ctypes.data_as(u32p), data.ctypes.data, data.strides[0],
+                                              len(tags), status, io.ptr)
+        return rc, list(status[:len(tags)])
+
+    def set_devices(self, n):
+        return lib().nanorq_set_devices(self.h, n)
 
     def num_missing(self, sbn):
         return lib().nanorq_num_missing(self.h, sbn)
@@ -504,14 +587,15 @@ class Solver:
     """rqb_solver: one source block resident on the GPU."""
     h = None
 
-    def __init__(self, K, T, max_in=None, max_out=1, K_params=None):
+    def __init__(self, K, T, max_in=None, max_out=1, K_params=None, device=-1, flavour="auto"):
         self.K, self.T = K, T
         self.max_in = int(max_in or K)
         self.max_out = int(max_out)
         h = vp()
-        _check(lib().rqb_solver_create_ex(C.byref(h), K, K_params or K, T, self.max_in, self.max_out),
+        _check(lib().rqb_solver_create_on(C.byref(h), device, K, K_params or K, T, self.max_in, self.max_out),
                "rqb_solver_create")
         self.h = h
+        lib().rqb_solver_set_flavour(h, 1 if flavour == "hbm" else 0)
         lib().rqb_solver_set_timing(h, 1)  # tests and tools read last_kernel_ms()
         self.pitch = lib().rqb_solver_pitch(h)
         buf = (C.c_uint8 * (self.max_in * self.pitch)).from_address(lib().rqb_solver_staging(h))

@@ -63,6 +63,15 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    # the same round trips through the batch calls of nanorq_batch.h (this library only)
+    rtb_src = os.path.join(ROOT, "bench", "rq_roundtrip_batch.c")
+    rtb_out = os.path.join(HERE, "librq_roundtrip_batch.so")
+    if os.path.exists(rtb_src) and (force or _stale(rtb_out, [rtb_src, OUT] + hdrs)):
+        cmd = [CC, "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-pthread", "-o", rtb_out, rtb_src,
+               "-I" + os.path.join(ROOT, "include"), "-L" + HERE, "-lnanorq_b200", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
     return OUT
 
 

@@ -4,6 +4,7 @@
  * (cited per function); all symbol arithmetic happens on the device.
  */
 #include "nanorq.h"
+#include "nanorq_batch.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -35,13 +36,22 @@ struct block {
   uint32_t *mask;
   size_t mask_words;
   size_t gaps;
-  uint32_t *rep_esi;
+  uint32_t *src_row;           /* [K] input row holding source symbol esi (valid where the mask is set) */
+  uint32_t *rep_esi, *rep_row; /* repair symbols in arrival order: ESI and input row */
   size_t nrep, rep_cap;
   uint32_t in_cap;
+  uint32_t landed;               /* input rows handed out so far (arrival order) */
+  uint32_t staged_lo, staged_hi; /* staging rows written by per-symbol calls, not yet queued for upload */
+  bool out_decided, written;     /* output mode chosen / deferred block image already written */
+  uint8_t *out_mem;              /* deferred output: the block's bytes inside a page-locked memory ioctx */
+  size_t out_bytes;
   /* encoder: window of repair symbols already produced on the device */
   uint32_t win_first, win_n, win_cap;
   bool win_pending; /* the window's copy to the host is queued but not waited for */
+  bool win_on_host; /* the pinned mirror holds the current window */
   uint32_t loaded_rows; /* staging rows already queued for upload */
+  const uint8_t *src_mem; /* encoder loaded by DMA from a page-locked memory ioctx: the block's bytes there */
+  size_t src_bytes;
 };
 
 struct nanorq {
@@ -49,6 +59,7 @@ struct nanorq {
   struct part src_part, sub_part;
   rqb_block_params P;
   uint32_t max_esi;
+  int n_dev; /* devices the blocks are spread over (nanorq_set_devices); 0/1 = the default device */
   struct block *blocks[Z_MAX];
 };
 
@@ -202,7 +213,32 @@ static void block_free(struct block *b) {
   rqb_solver_destroy(b->sv);
   free(b->mask);
   free(b->rep_esi);
+  free(b->rep_row);
+  free(b->src_row);
   free(b);
+}
+
+/* first symbol of block sbn in the object, in symbols (get_source_block :97-112) */
+static size_t block_first_symbol(nanorq *rq, uint8_t sbn) {
+  if (sbn < rq->src_part.JL) return (size_t)sbn * rq->src_part.IL;
+  return rq->src_part.IL * rq->src_part.JL + ((size_t)sbn - rq->src_part.JL) * rq->src_part.IS;
+}
+
+/* the block's span inside a memory ioctx this library made (ioctx_from_mem / _from_pinned_mem):
+ * *bytes = payload bytes of the block present in the object (the object's last symbol may be
+ * short); returns the address of the block's first byte or NULL */
+int rqb_ioctx_mem_view(struct ioctx *io, uint8_t **base, size_t *len, int *pinned);
+static uint8_t *block_span(nanorq *rq, uint8_t sbn, const struct block *b, struct ioctx *io, size_t *bytes,
+                           int *pinned) {
+  uint8_t *base = NULL;
+  size_t len = 0;
+  if (!rqb_ioctx_mem_view(io, &base, &len, pinned)) return NULL;
+  const size_t off = block_first_symbol(rq, sbn) * rq->T;
+  if (off >= rq->F || rq->F > len) return NULL;
+  size_t n = (size_t)b->K * rq->T;
+  if (off + n > rq->F) n = rq->F - off;
+  *bytes = n;
+  return base + off;
 }
 
 static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :130-146 */
@@ -213,14 +249,15 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   if (!b) return NULL;
   b->K = (uint16_t)K;
   uint32_t max_in, max_out;
-  if (rq->max_esi) { /* decoder: source slots + every repair ESI that may arrive */
+  if (rq->max_esi) { /* decoder: every symbol that may arrive lands in its own input row */
     uint32_t spare = rq->max_esi >= K ? rq->max_esi - (uint32_t)K + 1 : 1;
     max_in = (uint32_t)rq->P.Kprime + spare;
     max_out = (uint32_t)K;
     b->mask_words = rq->max_esi / 32 + 2;
     b->mask = calloc(b->mask_words, sizeof(uint32_t));
-    if (!b->mask) {
-      free(b);
+    b->src_row = malloc(sizeof(uint32_t) * K);
+    if (!b->mask || !b->src_row) {
+      block_free(b);
       return NULL;
     }
     b->gaps = K;
@@ -230,7 +267,10 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
     max_out = b->win_cap;
   }
   b->in_cap = max_in;
-  if (rqb_solver_create_ex(&b->sv, (int)K, rq->P.Kprime, rq->T, max_in, max_out) != 0) {
+  /* independent source blocks shard over the devices of the box, block sbn on device sbn mod n
+   * (SURVEY 8(e)); one device unless nanorq_set_devices asked for more */
+  const int dev = rq->n_dev > 1 ? (int)(sbn % (unsigned)rq->n_dev) : -1;
+  if (rqb_solver_create_on(&b->sv, dev, (int)K, rq->P.Kprime, rq->T, max_in, max_out) != 0) {
     block_free(b);
     return NULL;
   }
@@ -239,12 +279,41 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   return b;
 }
 
+int nanorq_set_devices(nanorq *rq, int n) {
+  const int have = rqb_device_count();
+  if (!rq || have <= 0) return 0;
+  if (n <= 0 || n > have) n = have;
+  rq->n_dev = n;
+  return n;
+}
 
+/* ------------------------------------------------------------------ encoder */
 static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
+  b->loaded_rows = 0;
+  int pinned = 0;
+  size_t bytes = 0;
+  uint8_t *span = block_span(rq, sbn, b, io, &bytes, &pinned);
+  if (span && pinned) {
+    /* page-locked caller memory: the copy engine reads the block where it lies (no staging copy);
+     * only a short last symbol goes through a zero-padded staging row */
+    const uint32_t full = (uint32_t)(bytes / rq->T);
+    if (rqb_solver_upload_rows(b->sv, 0, full, span, rq->T)) return false;
+    if (full < b->K) {
+      uint8_t *row = rqb_solver_staging(b->sv) + (size_t)full * b->pitch;
+      memcpy(row, span + (size_t)full * rq->T, bytes - (size_t)full * rq->T);
+      memset(row + (bytes - (size_t)full * rq->T), 0, rq->T - (bytes - (size_t)full * rq->T));
+      for (uint32_t r = full + 1; r < b->K; r++) memset(rqb_solver_staging(b->sv) + (size_t)r * b->pitch, 0, rq->T);
+      if (rqb_solver_upload(b->sv, full, b->K - full)) return false;
+    }
+    b->src_mem = span;
+    b->src_bytes = bytes;
+    b->loaded_rows = b->K;
+    return true;
+  }
   /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging
    * rows; the rows start moving to the GPU while the rest is still being read */
   uint8_t *st = rqb_solver_staging(b->sv);
-  b->loaded_rows = 0;
+  b->src_mem = NULL;
   for (uint32_t esi = 0; esi < b->K; esi++) {
     uint8_t *row = st + (size_t)esi * b->pitch;
     size_t got = transfer_symbol(rq, sbn, esi, row, io, 0);
@@ -288,6 +357,35 @@ bool nanorq_precalculate(nanorq *rq) { /* :393-401 */
   return rqb_solver_plan_encode(b->sv, 1, b->win_cap) == 0;
 }
 
+/* source symbol esi as the block was loaded (zero-padded past the end of the object) */
+static void copy_source_symbol(nanorq *rq, const struct block *b, uint32_t esi, uint8_t *dst) {
+  if (!b->src_mem) {
+    memcpy(dst, rqb_solver_staging(b->sv) + (size_t)esi * b->pitch, rq->T);
+    return;
+  }
+  const size_t off = (size_t)esi * rq->T;
+  const size_t have = off >= b->src_bytes ? 0 : (b->src_bytes - off < rq->T ? b->src_bytes - off : rq->T);
+  memcpy(dst, b->src_mem + off, have);
+  if (have < rq->T) memset(dst + have, 0, rq->T - have);
+}
+
+/* produce repair symbols esi .. esi+n-1 (n <= win_cap) on the device in one LT launch; they stay
+ * in the emitted-symbol rows 0..n-1 */
+static bool emit_window(nanorq *rq, struct block *b, uint32_t esi, uint32_t n) {
+  const uint32_t pad = (uint32_t)rq->P.Kprime - b->K;
+  uint32_t *isi = malloc(sizeof(uint32_t) * n);
+  if (!isi) return false;
+  for (uint32_t k = 0; k < n; k++) isi[k] = esi + k + pad; /* ISI = ESI + (K'-K) :429 */
+  int rc = rqb_solver_emit(b->sv, isi, n);
+  free(isi);
+  if (rc) return false;
+  b->win_first = esi;
+  b->win_n = n;
+  b->win_on_host = false;
+  b->win_pending = false; /* the mirror copy queued by generate_symbols belongs to a window that is gone */
+  return true;
+}
+
 size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct ioctx *io) { /* :403-435 */
   struct block *b = get_block(rq, sbn);
   if (!b) return 0;
@@ -297,7 +395,7 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
     if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
     if (!b->loaded) return 0;
     PF_T0;
-    memcpy(data, rqb_solver_staging(b->sv) + (size_t)esi * b->pitch, rq->T);
+    copy_source_symbol(rq, b, esi, data);
     PF(RQB_PF_EMIT_SRC);
     return rq->T;
   }
@@ -307,24 +405,58 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
   if (b->win_pending) { /* the solve and the copy of the first window were queued by generate_symbols */
     if (rqb_solver_sync(b->sv)) return 0;
     b->win_pending = false;
+    b->win_on_host = true;
     PF(RQB_PF_GEN_SYNC);
   }
   if (!(b->win_n && esi >= b->win_first && esi < b->win_first + b->win_n)) {
-    /* produce the next window of repair symbols on the device in one LT launch */
-    uint32_t n = b->win_cap, pad = (uint32_t)rq->P.Kprime - b->K;
+    uint32_t n = b->win_cap;
     if ((uint64_t)esi + n > (1u << 24)) n = (1u << 24) - esi;
-    uint32_t *isi = malloc(sizeof(uint32_t) * n);
-    if (!isi) return 0;
-    for (uint32_t k = 0; k < n; k++) isi[k] = esi + k + pad; /* ISI = ESI + (K'-K) :429 */
-    int rc = rqb_solver_emit(b->sv, isi, n);
-    free(isi);
-    if (rc || rqb_solver_fetch_syms(b->sv, 0, n, NULL, 0)) return 0;
-    b->win_first = esi;
-    b->win_n = n;
+    if (!emit_window(rq, b, esi, n)) return 0;
+  }
+  if (!b->win_on_host) { /* bring the window to the pinned mirror once; per-symbol calls are views of it */
+    if (rqb_solver_fetch_syms(b->sv, 0, b->win_n, NULL, 0)) return 0;
+    b->win_on_host = true;
   }
   memcpy(data, rqb_solver_sym_mirror(b->sv) + (size_t)(esi - b->win_first) * b->pitch, rq->T);
   PF(RQB_PF_EMIT_WINDOW);
   return rq->T;
+}
+
+size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, void *dst, size_t pitch,
+                           struct ioctx *io) {
+  struct block *b = rq ? get_block(rq, sbn) : NULL;
+  if (!b || b->mask || !dst || pitch < rq->T || n == 0 || (uint64_t)esi0 + n > (1u << 24)) return 0;
+  if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  uint8_t *out = dst;
+  uint32_t esi = esi0, left = n;
+  /* source symbols: straight from the device's input rows into the caller's rows (DMA when the
+   * destination is page-locked) -- the host never touches the bytes */
+  if (esi < b->K) {
+    const uint32_t m = b->K - esi < left ? b->K - esi : left;
+    if (rqb_solver_fetch_rows(b->sv, 0, esi, m, out, pitch, 0)) return 0;
+    out += (size_t)m * pitch;
+    esi += m;
+    left -= m;
+  }
+  /* repair symbols: whatever part of the range the current device window holds is copied from
+   * there, the rest is produced window by window (one LT launch each) */
+  while (left) {
+    if (!(b->win_n && esi >= b->win_first && esi < b->win_first + b->win_n)) {
+      uint32_t w = left < b->win_cap ? left : b->win_cap;
+      if (!emit_window(rq, b, esi, w)) return 0; /* queued behind whatever still reads the old window's rows */
+    }
+    const uint32_t avail = b->win_first + b->win_n - esi, m = avail < left ? avail : left;
+    if (rqb_solver_fetch_rows(b->sv, 1, esi - b->win_first, m, out, pitch, 0)) return 0;
+    out += (size_t)m * pitch;
+    esi += m;
+    left -= m;
+  }
+  if (rqb_solver_sync(b->sv)) return 0;
+  if (b->win_pending) {
+    b->win_pending = false;
+    b->win_on_host = true;
+  }
+  return n;
 }
 
 void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn) { /* :437-451 */
@@ -336,11 +468,13 @@ void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn) { /* :437-451 */
 void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
   struct block *b = rq->blocks[sbn];
   if (!b) return;
-  if (b->win_pending) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
-  b->loaded = b->inverted = b->win_pending = false;
+  if (b->win_pending || b->src_mem) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
+  b->loaded = b->inverted = b->win_pending = b->win_on_host = false;
   b->win_n = 0;
   b->loaded_rows = 0;
+  b->src_mem = NULL;
   b->nrep = 0;
+  b->landed = b->staged_lo = b->staged_hi = 0;
   if (b->mask) {
     memset(b->mask, 0, b->mask_words * sizeof(uint32_t));
     b->gaps = b->K;
@@ -356,8 +490,71 @@ void nanorq_free(nanorq *rq) { /* :298-307 (NULL-safe here) */
   PF(RQB_PF_FREE);
 }
 
+/* ------------------------------------------------------------------ decoder
+ * Every symbol a block accepts lands in its own input row, in arrival order (src_row[esi] /
+ * rep_row[k] remember where): a whole batch of symbols is then ONE copy into consecutive rows,
+ * straight from the caller's memory when it comes through nanorq_decoder_add_symbols, through
+ * the pinned staging rows when it comes one symbol at a time. */
 static inline bool mask_get(const struct block *b, uint32_t id) { return (b->mask[id / 32] >> (id % 32)) & 1; }
 static inline void mask_set(struct block *b, uint32_t id) { b->mask[id / 32] |= 1u << (id % 32); }
+
+/* staging rows [staged_lo, staged_hi) hold symbols not yet queued for upload */
+static bool flush_staged(struct block *b) {
+  if (b->staged_hi > b->staged_lo && rqb_solver_upload(b->sv, b->staged_lo, b->staged_hi - b->staged_lo)) return false;
+  b->staged_lo = b->staged_hi = b->landed;
+  return true;
+}
+
+static bool grow_rep(struct block *b) {
+  if (b->nrep < b->rep_cap) return true;
+  size_t cap = b->rep_cap ? b->rep_cap * 2 : 256;
+  uint32_t *e = realloc(b->rep_esi, cap * sizeof(uint32_t));
+  if (e) b->rep_esi = e;
+  uint32_t *r = realloc(b->rep_row, cap * sizeof(uint32_t));
+  if (r) b->rep_row = r;
+  if (!e || !r) return false; /* what was collected so far stays valid */
+  b->rep_cap = cap;
+  return true;
+}
+
+/* bookkeeping of one accepted symbol that sits in input row `row` (:478-509 without the copies) */
+static int note_symbol(struct block *b, uint32_t esi, uint32_t row) {
+  if (esi < b->K) {
+    b->src_row[esi] = row;
+    b->gaps--;
+  } else {
+    if (!grow_rep(b)) return NANORQ_SYM_ERR;
+    b->rep_esi[b->nrep] = esi;
+    b->rep_row[b->nrep++] = row;
+  }
+  mask_set(b, esi);
+  return NANORQ_SYM_ADDED;
+}
+
+/* classification shared by the per-symbol and the batch call; SYM_ADDED = "would be added" */
+static int classify(nanorq *rq, const struct block *b, uint32_t esi) {
+  if (!b || !b->mask || esi > rq->max_esi || esi / 32 >= b->mask_words) return NANORQ_SYM_ERR;
+  if (b->gaps == 0) return NANORQ_SYM_IGN;
+  if (mask_get(b, esi)) return NANORQ_SYM_DUP;
+  if (b->landed >= b->in_cap) return NANORQ_SYM_ERR;
+  return NANORQ_SYM_ADDED;
+}
+
+static bool complete_block(nanorq *rq, struct ioctx *io, uint8_t sbn, struct block *b);
+
+/* is the output a page-locked memory ioctx, so that a block is handed back as one DMA? */
+static bool deferred_output(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
+  if (b->out_decided) return b->out_mem != NULL;
+  int pinned = 0;
+  size_t bytes = 0;
+  uint8_t *span = block_span(rq, sbn, b, io, &bytes, &pinned);
+  b->out_decided = true;
+  if (span && pinned) {
+    b->out_mem = span;
+    b->out_bytes = bytes;
+  }
+  return b->out_mem != NULL;
+}
 
 int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx *io) { /* :478-509 */
   uint8_t sbn = (tag >> 24) & 0xff;
@@ -365,32 +562,77 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
   PF_T0;
   struct block *b = get_block(rq, sbn);
   PF(RQB_PF_ADD_CREATE);
-  if (!b || !b->mask || esi > rq->max_esi || esi / 32 >= b->mask_words) return NANORQ_SYM_ERR;
-  if (b->gaps == 0) return NANORQ_SYM_IGN;
-  if (mask_get(b, esi)) return NANORQ_SYM_DUP;
-  uint8_t *st = rqb_solver_staging(b->sv);
-  if (esi < b->K) {
-    rqb_copy_stream(st + (size_t)esi * b->pitch, data, rq->T);
-    PF(RQB_PF_ADD_COPY);
-    transfer_symbol(rq, sbn, esi, data, io, 1); /* source symbols go straight to the output */
-    PF(RQB_PF_ADD_WRITE);
-    if (--b->gaps == 0) rqb_copy_fence(); /* the block's output is complete: publish the streamed rows */
-  } else {
-    uint32_t row = (uint32_t)rq->P.Kprime + (uint32_t)b->nrep;
-    if (row >= b->in_cap) return NANORQ_SYM_ERR;
-    if (b->nrep == b->rep_cap) {
-      size_t cap = b->rep_cap ? b->rep_cap * 2 : 256;
-      uint32_t *grown = realloc(b->rep_esi, cap * sizeof(uint32_t));
-      if (!grown) return NANORQ_SYM_ERR; /* the list collected so far stays valid */
-      b->rep_esi = grown;
-      b->rep_cap = cap;
-    }
-    rqb_copy_stream(st + (size_t)row * b->pitch, data, rq->T); /* arrival order, like repair_bin */
-    PF(RQB_PF_ADD_COPY);
-    b->rep_esi[b->nrep++] = esi;
+  int st = classify(rq, b, esi);
+  if (st != NANORQ_SYM_ADDED) return st;
+  const uint32_t row = b->landed;
+  rqb_copy_stream(rqb_solver_staging(b->sv) + (size_t)row * b->pitch, data, rq->T);
+  PF(RQB_PF_ADD_COPY);
+  if (b->staged_hi != row) { /* rows of a batch call lie in between: start a new pending range */
+    if (!flush_staged(b)) return NANORQ_SYM_ERR;
   }
-  mask_set(b, esi);
+  st = note_symbol(b, esi, row);
+  if (st != NANORQ_SYM_ADDED) return st;
+  b->landed = b->staged_hi = row + 1;
+  if (esi < b->K) {
+    if (!deferred_output(rq, sbn, b, io)) {
+      transfer_symbol(rq, sbn, esi, data, io, 1); /* source symbols go straight to the output */
+      PF(RQB_PF_ADD_WRITE);
+      if (b->gaps == 0) rqb_copy_fence(); /* the block's output is complete: publish the streamed rows */
+    } else if (b->gaps == 0 && !complete_block(rq, io, sbn, b)) {
+      return NANORQ_SYM_ERR;
+    }
+  }
   return NANORQ_SYM_ADDED;
+}
+
+int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *data, size_t pitch, size_t n,
+                               int *status, struct ioctx *io) {
+  if (!rq || !tags || !data || pitch < rq->T) return -1;
+  const uint8_t *rows = data;
+  int added = 0, err = 0;
+  size_t k = 0;
+  while (k < n) {
+    /* a run of symbols of one block: all of them are copied into consecutive input rows with
+     * ONE copy from the caller's memory; the ones the block does not accept (duplicates,
+     * symbols after completion) simply leave their row unused */
+    const uint8_t sbn = (tags[k] >> 24) & 0xff;
+    size_t run = 1;
+    while (k + run < n && ((tags[k + run] >> 24) & 0xff) == sbn) run++;
+    struct block *b = get_block(rq, sbn);
+    size_t take = run;
+    if (b && b->mask && b->landed + take > b->in_cap) take = b->in_cap - b->landed; /* never more rows than the block has */
+    bool copied = false;
+    const uint32_t row0 = b ? b->landed : 0;
+    for (size_t q = 0; q < run; q++) {
+      const uint32_t esi = tags[k + q] & 0x00ffffff;
+      int st = q < take ? classify(rq, b, esi) : NANORQ_SYM_ERR;
+      if (st == NANORQ_SYM_ADDED) {
+        if (!copied) { /* first accepted symbol of the run: queue the copy of the run's rows */
+          if (!flush_staged(b) || rqb_solver_upload_rows(b->sv, row0, (uint32_t)take, rows + k * pitch, pitch)) {
+            st = NANORQ_SYM_ERR;
+          } else {
+            copied = true;
+            b->landed = b->staged_lo = b->staged_hi = row0 + (uint32_t)take;
+          }
+        }
+        if (st == NANORQ_SYM_ADDED) st = note_symbol(b, esi, row0 + (uint32_t)q);
+        if (st == NANORQ_SYM_ADDED && esi < b->K && !deferred_output(rq, sbn, b, io))
+          transfer_symbol(rq, sbn, esi, (uint8_t *)(uintptr_t)(rows + (k + q) * pitch), io, 1);
+      }
+      if (status) status[k + q] = st;
+      added += st == NANORQ_SYM_ADDED;
+      err |= st == NANORQ_SYM_ERR;
+    }
+    if (b && b->mask && b->gaps == 0 && copied) {
+      if (b->out_mem) {
+        if (!complete_block(rq, io, sbn, b)) err = 1;
+      } else {
+        rqb_copy_fence();
+      }
+    }
+    k += run;
+  }
+  return err ? -1 : added;
 }
 
 size_t nanorq_num_missing(nanorq *rq, uint8_t sbn) { /* :511-517 */
@@ -403,28 +645,62 @@ size_t nanorq_num_repair(nanorq *rq, uint8_t sbn) { /* :519-525 */
   return b ? b->nrep : 0;
 }
 
+/* deferred output: received source symbols are placed next to the recovered ones in the block
+ * image on the device (emitted-symbol row = ESI) and the image goes to the caller's page-locked
+ * memory with one copy */
+static bool write_block_image(nanorq *rq, struct block *b, const uint32_t *have_esi, const uint32_t *have_row,
+                              uint32_t n_have) {
+  if (rqb_solver_copy_in_to_sym(b->sv, have_esi, have_row, n_have)) return false;
+  const uint32_t full = (uint32_t)(b->out_bytes / rq->T);
+  if (full && rqb_solver_fetch_rows(b->sv, 1, 0, full, b->out_mem, rq->T, 0)) return false;
+  if (full < b->K && b->out_bytes > (size_t)full * rq->T) { /* the object's short last symbol */
+    if (rqb_solver_fetch_syms(b->sv, full, 1, NULL, 0)) return false;
+    memcpy(b->out_mem + (size_t)full * rq->T, rqb_solver_sym_mirror(b->sv) + (size_t)full * b->pitch,
+           b->out_bytes - (size_t)full * rq->T);
+  }
+  return rqb_solver_sync(b->sv) == 0;
+}
+
+/* every source symbol has arrived and the output is deferred: hand the block back */
+static bool complete_block(nanorq *rq, struct ioctx *io, uint8_t sbn, struct block *b) {
+  (void)io;
+  (void)sbn;
+  if (b->written) return true;
+  if (!flush_staged(b)) return false;
+  uint32_t *esi = malloc(sizeof(uint32_t) * b->K);
+  if (!esi) return false;
+  for (uint32_t e = 0; e < b->K; e++) esi[e] = e;
+  bool ok = write_block_image(rq, b, esi, b->src_row, b->K);
+  free(esi);
+  b->written = ok;
+  return ok;
+}
+
 bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-631 */
   struct block *b = get_block(rq, sbn);
   if (!b || !b->mask) return false;
-  if (b->gaps == 0) return true;
+  if (b->gaps == 0) return !b->out_mem || complete_block(rq, io, sbn, b);
   if (b->nrep < b->gaps) return false;
   const int Kp = rq->P.Kprime;
   const size_t gaps = b->gaps, overhead = b->nrep - gaps;
   const uint32_t pad = (uint32_t)Kp - b->K;
+  const bool deferred = deferred_output(rq, sbn, b, io);
   /* the symbol bytes start moving to the GPU while the host analyses the matrix */
   PF_T0;
-  if (rqb_solver_upload(b->sv, 0, (uint32_t)Kp + (uint32_t)b->nrep)) return false;
+  if (!flush_staged(b)) return false;
   PF(RQB_PF_REP_UPLOAD);
   size_t nlt = (size_t)Kp + overhead;
   uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);
   uint32_t *missing = malloc(sizeof(uint32_t) * gaps);
-  if (!isi || !in_row || !missing) {
+  uint32_t *have = deferred ? malloc(sizeof(uint32_t) * 2 * b->K) : NULL;
+  if (!isi || !in_row || !missing || (deferred && !have)) {
     free(isi);
     free(in_row);
     free(missing);
+    free(have);
     return false;
   }
-  size_t rep = 0, nm = 0;
+  size_t rep = 0, nm = 0, nh = 0;
   /* fill_symbol_matrix_gaps + patch_precode_matrix (:527-565): missing source rows take
    * the repair symbols in arrival order, the rest become overhead rows */
   for (uint32_t e = 0; e < (uint32_t)Kp; e++) {
@@ -433,19 +709,24 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
       in_row[e] = RQB_NO_ROW;
     } else if (mask_get(b, e)) {
       isi[e] = e;
-      in_row[e] = e;
+      in_row[e] = b->src_row[e];
+      if (have) {
+        have[nh] = e;
+        have[b->K + nh++] = b->src_row[e];
+      }
     } else {
       isi[e] = b->rep_esi[rep] + pad;
-      in_row[e] = (uint32_t)Kp + (uint32_t)rep;
+      in_row[e] = b->rep_row[rep];
       rep++;
       missing[nm++] = e;
     }
   }
   for (size_t x = 0; x < overhead; x++, rep++) {
     isi[Kp + x] = b->rep_esi[rep] + pad;
-    in_row[Kp + x] = (uint32_t)Kp + (uint32_t)rep;
+    in_row[Kp + x] = b->rep_row[rep];
   }
-  rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing};
+  /* deferred output: the recovered symbol of ESI e is written to emitted-symbol row e */
+  rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing, deferred ? missing : NULL};
   PF(RQB_PF_REP_REQUEST);
   int rc = rqb_solver_plan(b->sv, &req); /* charges repair.plan / .pages / .args itself */
   free(isi);
@@ -454,22 +735,32 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
   if (rqb_prof_enabled()) pf_t = rqb_prof_now();
   if (rc == 0) rc = rqb_solver_run(b->sv);
   PF(RQB_PF_REP_RUN);
-  if (rc == 0) rc = rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0);
-  PF(RQB_PF_REP_FETCH);
-  if (rc == 0) {
-    /* decode_repair_rows + write_repair_rows (:567-589) */
-    const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
-    for (size_t k = 0; k < nm; k++) {
-      transfer_symbol(rq, sbn, missing[k], (uint8_t *)sy + k * b->pitch, io, 1);
-      mask_set(b, missing[k]);
+  if (rc == 0 && deferred) {
+    ok = write_block_image(rq, b, have, have + b->K, (uint32_t)nh);
+    PF(RQB_PF_REP_FETCH);
+    if (ok) {
+      for (size_t k = 0; k < nm; k++) mask_set(b, missing[k]);
+      b->gaps = 0;
+      b->written = true;
     }
-    b->gaps = 0;
-    ok = true;
-    rqb_copy_fence();
-    PF(RQB_PF_REP_WRITE);
-  } else {
-    rqb_solver_sync(b->sv);
+  } else if (rc == 0) {
+    rc = rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0);
+    PF(RQB_PF_REP_FETCH);
+    if (rc == 0) {
+      /* decode_repair_rows + write_repair_rows (:567-589) */
+      const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
+      for (size_t k = 0; k < nm; k++) {
+        transfer_symbol(rq, sbn, missing[k], (uint8_t *)sy + k * b->pitch, io, 1);
+        mask_set(b, missing[k]);
+      }
+      b->gaps = 0;
+      ok = true;
+      rqb_copy_fence();
+      PF(RQB_PF_REP_WRITE);
+    }
   }
+  if (!ok) rqb_solver_sync(b->sv);
   free(missing);
+  free(have);
   return ok;
 }

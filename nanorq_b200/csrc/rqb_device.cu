@@ -50,7 +50,7 @@ static constexpr int kSolveMinCtas = RQB_SOLVE_MIN_CTAS;       // CTAs per SM th
 // big batches (the thin levels of the triangular solve keep more of the CTA's lanes busy and
 // every barrier covers twice the bytes); 4 lanes = 64-byte slices when only a few blocks are
 // in flight (twice the CTAs for the fat levels).
-static constexpr int kRingStages = 4;
+static constexpr int kRingStages = 8; // 8 x 4 KiB pages in flight per CTA
 static constexpr uint32_t kRingBytes = kRingStages * RQB_PAGE_BYTES;
 static constexpr uint32_t kSolveSmem = kRingBytes + 128;       // ring + mbarriers
 
@@ -312,6 +312,21 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
   }
 }
 
+#ifdef RQB_TRACE
+// debug builds only (-DRQB_TRACE): CTA (0,0) of the shared-memory kernel logs the clock after
+// every page wait and every level barrier; rqb_dev_trace_fetch reads the log back
+__device__ unsigned long long g_trace[16384];
+__device__ unsigned g_trace_n;
+#define TRACE(tag, val)                                                                          \
+  do {                                                                                           \
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && g_trace_n < 16384)                     \
+      g_trace[g_trace_n++] = ((unsigned long long)(tag) << 62) | ((unsigned long long)(val) << 40) | \
+                             (clock64() & 0xFFFFFFFFFFull);                                       \
+  } while (0)
+#else
+#define TRACE(tag, val) do { } while (0)
+#endif
+
 // ------------------------------------------------- shared-memory solve kernel
 // The shared-memory flavour of the program (rqb_program.h): a CTA keeps its column slice
 // (kLanes x 16 bytes) of every live row of the block in shared-memory SLOTS for the whole
@@ -319,10 +334,10 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
 // the elimination runs in place on the slots -- ~30-cycle shared-memory latency per
 // dependency level instead of an L2/HBM round trip -- and only results go back to HBM, so
 // DRAM traffic is the compulsory traffic.  One CTA per SM (the slots take most of the 227 KB),
-// 512 threads = 512 / kLanes tasks at a time; program pages arrive through a 2-deep TMA ring.
+// 512 threads = 512 / kLanes tasks at a time; program pages arrive through a 6-deep TMA ring.
 // grid = (ceil(width / (16 kLanes)), nblocks); dynamic smem = ring + barriers + n_slots * 16 kLanes.
 static constexpr int kSmemThreads = 512;
-static constexpr int kSmemRingStages = 2;
+static constexpr int kSmemRingStages = RQB_SMEM_RING_STAGES; // the thin levels consume ~6 B/cycle, a page takes 1-2 us to arrive
 static constexpr uint32_t kSmemRingBytes = kSmemRingStages * RQB_PAGE_BYTES;
 static constexpr uint32_t kSmemFixedBytes = kSmemRingBytes + 128; // ring + mbarriers, then the slots
 
@@ -486,10 +501,15 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
     }
   }
   const bool active = col0 + lane * 16u < width; // the last slice of a row may be narrower
+#ifdef RQB_TRACE
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_trace_n = 0;
+#endif
+  TRACE(0, 0);
 
   for (uint32_t pg = 0; pg < n_pages; pg++) {
     const uint32_t st = pg % kSmemRingStages;
     mbar_wait(&bars[st], (pg / kSmemRingStages) & 1u);
+    TRACE(1, pg);
     const uint8_t *page = ring + st * RQB_PAGE_BYTES;
     const uint32_t n_levels = reinterpret_cast<const rqb_page_hdr *>(page)->n_levels;
     uint32_t off = sizeof(rqb_page_hdr);
@@ -502,24 +522,44 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
           const uint32_t nsrc = th.z & 0xffffu, kind = (th.z >> 16) & 0xffu;
           const uint32_t *sp = reinterpret_cast<const uint32_t *>(page + th.x);
           if (kind == RQB_T_XOR) {
-            // exactly 4 or 8 references (padded with slot 0): all loads issued before the first use
+            // exactly 4 or 8 references (padded with slot 0): all loads issued before the first use.
+            // aux bit 0: every reference is a slot -- the hot path of the thin levels: a level's latency
+            // is the instruction count of one warp, so it carries no address arithmetic for HBM rows
             const uint4 i0 = *reinterpret_cast<const uint4 *>(sp);
-            uint4 v0 = R.ld(i0.x), v1 = R.ld(i0.y), v2 = R.ld(i0.z), v3 = R.ld(i0.w);
             uint4 acc;
-            if (nsrc > 4) {
-              const uint4 i1 = *reinterpret_cast<const uint4 *>(sp + 4);
-              uint4 v4 = R.ld(i1.x), v5 = R.ld(i1.y), v6 = R.ld(i1.z), v7 = R.ld(i1.w);
-              acc.x = xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
-              acc.y = xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
-              acc.z = xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
-              acc.w = xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+            if (th.z >> 24) {
+              uint4 v0 = R.lds(i0.x), v1 = R.lds(i0.y), v2 = R.lds(i0.z), v3 = R.lds(i0.w);
+              if (nsrc > 4) {
+                const uint4 i1 = *reinterpret_cast<const uint4 *>(sp + 4);
+                uint4 v4 = R.lds(i1.x), v5 = R.lds(i1.y), v6 = R.lds(i1.z), v7 = R.lds(i1.w);
+                acc.x = xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+                acc.y = xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+                acc.z = xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+                acc.w = xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+              } else {
+                acc.x = xor3(v0.x, v1.x, v2.x) ^ v3.x;
+                acc.y = xor3(v0.y, v1.y, v2.y) ^ v3.y;
+                acc.z = xor3(v0.z, v1.z, v2.z) ^ v3.z;
+                acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
+              }
+              R.sts(th.y, acc);
             } else {
-              acc.x = xor3(v0.x, v1.x, v2.x) ^ v3.x;
-              acc.y = xor3(v0.y, v1.y, v2.y) ^ v3.y;
-              acc.z = xor3(v0.z, v1.z, v2.z) ^ v3.z;
-              acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
+              uint4 v0 = R.ld(i0.x), v1 = R.ld(i0.y), v2 = R.ld(i0.z), v3 = R.ld(i0.w);
+              if (nsrc > 4) {
+                const uint4 i1 = *reinterpret_cast<const uint4 *>(sp + 4);
+                uint4 v4 = R.ld(i1.x), v5 = R.ld(i1.y), v6 = R.ld(i1.z), v7 = R.ld(i1.w);
+                acc.x = xor3(xor3(v0.x, v1.x, v2.x), xor3(v3.x, v4.x, v5.x), v6.x ^ v7.x);
+                acc.y = xor3(xor3(v0.y, v1.y, v2.y), xor3(v3.y, v4.y, v5.y), v6.y ^ v7.y);
+                acc.z = xor3(xor3(v0.z, v1.z, v2.z), xor3(v3.z, v4.z, v5.z), v6.z ^ v7.z);
+                acc.w = xor3(xor3(v0.w, v1.w, v2.w), xor3(v3.w, v4.w, v5.w), v6.w ^ v7.w);
+              } else {
+                acc.x = xor3(v0.x, v1.x, v2.x) ^ v3.x;
+                acc.y = xor3(v0.y, v1.y, v2.y) ^ v3.y;
+                acc.z = xor3(v0.z, v1.z, v2.z) ^ v3.z;
+                acc.w = xor3(v0.w, v1.w, v2.w) ^ v3.w;
+              }
+              R.st(th.y, acc);
             }
-            R.st(th.y, acc);
           } else if (kind == RQB_T_TAB) {
             smem_task_tab<kLanes>(R, sp, nsrc, th.y, th.w, lh.z, th.z >> 24);
           } else if (kind == RQB_T_LOAD) {
@@ -540,12 +580,15 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
           }
         }
       }
+      TRACE(2, lh.x);
       __syncthreads();
+      TRACE(3, lh.x);
       off = lh.y;
     }
     if (n_levels == 0) __syncthreads();
-    // every thread is past its last read of this stage: refill it
-    if (tid == 0 && pg + kSmemRingStages < n_pages) {
+    // every thread is past its last read of this stage: refill it -- from the last warp, which has
+    // tasks only in the fat levels (warp 0 is the one the thin levels wait for)
+    if (tid == kSmemThreads - 1 && pg + kSmemRingStages < n_pages) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bars[st], RQB_PAGE_BYTES);
       tma_bulk_g2s(ring + st * RQB_PAGE_BYTES, pages + (size_t)(pg + kSmemRingStages) * RQB_PAGE_BYTES,
@@ -616,6 +659,19 @@ rqb_gather_rows_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *
     const uint32_t r = (uint32_t)(g / vpr), v = (uint32_t)(g - (uint64_t)r * vpr);
     reinterpret_cast<uint4 *>(dst + (size_t)r * dpitch)[v] =
         __ldg(reinterpret_cast<const uint4 *>(src + (size_t)map[r] * spitch) + v);
+  }
+}
+
+// row[pairs[2k+1]] = row[pairs[2k]] inside one arena
+__global__ void __launch_bounds__(256)
+rqb_copy_rows_kernel(uint8_t *__restrict__ base, size_t pitch, const uint32_t *__restrict__ pairs, uint32_t n,
+                     uint32_t vpr) {
+  const uint64_t total = (uint64_t)n * vpr;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(g / vpr), v = (uint32_t)(g - (uint64_t)r * vpr);
+    reinterpret_cast<uint4 *>(base + (size_t)pairs[2 * r + 1] * pitch)[v] =
+        __ldg(reinterpret_cast<const uint4 *>(base + (size_t)pairs[2 * r] * pitch) + v);
   }
 }
 
@@ -911,6 +967,17 @@ int rqb_launch_solve_smem(const rqb_solve_args *args_dev, int nblocks, uint32_t 
   return 0;
 }
 
+#ifdef RQB_TRACE
+int rqb_dev_trace_fetch(unsigned long long *out, unsigned cap) {
+  unsigned n = 0;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
+  if (n > cap) n = cap;
+  CK(cudaMemcpyFromSymbol(out, g_trace, (size_t)n * sizeof(unsigned long long)));
+  return (int)n;
+}
+#endif
+
 int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const uint32_t *isi_dev, uint32_t n,
                   uint8_t *out, uint32_t out_pitch, uint32_t width, void *stream) {
   if (n == 0) return 0;
@@ -935,6 +1002,17 @@ int rqb_launch_rowops(uint8_t *D, size_t pitch, uint32_t width, const rqb_rowop 
   if (n == 0) return 0;
   const uint32_t vpr = width / 16;
   rqb_rowops_kernel<<<stream_grid((uint64_t)n * vpr, 256), 256, 0, (cudaStream_t)stream>>>(D, pitch, vpr, ops_dev, n);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rqb_launch_copy_rows(uint8_t *base, size_t pitch, const uint32_t *pairs_dev, uint32_t n, uint32_t width,
+                         void *stream) {
+  if (n == 0) return 0;
+  const uint32_t vpr = width / 16;
+  rqb_copy_rows_kernel<<<stream_grid((uint64_t)n * vpr, 256), 256, 0, (cudaStream_t)stream>>>(base, pitch, pairs_dev,
+                                                                                               n, vpr);
   g_launches++;
   CK(cudaGetLastError());
   return 0;

@@ -96,6 +96,10 @@ int rqb_launch_rowops(uint8_t *D, size_t pitch, uint32_t width, const rqb_rowop 
 int rqb_launch_gather_rows(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch,
                            const uint32_t *map_dev, uint32_t n, uint32_t width, void *stream);
 
+/* row copies inside one arena: row pairs[2k+1] = row pairs[2k], k < n (pairs_dev: device array) */
+int rqb_launch_copy_rows(uint8_t *base, size_t pitch, const uint32_t *pairs_dev, uint32_t n, uint32_t width,
+                         void *stream);
+
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 unsigned long long rqb_dev_launch_count(void);
 /* bytes moved by rqb_copy* so far */

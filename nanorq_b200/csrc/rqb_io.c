@@ -12,6 +12,8 @@
 #include <unistd.h>
 
 #include "io.h"
+#include "nanorq_batch.h"
+#include "rqb200.h"
 #include "rqb_hostcopy.h"
 
 /* ------------------------------------------------------------- stdio file */
@@ -58,6 +60,7 @@ typedef struct {
   struct ioctx io;
   uint8_t *base;
   size_t pos, len;
+  int pinned;  /* 1: page-locked by the caller (rqb_host_alloc / rqb_host_pin), 2: page-locked here */
 } mem_ctx;
 
 static size_t m_clip(mem_ctx *c, size_t n) { return c->pos + n > c->len ? c->len - c->pos : n; }
@@ -85,11 +88,13 @@ static long m_tell(struct ioctx *io) { return (long)((mem_ctx *)io)->pos; }
 static size_t m_size(struct ioctx *io) { return ((mem_ctx *)io)->len; }
 static void m_destroy(struct ioctx *io) {
   rqb_copy_fence(); /* rows were written with non-temporal stores */
+  if (((mem_ctx *)io)->pinned == 2) rqb_host_unpin(((mem_ctx *)io)->base);
   free(io);
 }
 
 struct ioctx *ioctx_from_mem(const uint8_t *ptr, size_t sz) {
   mem_ctx *c = calloc(1, sizeof(*c));
+  if (!c) return NULL;
   c->base = (uint8_t *)ptr;
   c->len = sz;
   c->io.read = m_read;
@@ -101,6 +106,40 @@ struct ioctx *ioctx_from_mem(const uint8_t *ptr, size_t sz) {
   c->io.seekable = true;
   c->io.writable = true;
   return &c->io;
+}
+
+/* Memory the GPU's copy engines can reach directly (the pinned/registered-memory ioctx of SURVEY
+ * 8(f)4; the reference's ioctx_from_mem, lib/io.c:139-157, always goes through memcpy): same
+ * behaviour as ioctx_from_mem for every caller of the vtable, but the nanorq_* calls of this
+ * library recognise it (rqb_ioctx_mem_view) and move symbols between this memory and the device by
+ * DMA, without the copy through a staging row.
+ * already_pinned != 0: the caller page-locked the memory (rqb_host_alloc, rqb_host_pin, or
+ * cudaHostAlloc / cudaHostRegister of its own); 0: it is page-locked here for the lifetime of
+ * the context (takes ~0.2 ms per MiB: meant for long-lived buffers). */
+struct ioctx *ioctx_from_pinned_mem(uint8_t *ptr, size_t sz, int already_pinned) {
+  if (!ptr || !sz) return NULL;
+  int pinned = 1;
+  if (!already_pinned) {
+    if (rqb_host_pin(ptr, sz) != 0) return NULL;
+    pinned = 2;
+  }
+  struct ioctx *io = ioctx_from_mem(ptr, sz);
+  if (!io) {
+    if (pinned == 2) rqb_host_unpin(ptr);
+    return NULL;
+  }
+  ((mem_ctx *)io)->pinned = pinned;
+  return io;
+}
+
+/* library-internal: is `io` one of the memory contexts above?  Gives its span. */
+int rqb_ioctx_mem_view(struct ioctx *io, uint8_t **base, size_t *len, int *pinned) {
+  if (!io || io->read != m_read || io->destroy != m_destroy) return 0;
+  const mem_ctx *c = (const mem_ctx *)io;
+  *base = c->base;
+  *len = c->len;
+  *pinned = c->pinned != 0;
+  return 1;
 }
 
 /* ------------------------------------------------------------------- mmap

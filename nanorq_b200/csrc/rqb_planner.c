@@ -326,7 +326,7 @@ static size_t task_bytes(const ptask *t) { return sizeof(rqb_task) + list_bytes(
 
 /* pack the tasks, level by level, into pages (a level may be split over pages:
  * its tasks are independent).  Returns 0 or a negative error. */
-static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *tot_levels, uint8_t *ext_buf,
+static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, int smem, size_t *tot_levels, uint8_t *ext_buf,
                        size_t ext_cap) {
   scratch_t *sc = b->sc;
   const uint32_t nl = b->max_level + 1;
@@ -413,13 +413,20 @@ static int write_pages(builder *b, rqb_plan *plan, uint32_t zero_row, size_t *to
         size_t sb = list_bytes(t);
         if (t->kind != RQB_T_LOAD)
           memcpy(page + soff, b->srcs + t->src_at, t->kind == RQB_T_TAB ? (size_t)t->nsrc : (size_t)t->nsrc * 4);
-        if (t->kind == RQB_T_XOR)
+        uint8_t aux = t->aux;
+        if (t->kind == RQB_T_XOR) {
           for (size_t q = t->nsrc; q < sb / 4; q++) ((uint32_t *)(page + soff))[q] = zero_row;
+          if (smem) { /* aux bit 0: destination and every source are slots (the kernel's lean path) */
+            int all_slots = !(t->dst & RQB_REF_GLOBAL);
+            for (size_t q = 0; q < t->nsrc; q++) all_slots &= !(b->srcs[t->src_at + q] & RQB_REF_GLOBAL);
+            aux = (uint8_t)all_slots;
+          }
+        }
         dst[k].src_off = soff;
         dst[k].dst = t->dst;
         dst[k].nsrc = t->nsrc;
         dst[k].kind = t->kind;
-        dst[k].aux = t->aux;
+        dst[k].aux = aux;
         dst[k].pad = t->extra;
         soff += (uint32_t)sb;
       }
@@ -1015,7 +1022,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
       lv += 2;
       bd->ws_next = SCR;
     }
-    b_tree(bd, RQB_T_XOR, SM_G(v->row0[RQB_SP_SYM] + (uint32_t)k), tmp, ns, lv);
+    b_tree(bd, RQB_T_XOR, SM_G(v->row0[RQB_SP_SYM] + (req->out_row ? req->out_row[k] : (uint32_t)k)), tmp, ns, lv);
     if (bd->ws_next > peak) peak = bd->ws_next;
   }
   if (peak > v->slot_budget) return -8;
@@ -1523,6 +1530,9 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   const uint32_t zero_row = row0[RQB_SP_C] + (uint32_t)L;
   row0[RQB_SP_WS] = zero_row + 1;
   if (req->sym_rows < (uint32_t)req->n_out) return -1;
+  if (req->out_row)
+    for (int k = 0; k < req->n_out; k++)
+      if (req->out_row[k] >= req->sym_rows) return -1;
   builder bd;
   memset(&bd, 0, sizeof(bd));
   bd.sc = sc;
@@ -1841,7 +1851,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     int cnt = rqb_host_lt_indices(&P, req->out_isi[k], idx);
     uint32_t ns = 0;
     for (int q = 0; q < cnt; q++) PUSH(ns, cloc[idx[q]]);
-    b_tree(&bd, RQB_T_XOR, row0[RQB_SP_SYM] + (uint32_t)k, tmp, ns, lv);
+    b_tree(&bd, RQB_T_XOR, row0[RQB_SP_SYM] + (req->out_row ? req->out_row[k] : (uint32_t)k), tmp, ns, lv);
   }
 #undef PUSH
 #undef WSREF
@@ -1856,7 +1866,7 @@ emitted:
   if (!plan) return -7;
   size_t tot_levels = 0;
   /* the shared-memory flavour pads its XOR lists with slot 0 */
-  rc = write_pages(&bd, plan, smem ? 0u : zero_row, &tot_levels, req->pages_buf, req->pages_buf_cap);
+  rc = write_pages(&bd, plan, smem ? 0u : zero_row, smem, &tot_levels, req->pages_buf, req->pages_buf_cap);
   if (rc) {
     rqb_plan_free(plan);
     return rc;
@@ -1995,7 +2005,7 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
     if (!rc) {
       rqb_plan *plan = plan_acquire();
       size_t tot_levels = 0;
-      rc = write_pages(&bd, plan, zero_row, &tot_levels, NULL, 0);
+      rc = write_pages(&bd, plan, zero_row, 0, &tot_levels, NULL, 0);
       if (rc) {
         rqb_plan_free(plan);
       } else {

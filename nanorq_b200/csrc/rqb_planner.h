@@ -32,6 +32,7 @@ typedef struct {
   uint8_t *pages_buf;      /* optional: write the program here (e.g. pinned memory the DMA    */
   size_t pages_buf_cap;    /* engine reads) instead of the plan's own buffer; if it is too     */
                            /* small the plan's buffer is used (plan->pages tells which)        */
+  const uint32_t *out_row; /* optional [n_out]: row of the SYM space symbol k is written to (default k) */
   uint32_t smem_budget;    /* bytes of shared memory a CTA may use for row slots: > 0 asks for */
                            /* the shared-memory flavour of the program (rqb_program.h) when    */
                            /* the block's live rows fit, 0 for the HBM flavour                 */

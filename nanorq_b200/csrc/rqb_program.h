@@ -33,7 +33,7 @@
 
 #include <stdint.h>
 
-#define RQB_PAGE_BYTES 8192u /* multiple of 16 (TMA bulk copy granularity) */
+#define RQB_PAGE_BYTES 4096u /* multiple of 16 (TMA bulk copy granularity) */
 #define RQB_SLICE_BYTES 128u /* default column slice per CTA (rqb_device.cu picks 64 / 128 / 256 per launch) */
 #define RQB_MAX_SRCS 8u      /* sources per XOR/GF task (the kernel keeps them all in flight) */
 #define RQB_ROW_NONE 0xFFFFFFFFu
@@ -109,7 +109,8 @@ typedef struct {
  *                   bit 23 clear -> shared-memory slot `ref`.  Slot 0 is all zero and never
  *                   written (it pads XOR lists; level header zero_row = 0).
  *   XOR / GF        as above over mixed references; a destination that accumulates lists
- *                   itself as a source (rows are updated in place).
+ *                   itself as a source (rows are updated in place).  XOR: aux bit 0 = the
+ *                   destination and every source are slots (no HBM reference).
  *   LOAD            slots dst .. dst+nsrc-1  =  arena rows pad .. pad+nsrc-1   (no list)
  *   SCAN2           alpha-scan with the HDPC sums folded in (the y_j are never stored):
  *                     y = alpha*y ^ row[ref(e_k)];  slot[dst + h1(e_k)] ^= y;  slot[dst + h2(e_k)] ^= y
@@ -125,6 +126,7 @@ typedef struct {
 #define RQB_REF_GLOBAL 0x00800000u
 #define RQB_T_LOAD 4
 #define RQB_T_SCAN2 5
-#define RQB_SMEM_BUDGET_BYTES (227u * 1024u - 2u * RQB_PAGE_BYTES - 128u) /* slots of one CTA: 227 KB minus the page ring and its barriers */
+#define RQB_SMEM_RING_STAGES 6u
+#define RQB_SMEM_BUDGET_BYTES (227u * 1024u - RQB_SMEM_RING_STAGES * RQB_PAGE_BYTES - 128u) /* slots of one CTA: 227 KB minus the page ring and its barriers */
 
 #endif

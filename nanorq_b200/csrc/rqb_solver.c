@@ -238,7 +238,7 @@ static void pool_drain(void) { /* hand every pooled buffer back to the driver */
  * the schedule nanorq_precalculate keeps in rq->S (lib/nanorq.c:393-401); here
  * it is cached process-wide together with its device copy. */
 typedef struct enc_plan {
-  int K, Kparams, want_c, dev;
+  int K, Kparams, want_c, dev, hbm; /* hbm: asked for the HBM flavour */
   uint32_t n_out, in_rows, sym_rows; /* the arena layout is part of the program */
   rqb_plan *plan;
   uint8_t *d_pages;
@@ -298,6 +298,7 @@ struct rqb_solver {
    * launching stream after a batched kernel that works on other solvers' rows */
   void *ev_ready, *ev_done;
   struct enc_plan *enc; /* the cached encoder program attached to this context (reference counted) */
+  int flavour;          /* RQB_FLAVOUR_*: which flavour of the program to ask the planner for */
   uint8_t *h_in, *h_sym; /* pinned: staging rows of the input space, mirror of the emitted symbols */
   uint32_t *h_flag;      /* pinned word the stream sets when it has drained (rqb_stream_wait_flag) */
   uint32_t flag_seq;
@@ -307,6 +308,7 @@ struct rqb_solver {
   size_t arena_cap; /* bytes */
   uint32_t row0[4], zero_row;
   uint32_t *d_isi, *h_isi;
+  uint32_t *d_pairs, pairs_cap; /* (input row, emitted row) pairs of rqb_solver_copy_in_to_sym */
   /* current program */
   rqb_plan *plan; /* owned unless shared */
   int plan_shared, has_c, timed;
@@ -382,6 +384,7 @@ static void solver_release(rqb_solver *s) {
   buf_free(s->h_sym, 1);
   buf_free(s->h_flag, 1);
   buf_free(s->d_isi, 0);
+  buf_free(s->d_pairs, 0);
   free(s->h_isi);
   buf_free(s->d_pages, 0);
   buf_free(s->h_pages, 1);
@@ -461,6 +464,14 @@ int rqb_solver_create(rqb_solver **out, int K, size_t T, uint32_t max_in, uint32
 }
 
 int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_t max_in, uint32_t max_out) {
+  return rqb_solver_create_on(out, -1, K, Kparams, T, max_in, max_out);
+}
+
+int rqb_solver_device(const rqb_solver *s) { return s->dev; }
+void rqb_solver_set_flavour(rqb_solver *s, int flavour) { s->flavour = flavour == RQB_FLAVOUR_HBM ? RQB_FLAVOUR_HBM : RQB_FLAVOUR_AUTO; }
+
+int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, size_t T, uint32_t max_in,
+                         uint32_t max_out) {
   *out = NULL;
   rqb_params P;
   if (K < 1 || rqb_params_init(Kparams, &P) || K > P.Kprime || T == 0 || T > 65535 || max_in < (uint32_t)K) {
@@ -472,7 +483,11 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     return RQB_E_NODEVICE;
   }
   if (!max_out) max_out = 1;
-  const int dev = rqb_dev_default();
+  const int dev = want_dev >= 0 ? want_dev : rqb_dev_default();
+  if (dev >= rqb_dev_count()) {
+    snprintf(g_err, sizeof(g_err), "rqb_solver_create: no CUDA device %d", dev);
+    return RQB_E_ARG;
+  }
   rqb_solver *s = NULL;
   pthread_mutex_lock(&g_shell_mu);
   {
@@ -511,6 +526,7 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
     s->max_in = max_in;
     s->max_out = max_out;
     s->has_c = s->timed = s->want_timing = 0;
+    s->flavour = RQB_FLAVOUR_AUTO;
     s->n_out_last = 0;
     s->next_shell = NULL;
     if (bind_dev(s->dev)) { /* the context is already out of the list: do not leak it */
@@ -605,6 +621,86 @@ int rqb_solver_upload(rqb_solver *s, uint32_t first, uint32_t n) {
   s->busy = 1;
   DEV(rqb_copy_h2d(ROW_PTR(s, RQB_SP_IN, first), s->h_in + (size_t)first * s->pitch, (size_t)n * s->pitch,
                    s->stream));
+  return 0;
+}
+
+int rqb_solver_upload_rows(rqb_solver *s, uint32_t first, uint32_t n, const uint8_t *src, size_t src_pitch) {
+  BIND(s->dev);
+  if ((uint64_t)first + n > s->max_in || !src || src_pitch < s->T) return RQB_E_ARG;
+  if (!n) return 0;
+  rqb_copy_fence();
+  s->busy = 1;
+  /* pad bytes of the device rows are never read back and never mix with payload bytes (row operations
+   * are column-local), so only the T payload bytes of each row travel */
+  DEV(rqb_copy2d_h2d(ROW_PTR(s, RQB_SP_IN, first), s->pitch, src, src_pitch, s->T, n, s->stream));
+  return 0;
+}
+
+int rqb_solver_fetch_rows(rqb_solver *s, int space, uint32_t first, uint32_t n, uint8_t *dst, size_t dst_pitch,
+                          int wait) {
+  BIND(s->dev);
+  const uint32_t cap = space == RQB_SP_IN ? s->max_in : space == RQB_SP_SYM ? s->max_out : (uint32_t)s->P.L;
+  if (space < RQB_SP_IN || space > RQB_SP_C || (uint64_t)first + n > cap || !dst || dst_pitch < s->T) return RQB_E_ARG;
+  if (space == RQB_SP_C && !s->has_c) return RQB_E_ARG;
+  if (n) {
+    s->busy = 1;
+    DEV(rqb_copy2d_d2h(dst, dst_pitch, ROW_PTR(s, space, first), s->pitch, s->T, n, s->stream));
+  }
+  if (wait) {
+    int w = solver_wait(s);
+    if (w) return w;
+  }
+  return 0;
+}
+
+int rqb_solver_copy_in_to_sym(rqb_solver *s, const uint32_t *sym_row, const uint32_t *in_row, uint32_t n) {
+  BIND(s->dev);
+  if (!n) return 0;
+  if (n > s->max_out) return RQB_E_ARG;
+  if (s->pairs_cap < n) {
+    if (s->d_pairs) {
+      int w = solver_wait(s);
+      if (w) return w;
+      pool_put(s->d_pairs, (size_t)s->pairs_cap * 8, 0);
+      s->d_pairs = NULL;
+      s->pairs_cap = 0;
+    }
+    DEV(pool_get((void **)&s->d_pairs, (size_t)s->max_out * 8, 0));
+    s->pairs_cap = s->max_out;
+  }
+  uint32_t *pairs = malloc((size_t)n * 8); /* pageable on purpose: staged by cudaMemcpyAsync before it returns */
+  if (!pairs) return RQB_E_ARG;
+  for (uint32_t k = 0; k < n; k++) {
+    if (in_row[k] >= s->max_in || sym_row[k] >= s->max_out) {
+      free(pairs);
+      return RQB_E_ARG;
+    }
+    pairs[2 * k] = s->row0[RQB_SP_IN] + in_row[k];
+    pairs[2 * k + 1] = s->row0[RQB_SP_SYM] + sym_row[k];
+  }
+  s->busy = 1;
+  int e = rqb_copy_h2d(s->d_pairs, pairs, (size_t)n * 8, s->stream);
+  free(pairs);
+  if (e) return dev_fail(e, "rqb_solver_copy_in_to_sym");
+  DEV(rqb_launch_copy_rows(s->d_arena, s->pitch, s->d_pairs, n, (uint32_t)round_up(s->T, 16), s->stream));
+  return 0;
+}
+
+void *rqb_host_alloc(size_t bytes) {
+  void *p = NULL;
+  if (rqb_dev_count() <= 0 || rqb_host_malloc(&p, bytes)) return NULL;
+  return p;
+}
+void rqb_host_release(void *p) {
+  if (p) rqb_host_free(p);
+}
+int rqb_host_pin(void *p, size_t bytes) {
+  if (rqb_dev_count() <= 0) return RQB_E_NODEVICE;
+  DEV(rqb_host_register(p, bytes));
+  return 0;
+}
+int rqb_host_unpin(void *p) {
+  DEV(rqb_host_unregister(p));
   return 0;
 }
 
@@ -715,7 +811,8 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
       if (w) return w;
     }
   }
-  pr.smem_budget = solver_smem_budget();
+  pr.out_row = req->out_row;
+  pr.smem_budget = s->flavour == RQB_FLAVOUR_HBM ? 0u : solver_smem_budget();
   pr.pages_buf = s->h_pages;
   pr.pages_buf_cap = s->h_pages_cap < s->d_pages_cap ? s->h_pages_cap : s->d_pages_cap;
   rqb_plan *p = NULL;
@@ -762,7 +859,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
   enc_plan *e = g_enc_plans;
   for (; e; e = e->next)
     if (e->K == s->K && e->Kparams == s->Kparams && e->want_c == want_c && e->n_out == n_rep && e->dev == s->dev &&
-        e->in_rows == s->max_in && e->sym_rows == s->max_out)
+        e->in_rows == s->max_in && e->sym_rows == s->max_out && e->hbm == (s->flavour == RQB_FLAVOUR_HBM))
       break;
   if (!e) {
     const int Kp = s->P.Kprime;
@@ -777,7 +874,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
       }
       for (uint32_t k = 0; k < n_rep; k++) oi[k] = (uint32_t)Kp + k; /* repair ESI K+k <-> ISI K'+k */
       rqb_plan_request pr = {s->Kparams, 0, isi, in_row, want_c, (int)n_rep, oi, s->max_in, s->max_out, NULL, 0,
-                             solver_smem_budget()};
+                             NULL, s->flavour == RQB_FLAVOUR_HBM ? 0u : solver_smem_budget()};
       rc = rqb_plan_build(&pr, &p);
     }
     free(isi);
@@ -799,6 +896,7 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
       e->in_rows = s->max_in;
       e->sym_rows = s->max_out;
       e->dev = s->dev;
+      e->hbm = s->flavour == RQB_FLAVOUR_HBM;
       e->plan = p;
       de = rqb_dev_malloc((void **)&e->d_pages, pb);
       de = de ? de : rqb_copy_h2d(e->d_pages, p->pages, pb, s->stream);
@@ -1003,7 +1101,7 @@ int rqb_plan_blob_build_ex(int K, const rqb_solve_request *req, uint32_t smem_bu
   for (int k = 0; k < P.Kprime + req->overhead; k++)
     if (req->in_row[k] != RQB_NO_ROW && req->in_row[k] >= in_rows) in_rows = req->in_row[k] + 1;
   rqb_plan_request pr = {K, req->overhead, req->isi, req->in_row, req->want_c, (int)req->n_out, req->out_isi,
-                         in_rows, req->n_out ? req->n_out : 1, NULL, 0, smem_budget};
+                         in_rows, req->n_out ? req->n_out : 1, NULL, 0, req->out_row, smem_budget};
   rqb_plan *p = NULL;
   int rc = rqb_plan_build(&pr, &p);
   if (rc == 1) return RQB_NEED_MORE;

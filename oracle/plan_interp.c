@@ -161,6 +161,11 @@ int rqb_interp_run2(const uint32_t *row0, uint32_t zero_row, uint32_t n_rows, ui
               if (t->src_off + (size_t)padded * 4 > RQB_PAGE_BYTES) { rc = 11; break; }
               for (uint32_t q = t->nsrc; q < padded; q++)
                 if (s32[q] != list_zero) rc = 15;
+              if (smem && (t->aux & 1u)) { /* the kernel's lean path: no reference may be an HBM row */
+                if (t->dst & RQB_REF_GLOBAL) rc = 11;
+                for (uint32_t q = 0; q < t->nsrc; q++)
+                  if (s32[q] & RQB_REF_GLOBAL) rc = 11;
+              }
               if (rc) break;
             }
             memset(tmp, 0, T);

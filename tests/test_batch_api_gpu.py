@@ -1,0 +1,219 @@
+"""nanorq_batch.h on the GPU: nanorq_encode_range / nanorq_decoder_add_symbols /
+ioctx_from_pinned_mem / nanorq_set_devices against the per-symbol calls of nanorq.h and
+against the oracle."""
+import numpy as np
+import pytest
+
+import nanorq_b200 as nb
+from nanorq_b200 import api
+from oracle_lib import orc_encode, orc_lt, orc_params
+
+pytestmark = pytest.mark.gpu
+
+
+def pinned_array(nbytes):
+    buf = nb.PinnedBuffer(nbytes)
+    return buf, buf.arr
+
+
+@pytest.mark.parametrize("F,T,K", [(640, 64, 10), (100 * 64 - 17, 64, 100), (1310720, 1280, 1024), (5242880, 1280, 4096)])
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_encode_range_equals_per_symbol_encode_and_oracle(F, T, K, pinned):
+    rng = np.random.default_rng(F)
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    keep = []
+    if pinned:
+        buf, arr = pinned_array(F)
+        arr[:] = payload
+        keep.append(buf)
+        io = nb.PinnedMemIO(arr)
+    else:
+        io = nb.MemIO(payload)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    ref = nb.Encoder(F, T, K, 0, 8)
+    io_ref = nb.MemIO(payload)
+    Kb = enc.block_symbols(0)
+    # a range that straddles source and repair symbols and more than one repair window
+    n_rep = max(40, Kb // 8 + 70)
+    first = max(0, Kb - 7)
+    if pinned:
+        obuf, oarr = pinned_array((Kb + n_rep) * (T + 16))
+        keep.append(obuf)
+        out = oarr.reshape(Kb + n_rep, T + 16)  # rows wider than T: the pitch is honoured
+    else:
+        out = np.zeros((Kb + n_rep, T), np.uint8)
+    got = enc.encode_range(0, first, Kb - first + n_rep, io, out=out)
+    assert got is not None
+    for k, esi in enumerate(range(first, Kb + n_rep)):
+        assert np.array_equal(got[k], ref.encode(esi, 0, io_ref)), esi
+    # all source symbols in one call, then an isolated far repair range
+    src = enc.encode_range(0, 0, Kb, io)
+    blk = np.zeros(Kb * T, np.uint8)
+    blk[:F] = payload
+    assert np.array_equal(src, blk.reshape(Kb, T))
+    far = enc.encode_range(0, Kb + 5000, 9, io)
+    p = orc_params(Kb)
+    Co, _, _ = orc_encode(Kb, T, blk)
+    for k in range(9):
+        assert np.array_equal(far[k], orc_lt(Kb, T, Co, Kb + 5000 + k + p.Kprime - Kb))
+    # per-symbol calls still work after range calls (window bookkeeping)
+    assert np.array_equal(enc.encode(Kb + 3, 0, io), orc_lt(Kb, T, Co, Kb + 3 + p.Kprime - Kb))
+    enc.close(); ref.close(); io.close(); io_ref.close()
+    for b in keep:
+        b.close()
+
+
+def make_packets(F, T, K, Z, loss, oh, seed):
+    rng = np.random.default_rng(seed)
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    enc = nb.Encoder(F, T, K, Z, 8)
+    io = nb.MemIO(payload)
+    tags, rows = [], []
+    for sbn in range(enc.blocks()):
+        Kb = enc.block_symbols(sbn)
+        drop = rng.random(Kb) < loss
+        n_rep = int(drop.sum()) + oh
+        syms = enc.encode_range(sbn, 0, Kb + n_rep, io)
+        for esi in list(np.nonzero(~drop)[0]) + list(range(Kb, Kb + n_rep)):
+            tags.append(api.tag(sbn, int(esi)))
+            rows.append(syms[esi])
+    oti = (enc.oti_common(), enc.oti_scheme_specific())
+    enc.close()
+    return payload, oti, np.array(tags, np.uint32), np.stack(rows)
+
+
+@pytest.mark.parametrize("F,T,K,Z,loss,oh", [(640, 64, 10, 0, 0.3, 2), (100 * 64 - 17, 64, 100, 0, 0.2, 2),
+                                              (1310720, 1280, 1024, 0, 0.05, 2), (5242880, 1280, 4096, 0, 0.10, 2),
+                                              (3 * 500 * 104 - 5, 104, 500, 0, 0.15, 3)])
+@pytest.mark.parametrize("mode", ["pageable", "pinned", "pinned-shuffled", "mixed-calls"])
+def test_add_symbols_decodes_like_per_symbol_calls(F, T, K, Z, loss, oh, mode):
+    payload, oti, tags, rows = make_packets(F, T, K, Z, loss, oh, seed=F % 89 + 1)
+    keep = []
+    if mode == "pinned-shuffled":
+        order = np.random.default_rng(1).permutation(len(tags))
+        tags, rows = tags[order], rows[order]
+    if mode.startswith("pinned"):
+        pb, parr = pinned_array(rows.size)
+        parr[:] = rows.reshape(-1)
+        data = parr.reshape(rows.shape)
+        ob, out = pinned_array(F)
+        out[:] = 0xEE
+        keep += [pb, ob]
+        io = nb.PinnedMemIO(out)
+    else:
+        data = rows
+        out = np.full(F, 0xEE, np.uint8)
+        io = nb.MemIO(out)
+    dec = nb.Decoder(*oti)
+    if mode == "mixed-calls":  # alternate between the batch call and the per-symbol call on the same blocks
+        k = 0
+        while k < len(tags):
+            n = min(37, len(tags) - k)
+            rc, st = dec.add_symbols(tags[k:k + n], data[k:k + n], io)
+            assert rc >= 0
+            k += n
+            for q in range(k, min(k + 5, len(tags))):
+                assert dec.add_symbol(data[q], int(tags[q]), io) in (nb.SYM_ADDED, nb.SYM_IGN)
+            k = min(k + 5, len(tags))
+    else:
+        rc, st = dec.add_symbols(tags, data, io)
+        assert rc >= 0 and all(s in (nb.SYM_ADDED, nb.SYM_IGN) for s in st)
+        # a second delivery of the same symbols is classified like the per-symbol call does
+        rc2, st2 = dec.add_symbols(tags[:5], data[:5], io)
+        assert rc2 == 0 and all(s in (nb.SYM_DUP, nb.SYM_IGN) for s in st2)
+    for sbn in range(dec.blocks()):
+        assert dec.repair_block(io, sbn), sbn
+        assert dec.repair_block(io, sbn)  # idempotent
+    assert np.array_equal(out, payload)
+    dec.close(); io.close()
+    for b in keep:
+        b.close()
+
+
+def test_pinned_output_block_completed_by_the_last_source_symbol():
+    """No loss: the call that delivers a block's last source symbol hands the block back."""
+    F, T, K = 300 * 48, 48, 300
+    payload, oti, tags, rows = make_packets(F, T, K, 0, 0.0, 0, seed=5)
+    pb, parr = pinned_array(rows.size)
+    parr[:] = rows.reshape(-1)
+    ob, out = pinned_array(F)
+    out[:] = 0
+    io = nb.PinnedMemIO(out)
+    dec = nb.Decoder(*oti)
+    rc, _ = dec.add_symbols(tags[:200], parr.reshape(rows.shape)[:200], io)
+    assert rc == 200 and dec.num_missing(0) == 100
+    rc, _ = dec.add_symbols(tags[200:], parr.reshape(rows.shape)[200:], io)
+    assert rc == 100 and dec.num_missing(0) == 0
+    assert np.array_equal(out, payload)
+    assert dec.repair_block(io, 0)
+    dec.close(); io.close(); pb.close(); ob.close()
+
+
+def test_pinned_ioctx_with_the_per_symbol_api_only():
+    """ioctx_from_pinned_mem behind the unchanged nanorq.h calls: load by DMA, output deferred."""
+    F, T, K = 1000 * 200 - 33, 200, 1000
+    rng = np.random.default_rng(8)
+    ib, inp = pinned_array(F)
+    inp[:] = rng.integers(0, 256, F, dtype=np.uint8)
+    ob, out = pinned_array(F)
+    out[:] = 0
+    io_in, io_out = nb.PinnedMemIO(inp), nb.PinnedMemIO(out)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    assert enc.generate_symbols(0, io_in)
+    drop = rng.random(K) < 0.1
+    for esi in list(np.nonzero(~drop)[0]) + list(range(K, K + int(drop.sum()) + 2)):
+        assert dec.add_symbol(enc.encode(int(esi), 0, io_in), api.tag(0, int(esi)), io_out) == nb.SYM_ADDED
+    assert dec.repair_block(io_out, 0)
+    assert np.array_equal(out, inp)
+    # a memory the library page-locks itself
+    plain = np.array(inp)
+    io2 = nb.PinnedMemIO(plain, already_pinned=False)
+    enc2 = nb.Encoder(F, T, K, 0, 8)
+    assert np.array_equal(enc2.encode_range(0, K, 4, io2), enc.encode_range(0, K, 4, io_in))
+    for x in (enc, enc2, dec, io_in, io_out, io2, ib, ob):
+        x.close()
+
+
+def test_blocks_of_one_object_spread_over_all_devices():
+    """nanorq_set_devices(0): block sbn is solved on device sbn mod n; one process, one object."""
+    n = nb.device_count()
+    F, T, K, Z = 8 * 1024 * 256, 256, 1024, 8
+    payload, oti, tags, rows = make_packets(F, T, K, 0, 0.1, 2, seed=12)
+    dec = nb.Decoder(*oti)
+    assert dec.set_devices(0) == n
+    out = np.zeros(F, np.uint8)
+    io = nb.MemIO(out)
+    rc, _ = dec.add_symbols(tags, rows, io)
+    assert rc >= 0
+    for sbn in range(dec.blocks()):
+        assert dec.repair_block(io, sbn)
+    assert np.array_equal(out, payload)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    assert enc.set_devices(0) == n
+    io_in = nb.MemIO(payload)
+    p = orc_params(K)
+    for sbn in (0, 1, Z - 1):
+        Co, _, _ = orc_encode(K, T, payload[sbn * K * T:(sbn + 1) * K * T])
+        got = enc.encode_range(sbn, K, 3, io_in)
+        assert np.array_equal(got, np.stack([orc_lt(K, T, Co, K + k + p.Kprime - K) for k in range(3)]))
+    print("devices used:", n)
+    for x in (enc, dec, io, io_in):
+        x.close()
+
+
+def test_solver_on_every_device_and_flavour_switch():
+    K, T = 500, 64
+    rng = np.random.default_rng(4)
+    src = rng.integers(0, 256, (K, T), dtype=np.uint8)
+    Co, _, _ = orc_encode(K, T, src)
+    for dev in range(nb.device_count()):
+        for fl in ("auto", "hbm"):
+            s = nb.Solver(K, T, max_in=K, max_out=4, device=dev, flavour=fl)
+            s.staging[:K, :T] = src
+            s.upload(0, K)
+            s.plan_encode(True, 0)
+            assert bool(s.stats()["smem"]) == (fl == "auto")
+            s.run()
+            assert np.array_equal(s.fetch_c(), Co), (dev, fl)
+            s.close()

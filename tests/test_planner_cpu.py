@@ -228,3 +228,31 @@ def test_random_op_list_as_one_program_equals_sequential_oracle(seed):
     rc, cout, _ = interp_run(blob, D, T, nr, 0, in_writable=True)
     assert rc == 0
     assert np.array_equal(cout, want)
+
+
+@pytest.mark.parametrize("smem", [False, True], ids=["hbm", "smem"])
+def test_out_row_places_recovered_symbols_at_their_esi(smem):
+    """rqb_solve_request.out_row: a decoder recovers straight into the rows of the block image."""
+    K, T = 200, 16
+    p = orc_params(K)
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (K, T), dtype=np.uint8)
+    Cm, _, _ = orc_encode(K, T, src)
+    drop = rng.random(K) < 0.2
+    esis = np.concatenate([np.nonzero(~drop)[0], np.arange(K, K + int(drop.sum()) + 2)]).astype(np.uint32)
+    syms = np.stack([src[e] if e < K else orc_lt(K, T, Cm, int(e) + p.Kprime - K) for e in esis])
+    req, missing = nb.SolveRequest.for_decoder(K, esis, want_c=False)
+    req2 = nb.SolveRequest(req.isi, req.in_row, req.c.overhead, False, missing, out_row=missing)
+    # the blob sizes the emitted-symbol space to n_out rows: rows beyond it are refused
+    assert max(missing) >= len(missing)
+    assert nb.plan_blob(K, req2, smem=smem)[0] != 0
+    bad = nb.SolveRequest(req.isi, req.in_row, req.c.overhead, False, missing, out_row=[10 ** 6] * len(missing))
+    assert nb.plan_blob(K, bad, smem=smem)[0] != 0
+    # ... and a permutation inside the space is honoured
+    perm = np.random.default_rng(1).permutation(len(missing)).astype(np.uint32)
+    req3 = nb.SolveRequest(req.isi, req.in_row, req.c.overhead, False, missing, out_row=perm)
+    rc, blob = nb.plan_blob(K, req3, smem=smem)
+    assert rc == 0
+    rc, _, sout = interp_run(blob, syms, T, 0, len(missing))
+    assert rc == 0
+    assert np.array_equal(sout[perm], src[missing])

@@ -4,7 +4,7 @@
 out=gpurun_out/flavour_ab.log
 : > $out
 for fl in smem hbm; do
-  for sl in 64 32 16; do
+  for sl in 64 32; do
     [ $fl = hbm ] && [ $sl != 64 ] && continue
     echo "== flavour=$fl max_slice=$sl" >> $out
     for kt in "1024 1280" "4096 1280"; do
