@@ -6,9 +6,10 @@
  * both this library and the unmodified reference); this file only exists for this
  * library because the reference has no batch calls.
  *
- * Per block the host does: two object constructors, one encode-range call for the
- * symbols that survive the loss pattern (runs of consecutive ESIs) plus the repair
- * range, one add-symbols call, one repair call.  No symbol byte is copied by the CPU:
+ * Per block the host does: two object constructors, one encode-range call (the block's
+ * source symbols and the repair symbols the receiver will need, into a packet ring whose
+ * row number is the sequence number), one add-symbols call over that ring with the lost
+ * packets marked as holes (NANORQ_TAG_NONE), one repair call.  No symbol byte is copied by the CPU:
  * payload -> device, device -> packet buffer, packet buffer -> device, device -> output
  * are all DMA.
  */
@@ -53,6 +54,8 @@ static inline uint32_t xs32(uint32_t *s) {
 typedef struct {
   const rt_config *cfg;
   uint8_t **payload, **decoded; /* page-locked */
+  uint8_t *pk;                  /* this worker's page-locked packet ring */
+  int from_payload, no_decode;
   int *next;
   pthread_mutex_t *mu;
   pthread_barrier_t *bar;
@@ -72,9 +75,8 @@ static void *work(void *arg) {
   const rt_config *c = w->cfg;
   const size_t K = (size_t)c->K, T = (size_t)c->T, F = K * T;
   const size_t max_pk = 2 * K + (size_t)c->overhead + 64;
-  uint8_t *pk = rqb_host_alloc(max_pk * T); /* the packet buffer a sender/receiver would reuse */
+  uint8_t *pk = w->pk; /* the page-locked packet ring a sender/receiver would reuse */
   uint32_t *tags = malloc(max_pk * sizeof(uint32_t));
-  if (pk) memset(pk, 0, max_pk * T);
   pthread_barrier_wait(w->bar);
   w->t_start = now_s();
   for (int b; pk && (b = take(w)) >= 0;) {
@@ -87,32 +89,23 @@ static void *work(void *arg) {
     double t0 = now_s();
     bool ok = nanorq_generate_symbols(enc, 0, in);
     double t1 = now_s();
-    /* the surviving source symbols, as runs of consecutive ESIs, then the repair range */
-    size_t n = 0, lost = 0;
-    uint32_t run0 = 0, run_n = 0;
-    for (uint32_t esi = 0; esi <= K && ok; esi++) {
-      const int drop = esi == K || xs32(&rs) < thresh;
-      if (!drop) {
-        if (!run_n) run0 = esi;
-        run_n++;
-        continue;
-      }
-      if (esi < K) lost++;
-      if (run_n) {
-        ok = nanorq_encode_range(enc, 0, run0, run_n, pk + n * T, T, in) == run_n;
-        for (uint32_t q = 0; q < run_n; q++) tags[n + q] = nanorq_tag(0, run0 + q);
-        n += run_n;
-        run_n = 0;
-      }
+    /* the sender emits the whole block and the repair symbols with ONE call into its packet ring
+     * (row = sequence number); the channel drops packets: their rows become holes */
+    size_t lost = 0;
+    for (uint32_t esi = 0; esi < K; esi++) {
+      const int drop = xs32(&rs) < thresh;
+      lost += (size_t)drop;
+      tags[esi] = drop ? NANORQ_TAG_NONE : nanorq_tag(0, esi);
     }
-    uint32_t next_rep = (uint32_t)K;
     const uint32_t n_rep = (uint32_t)(lost + (size_t)c->overhead);
-    if (ok && n_rep) {
-      ok = nanorq_encode_range(enc, 0, next_rep, n_rep, pk + n * T, T, in) == n_rep;
-      for (uint32_t q = 0; q < n_rep; q++) tags[n + q] = nanorq_tag(0, next_rep + q);
-      n += n_rep;
-      next_rep += n_rep;
-    }
+    size_t n = K + n_rep;
+    uint32_t next_rep = (uint32_t)(K + n_rep);
+    for (uint32_t q = 0; q < n_rep; q++) tags[K + q] = nanorq_tag(0, (uint32_t)K + q);
+    /* RQ_BATCH_SENDER=payload: the sender transmits source symbols straight from its payload buffer
+     * (they are the payload) and asks the encoder for the repair symbols only */
+    const int from_payload = w->from_payload;
+    if (ok && !from_payload) ok = nanorq_encode_range(enc, 0, 0, (uint32_t)n, pk, T, in) == n;
+    if (ok && from_payload && n_rep) ok = nanorq_encode_range(enc, 0, (uint32_t)K, n_rep, pk + K * T, T, in) == n_rep;
     double t2 = now_s();
     uint64_t oti_c = nanorq_oti_common(enc);
     uint32_t oti_s = nanorq_oti_scheme_specific(enc);
@@ -121,7 +114,23 @@ static void *work(void *arg) {
     bool done = false;
     double t3 = t2, t4 = t2;
     if (dec) {
-      if (nanorq_decoder_add_symbols(dec, tags, pk, T, n, NULL, out) < 0) ok = false;
+      if (w->no_decode) {
+        nanorq_free(dec);
+        dec = NULL;
+        memcpy(w->decoded[b], w->payload[b], F); /* experiment: encoder side only */
+        w->acc.t_gen += t1 - t0;
+        w->acc.t_emit += t2 - t1;
+        out->destroy(out);
+        in->destroy(in);
+        nanorq_free(enc);
+        continue;
+      }
+      if (!from_payload) {
+        if (nanorq_decoder_add_symbols(dec, tags, pk, T, n, NULL, out) < 0) ok = false;
+      } else { /* source symbols from the payload buffer (with holes), repair symbols from the ring */
+        if (nanorq_decoder_add_symbols(dec, tags, w->payload[b], T, K, NULL, out) < 0) ok = false;
+        if (n_rep && nanorq_decoder_add_symbols(dec, tags + K, pk + K * T, T, n_rep, NULL, out) < 0) ok = false;
+      }
       t3 = now_s();
       done = ok && nanorq_repair_block(dec, out, 0);
       t4 = now_s();
@@ -152,7 +161,6 @@ static void *work(void *arg) {
   }
   w->t_done = now_s();
   if (!pk) w->acc.failures++;
-  rqb_host_release(pk);
   free(tags);
   return NULL;
 }
@@ -184,8 +192,17 @@ int rq_roundtrip_batch_run(const rt_config *cfg, rt_result *res) {
   int next = 0;
   worker *ws = calloc((size_t)nt, sizeof(*ws));
   pthread_t *th = calloc((size_t)nt, sizeof(*th));
+  /* page-locked memory is allocated and released outside the clock and while no worker runs:
+   * cudaMallocHost / cudaFreeHost stall every thread of the process that talks to the driver */
+  const size_t pk_bytes = (2 * (size_t)cfg->K + (size_t)cfg->overhead + 64) * (size_t)cfg->T;
+  for (int k = 0; k < nt; k++) {
+    ws[k].pk = rqb_host_alloc(pk_bytes);
+    if (ws[k].pk) memset(ws[k].pk, 0, pk_bytes);
+  }
   for (int k = 0; k < nt; k++) {
     ws[k].cfg = cfg;
+    ws[k].from_payload = getenv("RQ_BATCH_SENDER") && !strcmp(getenv("RQ_BATCH_SENDER"), "payload");
+    ws[k].no_decode = getenv("RQ_BATCH_NO_DECODE") != NULL;
     ws[k].payload = payload;
     ws[k].decoded = decoded;
     ws[k].next = &next;
@@ -216,6 +233,7 @@ int rq_roundtrip_batch_run(const rt_config *cfg, rt_result *res) {
   }
   res->out_fnv = h;
   pthread_barrier_destroy(&bar);
+  for (int k = 0; k < nt; k++) rqb_host_release(ws[k].pk);
   rqb_host_release(pay);
   rqb_host_release(dec);
   free(payload);

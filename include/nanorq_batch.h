@@ -30,8 +30,12 @@ struct ioctx *ioctx_from_pinned_mem(uint8_t *ptr, size_t sz, int already_pinned)
 size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, void *dst, size_t pitch,
                            struct ioctx *io);
 
+/* a row of the caller's buffer that holds no symbol: a receive ring indexed by sequence number
+ * has such holes where packets were lost; the row is skipped (status NANORQ_SYM_IGN) */
+#define NANORQ_TAG_NONE 0xFFFFFFFFu
+
 /* ---- decoder: n symbols, symbol k = T bytes at data + k*pitch with tag tags[k]
- * (nanorq_tag; any mix of blocks and ESIs, any order).  Replaces n calls of
+ * (nanorq_tag; any mix of blocks and ESIs, any order; NANORQ_TAG_NONE = no symbol in this row).  Replaces n calls of
  * nanorq_decoder_add_symbol (lib/nanorq.c:478-509) and classifies every symbol the same way;
  * status[k] (optional) receives NANORQ_SYM_ADDED / _IGN / _DUP / _ERR.  Returns the number of
  * symbols added, or -1 if any symbol was rejected with NANORQ_SYM_ERR.

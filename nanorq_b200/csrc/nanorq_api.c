@@ -342,12 +342,13 @@ bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :20
    * nanorq_encode of a repair symbol does */
   if (rqb_solver_plan_encode(b->sv, 1, b->win_cap)) return false;
   PF(RQB_PF_GEN_PLAN);
-  if (rqb_solver_run(b->sv) || rqb_solver_fetch_syms_async(b->sv, 0, b->win_cap)) return false;
+  if (rqb_solver_run(b->sv)) return false;
   PF(RQB_PF_GEN_RUN);
   b->inverted = true;
   b->win_first = b->K;
   b->win_n = b->win_cap;
-  b->win_pending = true;
+  b->win_pending = false;
+  b->win_on_host = false; /* the window stays on the device until a per-symbol call asks for one of its symbols */
   return true;
 }
 
@@ -426,7 +427,9 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
                            struct ioctx *io) {
   struct block *b = rq ? get_block(rq, sbn) : NULL;
   if (!b || b->mask || !dst || pitch < rq->T || n == 0 || (uint64_t)esi0 + n > (1u << 24)) return 0;
+  PF_T0;
   if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  PF(RQB_PF_RANGE_GEN);
   uint8_t *out = dst;
   uint32_t esi = esi0, left = n;
   /* source symbols: straight from the device's input rows into the caller's rows (DMA when the
@@ -451,11 +454,9 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
     esi += m;
     left -= m;
   }
+  PF(RQB_PF_RANGE_QUEUE);
   if (rqb_solver_sync(b->sv)) return 0;
-  if (b->win_pending) {
-    b->win_pending = false;
-    b->win_on_host = true;
-  }
+  PF(RQB_PF_RANGE_WAIT);
   return n;
 }
 
@@ -588,6 +589,7 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
 int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *data, size_t pitch, size_t n,
                                int *status, struct ioctx *io) {
   if (!rq || !tags || !data || pitch < rq->T) return -1;
+  PF_T0;
   const uint8_t *rows = data;
   int added = 0, err = 0;
   size_t k = 0;
@@ -595,15 +597,31 @@ int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *dat
     /* a run of symbols of one block: all of them are copied into consecutive input rows with
      * ONE copy from the caller's memory; the ones the block does not accept (duplicates,
      * symbols after completion) simply leave their row unused */
+    if (tags[k] == NANORQ_TAG_NONE) { /* a hole at the start of a run */
+      if (status) status[k] = NANORQ_SYM_IGN;
+      k++;
+      continue;
+    }
     const uint8_t sbn = (tags[k] >> 24) & 0xff;
-    size_t run = 1;
-    while (k + run < n && ((tags[k + run] >> 24) & 0xff) == sbn) run++;
+    size_t run = 1, last = 1; /* holes inside a run travel with it; holes at its end do not */
+    while (k + run < n && (tags[k + run] == NANORQ_TAG_NONE || ((tags[k + run] >> 24) & 0xff) == sbn)) {
+      run++;
+      if (tags[k + run - 1] != NANORQ_TAG_NONE) last = run;
+    }
+    for (size_t q = last; q < run; q++)
+      if (status) status[k + q] = NANORQ_SYM_IGN;
+    const size_t skipped = run - last;
+    run = last;
     struct block *b = get_block(rq, sbn);
     size_t take = run;
     if (b && b->mask && b->landed + take > b->in_cap) take = b->in_cap - b->landed; /* never more rows than the block has */
     bool copied = false;
     const uint32_t row0 = b ? b->landed : 0;
     for (size_t q = 0; q < run; q++) {
+      if (tags[k + q] == NANORQ_TAG_NONE) {
+        if (status) status[k + q] = NANORQ_SYM_IGN;
+        continue;
+      }
       const uint32_t esi = tags[k + q] & 0x00ffffff;
       int st = q < take ? classify(rq, b, esi) : NANORQ_SYM_ERR;
       if (st == NANORQ_SYM_ADDED) {
@@ -630,8 +648,9 @@ int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *dat
         rqb_copy_fence();
       }
     }
-    k += run;
+    k += run + skipped;
   }
+  PF(RQB_PF_ADDS);
   return err ? -1 : added;
 }
 

@@ -7,7 +7,7 @@ enum {
   RQB_PF_GEN_LOAD, RQB_PF_GEN_UPLOAD, RQB_PF_GEN_PLAN, RQB_PF_GEN_RUN, RQB_PF_GEN_SYNC, RQB_PF_EMIT_SRC,
   RQB_PF_EMIT_WINDOW, RQB_PF_ADD_CREATE, RQB_PF_ADD_COPY, RQB_PF_ADD_WRITE, RQB_PF_REP_UPLOAD, RQB_PF_REP_REQUEST,
   RQB_PF_REP_PLAN, RQB_PF_REP_PAGES, RQB_PF_REP_ARGS, RQB_PF_REP_RUN, RQB_PF_REP_FETCH, RQB_PF_REP_WRITE,
-  RQB_PF_FREE, RQB_PF_COUNT
+  RQB_PF_FREE, RQB_PF_RANGE_GEN, RQB_PF_RANGE_QUEUE, RQB_PF_RANGE_WAIT, RQB_PF_ADDS, RQB_PF_COUNT
 };
 
 int rqb_prof_enabled(void);

@@ -39,7 +39,8 @@ static pthread_once_t g_prof_once = PTHREAD_ONCE_INIT;
 static const char *const g_prof_names[RQB_PF_COUNT] = {
     "gen.load", "gen.upload", "gen.plan", "gen.run", "gen.sync", "emit.source", "emit.window", "add.create",
     "add.copy", "add.write", "repair.upload", "repair.request", "repair.plan", "repair.pages", "repair.args",
-    "repair.run", "repair.fetch", "repair.write", "free"};
+    "repair.run", "repair.fetch", "repair.write", "free", "range.generate", "range.queue", "range.wait",
+    "add_symbols"};
 static void prof_init(void) {
   const char *e = getenv("NANORQ_B200_PROFILE");
   g_prof_on = e && e[0] == '1';
@@ -307,8 +308,10 @@ struct rqb_solver {
   uint8_t *d_arena;
   size_t arena_cap; /* bytes */
   uint32_t row0[4], zero_row;
-  uint32_t *d_isi, *h_isi;
-  uint32_t *d_pairs, pairs_cap; /* (input row, emitted row) pairs of rqb_solver_copy_in_to_sym */
+  uint32_t *h_isi; /* pinned: the ISIs of rqb_solver_emit, read in place by the LT kernel */
+  int isi_pending; /* an LT kernel reading h_isi has been queued since the last wait */
+  uint32_t *h_pairs, pairs_cap; /* pinned: (input row, emitted row) pairs of rqb_solver_copy_in_to_sym */
+  int pairs_pending;            /* a copy kernel reading h_pairs has been queued since the last wait */
   /* current program */
   rqb_plan *plan; /* owned unless shared */
   int plan_shared, has_c, timed;
@@ -361,7 +364,7 @@ static pthread_mutex_t g_shell_mu = PTHREAD_MUTEX_INITIALIZER;
 
 static size_t solver_bytes(const rqb_solver *s) { /* pinned + device memory a context holds */
   return (size_t)s->in_cap * s->pitch + s->arena_cap + (size_t)s->out_cap * s->pitch + s->d_pages_cap +
-         s->h_pages_cap + (size_t)s->out_cap * 4 + RQB_ARGS_BYTES;
+         s->h_pages_cap + (size_t)s->out_cap * 4 + (size_t)s->pairs_cap * 8 + RQB_ARGS_BYTES;
 }
 
 static void solver_detach_plan(rqb_solver *s) {
@@ -383,9 +386,8 @@ static void solver_release(rqb_solver *s) {
   buf_free(s->d_arena, 0);
   buf_free(s->h_sym, 1);
   buf_free(s->h_flag, 1);
-  buf_free(s->d_isi, 0);
-  buf_free(s->d_pairs, 0);
-  free(s->h_isi);
+  buf_free(s->h_pairs, 1);
+  buf_free(s->h_isi, 1);
   buf_free(s->d_pages, 0);
   buf_free(s->h_pages, 1);
   free(s->h_args);
@@ -576,13 +578,12 @@ int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, siz
   e = e ? e : pool_get((void **)&s->h_sym, (size_t)s->out_cap * s->pitch, 1);
   e = e ? e : pool_get((void **)&s->h_flag, 64, 1);
   if (!e) *s->h_flag = s->flag_seq = 0;
-  e = e ? e : pool_get((void **)&s->d_isi, (size_t)s->out_cap * 4, 0);
+  e = e ? e : pool_get((void **)&s->h_isi, (size_t)s->out_cap * 4, 1);
   /* small control blocks are sent from PAGEABLE memory on purpose: cudaMemcpyAsync
    * stages a pageable source before it returns, so these buffers may be rewritten
    * for the next launch while earlier copies are still queued on the stream */
-  s->h_isi = malloc((size_t)s->out_cap * 4);
   s->h_args = calloc(1, RQB_ARGS_BYTES);
-  if (!s->h_isi || !s->h_args) {
+  if (!s->h_args) {
     snprintf(g_err, sizeof(g_err), "rqb_solver_create: out of memory");
     s->broken = 1;
     rqb_solver_destroy(s);
@@ -610,6 +611,8 @@ static int solver_wait(rqb_solver *s) {
   DEV(rqb_stream_wait_flag(s->stream, s->h_flag, &s->flag_seq));
   s->busy = 0;
   s->pages_pending = 0;
+  s->pairs_pending = 0;
+  s->isi_pending = 0;
   return 0;
 }
 
@@ -657,32 +660,32 @@ int rqb_solver_copy_in_to_sym(rqb_solver *s, const uint32_t *sym_row, const uint
   BIND(s->dev);
   if (!n) return 0;
   if (n > s->max_out) return RQB_E_ARG;
+  /* The pairs live in page-locked host memory that the kernel reads in place (unified addressing):
+   * a copy from pageable memory would make the driver wait for everything queued on the stream --
+   * here the solve itself -- before it returns, and it does that under a lock other threads'
+   * launches need (measured: 0.6 ms per block, serialised over all threads). */
   if (s->pairs_cap < n) {
-    if (s->d_pairs) {
+    if (s->h_pairs) {
       int w = solver_wait(s);
       if (w) return w;
-      pool_put(s->d_pairs, (size_t)s->pairs_cap * 8, 0);
-      s->d_pairs = NULL;
+      pool_put(s->h_pairs, (size_t)s->pairs_cap * 8, 1);
+      s->h_pairs = NULL;
       s->pairs_cap = 0;
     }
-    DEV(pool_get((void **)&s->d_pairs, (size_t)s->max_out * 8, 0));
+    DEV(pool_get((void **)&s->h_pairs, (size_t)s->max_out * 8, 1));
     s->pairs_cap = s->max_out;
+  } else if (s->pairs_pending) { /* an earlier copy kernel may still be reading the buffer */
+    int w = solver_wait(s);
+    if (w) return w;
   }
-  uint32_t *pairs = malloc((size_t)n * 8); /* pageable on purpose: staged by cudaMemcpyAsync before it returns */
-  if (!pairs) return RQB_E_ARG;
   for (uint32_t k = 0; k < n; k++) {
-    if (in_row[k] >= s->max_in || sym_row[k] >= s->max_out) {
-      free(pairs);
-      return RQB_E_ARG;
-    }
-    pairs[2 * k] = s->row0[RQB_SP_IN] + in_row[k];
-    pairs[2 * k + 1] = s->row0[RQB_SP_SYM] + sym_row[k];
+    if (in_row[k] >= s->max_in || sym_row[k] >= s->max_out) return RQB_E_ARG;
+    s->h_pairs[2 * k] = s->row0[RQB_SP_IN] + in_row[k];
+    s->h_pairs[2 * k + 1] = s->row0[RQB_SP_SYM] + sym_row[k];
   }
   s->busy = 1;
-  int e = rqb_copy_h2d(s->d_pairs, pairs, (size_t)n * 8, s->stream);
-  free(pairs);
-  if (e) return dev_fail(e, "rqb_solver_copy_in_to_sym");
-  DEV(rqb_launch_copy_rows(s->d_arena, s->pitch, s->d_pairs, n, (uint32_t)round_up(s->T, 16), s->stream));
+  s->pairs_pending = 1;
+  DEV(rqb_launch_copy_rows(s->d_arena, s->pitch, s->h_pairs, n, (uint32_t)round_up(s->T, 16), s->stream));
   return 0;
 }
 
@@ -1028,10 +1031,16 @@ int rqb_solver_run_batch(rqb_solver **sv, int n) {
 int rqb_solver_emit(rqb_solver *s, const uint32_t *isi, uint32_t n) {
   BIND(s->dev);
   if (!s->has_c || n > s->max_out) return RQB_E_ARG;
+  /* the LT kernel reads the ISIs from page-locked host memory in place: no copy from pageable
+   * memory, which would wait for the whole stream under the driver's lock (see copy_in_to_sym) */
+  if (s->isi_pending) {
+    int w = solver_wait(s);
+    if (w) return w;
+  }
   memcpy(s->h_isi, isi, (size_t)n * 4);
   s->busy = 1;
-  DEV(rqb_copy_h2d(s->d_isi, s->h_isi, (size_t)n * 4, s->stream));
-  DEV(rqb_launch_lt(&s->P, ROW_PTR(s, RQB_SP_C, 0), (uint32_t)s->pitch, s->d_isi, n, ROW_PTR(s, RQB_SP_SYM, 0),
+  s->isi_pending = 1;
+  DEV(rqb_launch_lt(&s->P, ROW_PTR(s, RQB_SP_C, 0), (uint32_t)s->pitch, s->h_isi, n, ROW_PTR(s, RQB_SP_SYM, 0),
                     (uint32_t)s->pitch, (uint32_t)round_up(s->T, 16), s->stream));
   s->n_out_last = n;
   return 0;

@@ -217,3 +217,30 @@ def test_solver_on_every_device_and_flavour_switch():
             s.run()
             assert np.array_equal(s.fetch_c(), Co), (dev, fl)
             s.close()
+
+
+def test_receive_ring_with_holes_is_added_with_one_call():
+    """NANORQ_TAG_NONE marks rows of the caller's buffer that hold no symbol (lost packets in a
+    ring indexed by sequence number); everything else in the ring is added by one call."""
+    F, T, K = 700 * 48 - 5, 48, 700
+    rng = np.random.default_rng(21)
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    io_in = nb.MemIO(payload)
+    drop = rng.random(K) < 0.25
+    n_rep = int(drop.sum()) + 3
+    pb, parr = pinned_array((K + n_rep) * T)
+    ring = parr.reshape(K + n_rep, T)
+    assert enc.encode_range(0, 0, K + n_rep, io_in, out=ring) is not None
+    tags = np.array([0xFFFFFFFF if (e < K and drop[e]) else api.tag(0, e) for e in range(K + n_rep)], np.uint32)
+    ring[np.nonzero(drop)[0]] = 0x77  # whatever is in a hole must not matter
+    ob, out = pinned_array(F)
+    io_out = nb.PinnedMemIO(out)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    rc, st = dec.add_symbols(tags, ring, io_out)
+    assert rc == K - int(drop.sum()) + n_rep
+    assert all(s == nb.SYM_IGN for s, t in zip(st, tags) if t == 0xFFFFFFFF)
+    assert dec.repair_block(io_out, 0)
+    assert np.array_equal(out, payload)
+    for x in (enc, dec, io_in, io_out, pb, ob):
+        x.close()
