@@ -1,4 +1,3 @@
-#!/usr/bin/env python
 """bench.py -- encode+decode throughput of the nanorq hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -12,25 +11,37 @@ surviving + repair symbols, recovery of the lost symbols).
 Throughput = 2 * 8 * F * blocks / t  (F = K*T payload bytes; the factor 2 because
 encode and decode each process the payload -- SURVEY.md 8(d)).
 
-  value    device-resident: symbols and solve programs already in HBM, two kernel
-           launches per step (one batched solve for all encodes, one for all
-           decodes), timed with CUDA events on the launching stream.
-  e2e      host-to-host through the reference's own API (nanorq.h + io.h) with
-           pageable host buffers: bench/rq_roundtrip.c, the SAME source that is
-           compiled against the unmodified reference for `--impl reference`.
-           Includes loading through ioctx, H2D, host schedule construction, the
-           kernels, repair-symbol emission, decoder ingest, D2H and write-back.
-  roofline the batched solve kernel against measured HBM bandwidth, algorithmic
-           bytes = the reference's op sequence (constants from
-           tools/make_bench_constants.py); plus the row-axpy microbenchmark
-           (`row_axpy`) that genuinely streams HBM.
+  value    benchmark scope (what the reference's benchmark.c times: encode =
+           nanorq_generate_symbols, decode = nanorq_repair_block): symbols resident in HBM,
+           but every step DECODES A FRESH LOSS PATTERN PER BLOCK -- the host analyses each
+           block's constraint matrix and builds its solve program inside the timed region
+           (all host cores of the rank, overlapped with the previous step's kernels), the
+           programs are uploaded, and two batched solve kernels run.  Encoder programs are
+           cached per K like nanorq_precalculate's schedule.  Wall clock between two device
+           synchronisations, max over ranks.
+  kernel_only  the two batched solve launches of a step alone (programs built before the
+           clock), CUDA events on the launching stream: explains `value`, is not the metric.
+  e2e      host-to-host through the reference's own API (nanorq.h + io.h) with pageable host
+           buffers: bench/rq_roundtrip.c, the SAME source that is compiled against the
+           unmodified reference for `--impl reference`; objects of 8 source blocks,
+           nanorq_precalculate per object, one worker thread per host core on both arms.
+  e2e_batch  the same round trips through the batch calls of nanorq_batch.h over page-locked
+           buffers (bench/rq_roundtrip_batch.c): no CPU copy of symbol bytes.
+  roofline the batched solve kernel against measured HBM bandwidth: achieved = DRAM bytes the
+           kernel moves per launch (ncu capture of this command, profiles/, refused when the
+           kernel or planner sources changed since) / launch time measured live; next to it
+           the ALGORITHMIC bytes of the reference's op sequence (constants from
+           tools/make_bench_constants.py) and the compulsory bytes; plus the row-axpy
+           microbenchmark (`row_axpy`) that genuinely streams HBM.
   cpu_baseline  the unmodified reference (oracle/_ref) on ONE host core.
 
 `--impl reference` times the unmodified reference on all host cores on the same
 workload (rank 0 only).
 """
 import argparse
+import concurrent.futures
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -46,12 +57,14 @@ sys.path.insert(0, ROOT)
 K, T, LOSS, OVERHEAD = 4096, 1280, 0.10, 0
 F = K * T
 METRIC = "encode+decode Gbit/s at K=4096, T=1280 (K'=4112), 10% loss"
+ZBLOCKS = 8  # source blocks per object in the e2e arms (one object per worker thread per step)
 
 
 # ------------------------------------------------------------------ harness
 class RtConfig(C.Structure):
     _fields_ = [("K", C.c_int), ("T", C.c_int), ("nblocks", C.c_int), ("loss", C.c_double), ("overhead", C.c_int),
-                ("seed", C.c_uint), ("nthreads", C.c_int), ("precalc", C.c_int), ("verify", C.c_int)]
+                ("seed", C.c_uint), ("nthreads", C.c_int), ("precalc", C.c_int), ("verify", C.c_int),
+                ("zblocks", C.c_int)]
 
 
 class RtResult(C.Structure):
@@ -60,12 +73,13 @@ class RtResult(C.Structure):
                 ("failures", C.c_int), ("mismatches", C.c_int), ("out_fnv", C.c_ulonglong)]
 
 
-def roundtrip(libpath, nblocks, nthreads, seed, precalc=1, verify=1):
+def roundtrip(libpath, nblocks, nthreads, seed, precalc=1, verify=1, zblocks=ZBLOCKS, fn="rq_roundtrip_run"):
     L = C.CDLL(libpath)
-    L.rq_roundtrip_run.argtypes = [C.POINTER(RtConfig), C.POINTER(RtResult)]
-    cfg = RtConfig(K, T, nblocks, LOSS, OVERHEAD, seed, nthreads, precalc, verify)
+    f = getattr(L, fn)
+    f.argtypes = [C.POINTER(RtConfig), C.POINTER(RtResult)]
+    cfg = RtConfig(K, T, nblocks, LOSS, OVERHEAD, seed, nthreads, precalc, verify, zblocks)
     res = RtResult()
-    rc = L.rq_roundtrip_run(C.byref(cfg), C.byref(res))
+    rc = f(C.byref(cfg), C.byref(res))
     if rc != 0 or res.failures or res.mismatches:
         raise RuntimeError("round trip failed: rc=%d failures=%d mismatches=%d (%s)" %
                            (rc, res.failures, res.mismatches, libpath))
@@ -121,6 +135,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------ e2e workload
+def e2e_blocks(threads):
+    """Blocks per e2e step: one object of ZBLOCKS source blocks per worker thread, so both arms
+    keep every thread busy for the whole step."""
+    return ZBLOCKS * threads
+
+
+def config_workload(nb_kernel, nb_e2e):
+    return ("C3: K=4096 T=1280 loss=10%% overhead=0; %d independent blocks per GPU per step (device-resident "
+            "arm), %d blocks per step in objects of %d blocks (host-to-host arms)" % (nb_kernel, nb_e2e, ZBLOCKS))
+
+
 # ------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -129,23 +155,25 @@ def run_reference(args, rank, world):
     if not os.path.exists(so):
         raise SystemExit("oracle/_ref/librq_roundtrip_ref.so missing: run __graft_entry__.build() where /root/reference exists")
     cores = os.cpu_count() or 1
-    nb = args.blocks * max(1, args.gpus)
+    # the own arm at N GPUs runs N ranks with cores/N threads each: the same blocks in total
+    nb = e2e_blocks(max(1, cores // max(1, args.gpus))) * max(1, args.gpus)
     for w in range(args.warmup):
-        roundtrip(so, min(nb, cores), cores, 100 + w, precalc=0)
+        roundtrip(so, e2e_blocks(cores) // 4, cores, 100 + w, zblocks=2)
     walls, parts = [], np.zeros(4)
     for s in range(args.steps):
-        r = roundtrip(so, nb, cores, s, precalc=0)
+        r = roundtrip(so, nb, cores, s)  # objects of ZBLOCKS blocks, nanorq_precalculate per object
         walls.append(r.wall_s)
         parts += [r.t_gen, r.t_emit, r.t_add, r.t_repair]
     t = float(np.sum(walls))
     v = gbits(nb * args.steps, t)
-    sample = "%d steps x %d blocks of K=%d T=%d through nanorq.h on %d threads (bench/rq_roundtrip.c)" % (
-        args.steps, nb, K, T, cores)
+    sample = ("%d steps x %d blocks of K=%d T=%d through nanorq.h, objects of %d blocks with nanorq_precalculate, "
+              "%d threads (bench/rq_roundtrip.c)" % (args.steps, nb, K, T, ZBLOCKS, cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C3: K=4096 T=1280 loss=10%% overhead=0, %d blocks/step" % nb, "blocks_per_step": nb},
+        "config": {"workload": config_workload(args.blocks, nb // max(1, args.gpus)), "blocks_per_gpu": args.blocks,
+                   "e2e_blocks_per_step": nb, "zblocks": ZBLOCKS},
         "cpu_baseline": {"value": v, "unit": "Gbit/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phase_seconds_summed_over_threads": dict(zip(("generate_symbols", "encode_emit", "add_symbol", "repair_block"),
@@ -155,47 +183,70 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------ own arm
+N_REP_RESIDENT = 640  # repair symbols kept in HBM next to each block's source symbols (10 % loss needs ~410)
+
+
 def build_blocks(nb_mod, nblocks, seed0):
-    """Encode every block once on the GPU, derive the decoder's inputs and stage
-    them; returns (encoders, decoders, checks)."""
+    """Encode every block once on the GPU and make its symbols resident: the decoders' input rows hold
+    ALL K source symbols (row = ESI) followed by N_REP_RESIDENT repair symbols, so that any loss
+    pattern is only a choice of rows -- no symbol is uploaded again inside the timed region.
+    Two sets of decoders (a program is built for one set while the other one's runs).
+    Returns (encoders, [decoders A, decoders B], sources)."""
     from nanorq_b200 import workload
-    p = nb_mod.block_params(K)
-    pad = p.Kprime - K
-    n_rep_emit = 512  # repair symbols emitted together with the encode solve (>= lost symbols at 10 %)
-    encs, decs, checks = [], [], []
+    encs, srcs = [], []
     for b in range(nblocks):
-        seed = seed0 + b
-        src = workload.payload(K, T, seed)
-        e = nb_mod.Solver(K, T, max_in=K, max_out=n_rep_emit)
+        src = workload.payload(K, T, seed0 + b)
+        e = nb_mod.Solver(K, T, max_in=K, max_out=N_REP_RESIDENT, flavour="hbm")
         e.staging[:K, :T] = src
         e.upload(0, K)
-        e.plan_encode(True, n_rep_emit)
+        e.plan_encode(True, N_REP_RESIDENT)
         encs.append(e)
+        srcs.append(src)
     nb_mod.Solver.run_batch(encs, encs[0])
     encs[0].sync()
+    sets = [[], []]
     for b, e in enumerate(encs):
-        seed = seed0 + b
-        src = workload.payload(K, T, seed)
-        rep = e.fetch_syms(n_rep_emit)
-        drop = workload.loss_pattern(K, LOSS, seed)
-        extra = 0
-        while True:
-            esis = workload.received_esis(K, drop, OVERHEAD, extra)
-            assert len(esis) - (K - int(drop.sum())) <= n_rep_emit
-            req, missing = nb_mod.SolveRequest.for_decoder(K, esis, want_c=False)  # as nanorq_repair_block does
-            d = nb_mod.Solver(K, T, max_in=len(esis), max_out=len(missing))
-            if d.plan(req) == 0:
-                break
-            d.close()
-            extra += 2
-        syms = np.concatenate([src[~drop], rep[:len(esis) - int((~drop).sum())]])
-        d.staging[:len(esis), :T] = syms
-        d.upload(0, len(esis))
-        d.sync()
-        decs.append(d)
-        checks.append((np.asarray(missing), src[missing]))
-    del pad
-    return encs, decs, checks
+        rep = e.fetch_syms(N_REP_RESIDENT)
+        for which in (0, 1):
+            d = nb_mod.Solver(K, T, max_in=K + N_REP_RESIDENT, max_out=N_REP_RESIDENT, flavour="hbm")
+            d.staging[:K, :T] = srcs[b]
+            d.staging[K:K + N_REP_RESIDENT, :T] = rep
+            d.upload(0, K + N_REP_RESIDENT)
+            d.sync()
+            sets[which].append(d)
+    return encs, sets, srcs
+
+
+def fresh_request(nb_mod, seed, extra=0):
+    """A decode request for a fresh Bernoulli(LOSS) pattern over the resident rows: received source
+    symbol e sits in row e, repair symbol ESI K+j in row K+j.  Same construction as
+    nanorq_repair_block (missing source positions take the repair symbols in order, the rest are
+    overhead rows), vectorised so that the planning threads are not serialised by the interpreter."""
+    from nanorq_b200 import workload
+    Kp = nb_mod.block_params(K).Kprime
+    pad = Kp - K
+    drop = workload.loss_pattern(K, LOSS, seed)
+    missing = np.nonzero(drop)[0].astype(np.uint32)
+    nm, oh = len(missing), OVERHEAD + extra
+    assert nm + oh <= N_REP_RESIDENT
+    isi = np.arange(Kp + oh, dtype=np.uint32)
+    in_row = np.arange(Kp + oh, dtype=np.uint32)
+    in_row[K:Kp] = nb_mod.NO_ROW                      # padding symbols: known zero
+    j = np.arange(nm, dtype=np.uint32)
+    isi[missing] = K + j + pad                        # ISI of repair ESI K+j
+    in_row[missing] = K + j
+    x = np.arange(oh, dtype=np.uint32)
+    isi[Kp:] = K + nm + x + pad
+    in_row[Kp:] = K + nm + x
+    return nb_mod.SolveRequest(isi, in_row, oh, False, missing), missing
+
+
+def traffic_stamp():
+    """sha256 over the sources that decide what the solve kernel moves through DRAM."""
+    h = hashlib.sha256()
+    for f in ("nanorq_b200/csrc/rqb_device.cu", "nanorq_b200/csrc/rqb_planner.c", "nanorq_b200/csrc/rqb_program.h"):
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def run_own(args, rank, world, local_rank):
@@ -227,75 +278,180 @@ def run_own(args, rank, world, local_rank):
         return sharding.max_over_ranks(x, device="cuda")
 
     NB = args.blocks
-    encs, decs, checks = build_blocks(nb, NB, seed0=1000 * rank)
+    cores = max(1, (os.cpu_count() or 1) // world)  # host threads of this rank, all arms
+    threads = max(1, min(args.threads or cores, 64))
+    encs, dsets, srcs = build_blocks(nb, NB, seed0=1000 * rank)
     own = encs[0]
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=threads)
+    seed_ctr = [7777 + 100000 * rank]
+    missing_of = [[None] * NB, [None] * NB]
 
-    def step():
+    def plan_one(which, b, seed):
+        # host analysis of the block's constraint matrix + program emission + upload of the program
+        # (rqb_solver_plan; ctypes releases the GIL, so the pool's threads plan in parallel)
+        d = dsets[which][b]
+        extra = 0
+        while True:
+            req, missing = fresh_request(nb, seed, extra)
+            if d.plan(req) == 0:
+                break
+            extra += 2  # singular at overhead 0 (~1 % of patterns): two more repair symbols, like the e2e harness
+        missing_of[which][b] = missing
+
+    def plan_set(which):
+        seeds = [seed_ctr[0] + b for b in range(NB)]
+        seed_ctr[0] += NB
+        return [pool.submit(plan_one, which, b, seeds[b]) for b in range(NB)]
+
+    def wait_all(futs):
+        for f in futs:
+            f.result()
+
+    def launch(which):
         nb.Solver.run_batch(encs, own)
-        nb.Solver.run_batch(decs, own)
+        nb.Solver.run_batch(dsets[which], own)
 
-    # parity gate before timing: every decode returns the erased source symbols
-    step()
+    # parity gate before timing: every decode returns the erased source symbols of its fresh pattern
+    wait_all(plan_set(0))
+    launch(0)
     own.sync()
-    for d, (missing, want) in zip(decs, checks):
-        got = d.fetch_syms(len(missing))
-        if not np.array_equal(got, want):
+    for b, d in enumerate(dsets[0]):
+        m = np.asarray(missing_of[0][b])
+        if not np.array_equal(d.fetch_syms(len(m)), srcs[b][m]):
             raise SystemExit("decode does not reproduce the erased symbols")
 
-    # ---- value: device-resident, CUDA events on the launching stream
+    # ---- value: benchmark scope.  Step s: the GPU runs the programs of set s%2 while the host builds
+    # the programs of the other set for step s+1 (fresh patterns); K steps = K plannings + K kernel passes.
+    def pipelined(steps):
+        cur = 0
+        for _ in range(steps):
+            futs = plan_set(1 - cur)
+            launch(cur)
+            wait_all(futs)
+            own.sync()  # the other set's solvers are re-planned next: their kernels must be done
+            cur = 1 - cur
+        return cur
+
+    wait_all(plan_set(0))
+    cur = 0
     for _ in range(max(args.warmup, 3)):
-        step()
-    own.sync()
+        futs = plan_set(1 - cur); launch(cur); wait_all(futs); own.sync(); cur = 1 - cur
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = nb.kernel_launches()
-    own.mark(False)
+    h0, d0 = nb.transfer_bytes()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
-    own.mark(True)
-    ms = own.marked_ms()
+        futs = plan_set(1 - cur); launch(cur); wait_all(futs); own.sync(); cur = 1 - cur
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
     barrier()
     launches = nb.kernel_launches() - l0
-    ms = max_over_ranks(ms)
-    ms_step = ms / args.steps
+    h1, d1 = nb.transfer_bytes()
+    wall = max_over_ranks(wall)
+    ms_step = 1e3 * wall / args.steps
     value = gbits(NB * world, ms_step / 1e3)
+    # parity after the timed region as well (the last planned-and-run set)
+    last = 1 - cur
+    for b in (0, NB // 2, NB - 1):
+        m = np.asarray(missing_of[last][b])
+        if not np.array_equal(dsets[last][b].fetch_syms(len(m)), srcs[b][m]):
+            raise SystemExit("decode after the timed region does not reproduce the erased symbols")
 
-    # roofline of the batched solve kernel: algorithmic bytes per launch / mean launch time
+    # ---- kernel_only: the two batched launches alone, CUDA events on the launching stream
+    for _ in range(3):
+        launch(last)
+    own.sync()
+    barrier()
+    kl0 = nb.kernel_launches()
+    own.mark(False)
+    for _ in range(args.steps):
+        launch(last)
+    own.mark(True)
+    k_ms = max_over_ranks(own.marked_ms())
+    barrier()
+    k_launches = nb.kernel_launches() - kl0
+    k_ms_step = k_ms / args.steps
+    avg_launch_s = k_ms / 1e3 / k_launches
+    kernel_only = {"value": gbits(NB * world, k_ms_step / 1e3), "unit": "Gbit/s", "ms_per_step": k_ms_step,
+                   "gpu_launches": k_launches, "timing": "CUDA events on the launching stream",
+                   "scope": "two batched solve launches per step; programs built and uploaded before the clock"}
+
+    # host planning alone (one thread, same requests): what the pipelined figure hides or exposes
+    tp0 = time.perf_counter()
+    for b in range(min(NB, 32)):
+        plan_one(last, b, 424242 + b)
+    plan_ms = 1e3 * (time.perf_counter() - tp0) / min(NB, 32)
+
+    # ---- roofline of the batched solve kernel
     dec_c = consts["decode"]
-    enc_bytes = NB * (consts["encode"]["solve_bytes"] + consts["lt_repair_bytes_prefix"][511])
-    dec_bytes = sum(dec_c[b % len(dec_c)]["solve_bytes"] + dec_c[b % len(dec_c)]["lt_bytes"] for b in range(NB))
-    alg_per_launch = (enc_bytes + dec_bytes) / 2.0
+    enc_bytes = NB * (consts["encode"]["solve_bytes"] + consts["lt_repair_bytes_prefix"][N_REP_RESIDENT - 1])
+    dec_mean = float(np.mean([d["solve_bytes"] + d["lt_bytes"] for d in dec_c]))  # fresh patterns: mean over 64 seeded ones (+-2 %)
+    alg_per_launch = (enc_bytes + NB * dec_mean) / 2.0
     prog_bytes = 0
-    for sv in encs + decs:
+    for sv in encs + dsets[last]:
         st = sv.stats()
         prog_bytes += (st["n_srcs"] + st["n_gf_srcs"] + 2 * st["n_horner"] + st["n_tasks"]) * sv.pitch
-    avg_launch_s = ms / 1e3 / launches
-    achieved = alg_per_launch / avg_launch_s / 1e9
-    compulsory = NB * (K * T + consts["L"] * T + 512 * T) + sum((K + 0) * T + len(c[0]) * T for c in checks)
+    n_lost = float(np.mean([len(m) for m in missing_of[last]]))
+    compulsory = NB * (K * T + consts["L"] * T + N_REP_RESIDENT * T) + NB * ((K - n_lost) * T + 2 * n_lost * T)
     slice_bytes = nb.lib().rqb_batch_slice_bytes(NB, T)
     roofline = {"bound": "hbm", "kernel": "rqb_solve_kernel (batched, grid = %d column slices of %d bytes x %d blocks)" % (
-                    -(-T // slice_bytes), slice_bytes, NB), "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
-                "compulsory_bytes_per_step": compulsory,
-                "compulsory_gbs": compulsory / (ms_step / 1e3) / 1e9,
+                    -(-T // slice_bytes), slice_bytes, NB),
+                "peak": peak, "unit": "GB/s", "peak_source": peak_src, "avg_launch_ms": 1e3 * avg_launch_s,
+                "algorithmic_bytes_per_launch": alg_per_launch,
+                "algorithmic_gbs": alg_per_launch / avg_launch_s / 1e9,
+                "algorithmic_frac": alg_per_launch / avg_launch_s / 1e9 / peak,
+                "compulsory_bytes_per_launch": compulsory / 2.0,
+                "compulsory_gbs": compulsory / 2.0 / avg_launch_s / 1e9,
+                "compulsory_frac": compulsory / 2.0 / avg_launch_s / 1e9 / peak,
                 "program_bytes_per_launch": prog_bytes / 2.0,
-                "program_gbs": prog_bytes / 2.0 / avg_launch_s / 1e9,
-                "note": "achieved = ALGORITHMIC bytes of the reference's row-op sequence (3*pitch per axpy, SURVEY 8(d)) "
-                        "per second. The kernel does the same linear algebra with fewer bytes: accumulations into one "
-                        "destination are merged into one gather task (sources read once, destination written once) and "
-                        "the H dense HDPC rows become an alpha-scan, so frac can exceed 1. program_bytes = the row "
-                        "segments this kernel really loads and stores (from L1/L2/HBM); traffic = DRAM bytes per launch "
-                        "from ncu (profiles/)."}
-    traffic_file = os.path.join(ROOT, "profiles", "r01_solve_traffic.json")
+                "program_gbs": prog_bytes / 2.0 / avg_launch_s / 1e9}
+    traffic_file = os.path.join(ROOT, "profiles", "r02_solve_traffic.json")
+    traffic = None
     if os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-        if roofline["traffic"]:
-            # what the kernel really moves through HBM (ncu, same command) per second of measured launch time
-            roofline["traffic_gbs"] = roofline["traffic"] / avg_launch_s / 1e9
-            roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
+        tf = json.load(open(traffic_file))
+        if tf.get("source_stamp") == traffic_stamp() and tf.get("blocks_per_launch") == NB:
+            traffic = tf.get("dram_bytes_per_launch")
+        else:
+            roofline["traffic_note"] = ("profiles/r02_solve_traffic.json was captured for other kernel/planner sources or "
+                                        "another batch size (stamp %s, now %s): ignored" % (tf.get("source_stamp"), traffic_stamp()))
+    roofline["traffic"] = traffic
+    if traffic:
+        # what the kernel really moves through HBM (ncu capture of this command) per second of launch time measured now
+        roofline["achieved"] = traffic / avg_launch_s / 1e9
+        roofline["frac"] = roofline["achieved"] / peak
+        roofline["note"] = ("achieved/frac = measured DRAM traffic of the kernel (ncu dram__bytes_read+write per launch, "
+                            "profiles/r02_solve_ncu.json) / launch time measured in this run.  algorithmic_* = the "
+                            "reference's row-op sequence (3*pitch per axpy, SURVEY 8(d)): the kernel does the same algebra "
+                            "with fewer bytes (accumulations merged into gathers, HDPC rows as an alpha-scan), so "
+                            "algorithmic_frac exceeds 1 and is not a roofline fraction.  compulsory_* = symbols in + "
+                            "results out once.")
+    else:
+        roofline["achieved"] = roofline["algorithmic_gbs"]
+        roofline["frac"] = roofline["algorithmic_frac"]
+        roofline["note"] = ("no current ncu traffic capture: achieved = ALGORITHMIC bytes of the reference's row-op sequence "
+                            "per second (SURVEY 8(d)); the kernel merges accumulations into gathers, so this exceeds the "
+                            "bytes it moves and frac can exceed 1")
+
+    # ---- literal config C4: 8 independent blocks sharded over the ranks (8/N per GPU), one launch each way
+    c4 = None
+    if 8 % world == 0:
+        share = 8 // world
+        for _ in range(3):
+            nb.Solver.run_batch(encs[:share], own); nb.Solver.run_batch(dsets[last][:share], own)
+        own.sync()
+        barrier()
+        own.mark(False)
+        reps = 20
+        for _ in range(reps):
+            nb.Solver.run_batch(encs[:share], own); nb.Solver.run_batch(dsets[last][:share], own)
+        own.mark(True)
+        c4_ms = max_over_ranks(own.marked_ms()) / reps
+        barrier()
+        c4 = {"blocks": 8, "blocks_per_gpu": share, "ms_encode_plus_decode": c4_ms, "value": gbits(8, c4_ms / 1e3),
+              "unit": "Gbit/s", "scope": "kernel only (device-resident), CUDA events, max over ranks"}
 
     # ---- row-axpy microbenchmark (oaxpy, 3*T bytes per op) on a matrix >> L2
     row_axpy = None
@@ -319,70 +475,84 @@ def run_own(args, rank, world, local_rank):
         row_axpy = {"unit": "GB/s", "peak": peak, "ops_per_launch": half, "bytes_per_op": 3 * T,
                     "matrix_bytes": rows * T, **res}
     clocks = sampler.stop() if rank == 0 else None
+    for sv in encs + dsets[0] + dsets[1]:
+        sv.close()
+    pool.shutdown()
+    nb.release_cached()  # the resident blocks' HBM and pinned memory go back before the host-to-host arms
 
-    # ---- e2e: host buffers through nanorq.h (bench/rq_roundtrip.c)
-    rt_so = os.path.join(nb.api.LIB_DIR, "librq_roundtrip.so")
-    # 1.25 worker threads per host core: a thread that waits for its block's solve yields its core
-    threads = max(1, min(args.threads or (5 * (os.cpu_count() or 1)) // (4 * world), 64))
-    for w in range(0 if args.skip_e2e else max(args.warmup, 3)):
-        roundtrip(rt_so, NB, threads, 900 + w)  # full-size steps: every worker gets its contexts and buffers
-    barrier()
-    nb.host_profile(reset=True)
-    slow0 = nb.slow_path_counters()
-    h0, d0 = nb.transfer_bytes()
-    l1 = nb.kernel_launches()
-    parts, t_e2e = np.zeros(4), 0.0
-    for s in range(0 if args.skip_e2e else args.steps):
-        # wall_s: start barrier -> last worker done, inside the harness (payload generation
-        # and the byte-for-byte verification of the decoded output are outside, as in benchmark.c)
-        r = roundtrip(rt_so, NB, threads, 10 * rank + s)
-        parts += [r.t_gen, r.t_emit, r.t_add, r.t_repair]
-        t_e2e += r.wall_s
-    barrier()
-    h1, d1 = nb.transfer_bytes()
-    host_prof = nb.host_profile() if os.environ.get("NANORQ_B200_PROFILE") == "1" else None
-    e2e_launches = nb.kernel_launches() - l1
-    t_e2e = max_over_ranks(t_e2e)
-    e2e = None if args.skip_e2e else {"value": gbits(NB * world * args.steps, t_e2e), "unit": "Gbit/s",
-           "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
-           "host_threads": threads, "api": "nanorq.h (bench/rq_roundtrip.c)", "ms_per_step": 1e3 * t_e2e / args.steps,
-           "gpu_launches": e2e_launches,
-           "phase_seconds_summed_over_threads": dict(zip(("generate_symbols", "encode_emit", "add_symbol", "repair_block"),
-                                                         [float(x) for x in parts]))}
-    if e2e is not None:
-        # allocations / arena regrowths / new contexts inside the timed e2e steps: must be all zero in steady state
-        e2e["slow_path_events"] = {k: v - slow0[k] for k, v in nb.slow_path_counters().items()}
-    if e2e is not None and host_prof is not None:
-        e2e["host_profile_seconds_summed_over_threads"] = {k: round(v, 4) for k, v in host_prof.items()}
+    # ---- e2e arms: host buffers through nanorq.h (per-symbol, the drop-in arm) and nanorq_batch.h
+    NBE = e2e_blocks(threads)
+
+    def e2e_arm(so, fn, label):
+        if args.skip_e2e:
+            return None
+        for w in range(max(args.warmup, 3)):
+            roundtrip(so, NBE, threads, 900 + w, fn=fn)  # full-size steps: every worker gets its contexts and buffers
+        barrier()
+        nb.host_profile(reset=True)
+        slow0 = nb.slow_path_counters()
+        hh0, dd0 = nb.transfer_bytes()
+        ll = nb.kernel_launches()
+        parts, t_e2e = np.zeros(4), 0.0
+        for s in range(args.steps):
+            # wall_s: start barrier -> last worker done, inside the harness (payload generation and the
+            # byte-for-byte verification of the decoded output are outside, as in benchmark.c)
+            r = roundtrip(so, NBE, threads, 10 * rank + s, fn=fn)
+            parts += [r.t_gen, r.t_emit, r.t_add, r.t_repair]
+            t_e2e += r.wall_s
+        barrier()
+        hh1, dd1 = nb.transfer_bytes()
+        prof = nb.host_profile() if os.environ.get("NANORQ_B200_PROFILE") == "1" else None
+        t_e2e = max_over_ranks(t_e2e)
+        out = {"value": gbits(NBE * world * args.steps, t_e2e), "unit": "Gbit/s",
+               "h2d_bytes_per_step": (hh1 - hh0) // args.steps, "d2h_bytes_per_step": (dd1 - dd0) // args.steps,
+               "host_threads": threads, "blocks_per_step": NBE * world, "api": label,
+               "ms_per_step": 1e3 * t_e2e / args.steps, "gpu_launches": nb.kernel_launches() - ll,
+               "phase_seconds_summed_over_threads": dict(zip(("generate_symbols", "encode_emit", "add_symbol", "repair_block"),
+                                                             [float(x) for x in parts])),
+               # allocations / arena regrowths / new contexts inside the timed steps: all zero in steady state
+               "slow_path_events": {k: v - slow0[k] for k, v in nb.slow_path_counters().items()}}
+        if prof is not None:
+            out["host_profile_seconds_summed_over_threads"] = {k: round(v, 4) for k, v in prof.items()}
+        return out
+
+    e2e = e2e_arm(os.path.join(nb.api.LIB_DIR, "librq_roundtrip.so"), "rq_roundtrip_run",
+                  "nanorq.h per-symbol calls, pageable buffers (bench/rq_roundtrip.c, the source the reference arm runs)")
+    e2e_batch = e2e_arm(os.path.join(nb.api.LIB_DIR, "librq_roundtrip_batch.so"), "rq_roundtrip_batch_run",
+                        "nanorq_batch.h range calls, page-locked buffers (bench/rq_roundtrip_batch.c)")
 
     # ---- cpu_baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
     ref_so = os.path.join(ROOT, "oracle", "_ref", "librq_roundtrip_ref.so")
     if rank == 0 and world == 1 and not args.skip_cpu and os.path.exists(ref_so):
-        roundtrip(ref_so, 2, 1, 77, precalc=0)
+        roundtrip(ref_so, 2, 1, 77, zblocks=2)
         tot, nblk = 0.0, 0
         while tot < args.cpu_seconds:
-            r = roundtrip(ref_so, 16, 1, nblk, precalc=0)
+            r = roundtrip(ref_so, 16, 1, nblk, zblocks=ZBLOCKS)
             tot += r.wall_s
             nblk += 16
         cpu = {"value": gbits(nblk, tot), "unit": "Gbit/s", "cores": 1, "kind": "reference",
-               "sample": "%d blocks of K=%d T=%d, full round trip through nanorq.h (bench/rq_roundtrip.c) on 1 of %d host "
-                         "cores, unmodified reference AVX2 build (oracle/_ref)" % (nblk, K, T, os.cpu_count() or 1)}
+               "sample": "%d blocks of K=%d T=%d in objects of %d blocks with nanorq_precalculate, full round trip through "
+                         "nanorq.h (bench/rq_roundtrip.c) on 1 of %d host cores, unmodified reference AVX2 build "
+                         "(oracle/_ref)" % (nblk, K, T, ZBLOCKS, os.cpu_count() or 1)}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C3: K=4096 T=1280 loss=10%% overhead=0, %d independent blocks per GPU per step" % NB,
-                       "blocks_per_gpu": NB, "sharding": "independent source blocks per rank, no collective",
+            "config": {"workload": config_workload(NB, NBE), "blocks_per_gpu": NB, "e2e_blocks_per_step": NBE * world,
+                       "zblocks": ZBLOCKS, "sharding": "independent source blocks per rank, no collective",
                        "l2": "inputs larger than L2 (%.0f MB of symbols read per step)" % (2 * NB * F / 1e6),
-                       "value_scope": "symbols and solve programs resident in HBM; host schedule construction is inside e2e"},
-            "roofline": roofline, "row_axpy": row_axpy, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks,
+                       "value_scope": "benchmark scope: symbols resident in HBM; a fresh loss pattern per block per step is "
+                                      "analysed on the host (%d threads) and its solve program built and uploaded INSIDE the "
+                                      "timed region, overlapped with the previous step's kernels; wall clock between device "
+                                      "synchronisations" % threads,
+                       "host_plan_ms_per_block_one_thread": plan_ms},
+            "kernel_only": kernel_only, "c4_literal": c4,
+            "roofline": roofline, "row_axpy": row_axpy, "cpu_baseline": cpu, "e2e": e2e, "e2e_batch": e2e_batch,
+            "gpu_launches": launches, "h2d_bytes_per_step": (h1 - h0) // args.steps, "clocks": clocks,
         }))
-    for s in encs + decs:
-        s.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -395,7 +565,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--blocks", type=int, default=118,
                     help="source blocks per GPU per step (118 blocks x 5 column slices of 256 bytes fill the 148 x 4 resident CTA slots once)")
-    ap.add_argument("--threads", type=int, default=0, help="host threads for the e2e arm (default: cores / ranks)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads of a rank, all arms (default: cores / ranks)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-rowaxpy", action="store_true")

@@ -16,8 +16,15 @@
  * as were dropped, plus `overhead`).  If the decoder reports "need more"
  * (singular matrix) two further repair symbols are fed and the repair retried.
  *
- * Threads: `nthreads` workers take blocks from a shared counter; objects are
- * per block, so no nanorq object is shared between threads.
+ * Objects: the blocks are grouped into objects of `zblocks` source blocks each
+ * (nanorq_encoder_new_ex(Z*K*T, T, K, 0, 8) => Z blocks of K symbols), the way an
+ * application sends a large object; nanorq_precalculate is called once per object so
+ * that an implementation which keeps a per-object schedule (the reference: rq->S,
+ * lib/nanorq.c:219-221,393-401) amortises it over the object's blocks.  zblocks = 1
+ * gives one object per block.  Per-block state is released with
+ * nanorq_encoder_cleanup as soon as a block is done.
+ * Threads: `nthreads` workers take objects from a shared counter; no nanorq object is
+ * shared between threads.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
@@ -38,6 +45,7 @@ typedef struct {
   int nthreads;
   int precalc; /* call nanorq_precalculate before generate_symbols */
   int verify;  /* compare decoded bytes with the payload (after the clock stops) */
+  int zblocks; /* source blocks per object (0 or 1: one object per block) */
 } rt_config;
 
 typedef struct {
@@ -78,9 +86,9 @@ typedef struct {
   double t_start, t_done;
 } worker;
 
-static int take(worker *w) {
+static int take(worker *w, int nobj) {
   pthread_mutex_lock(w->mu);
-  int b = *w->next < w->cfg->nblocks ? (*w->next)++ : -1;
+  int b = *w->next < nobj ? (*w->next)++ : -1;
   pthread_mutex_unlock(w->mu);
   return b;
 }
@@ -89,68 +97,82 @@ static void *work(void *arg) {
   worker *w = arg;
   const rt_config *c = w->cfg;
   const size_t K = (size_t)c->K, T = (size_t)c->T, F = K * T;
+  const int Z = c->zblocks > 1 ? c->zblocks : 1, nobj = (c->nblocks + Z - 1) / Z;
   const size_t max_pk = 2 * K + (size_t)c->overhead + 64;
   uint8_t *pk = malloc(max_pk * T);
   uint32_t *tags = malloc(max_pk * sizeof(uint32_t));
   memset(pk, 0, max_pk * T); /* fault the packet buffer in before the clock starts */
   pthread_barrier_wait(w->bar);
   w->t_start = now_s();
-  for (int b; (b = take(w)) >= 0;) {
-    uint32_t rs = (c->seed + 0x9e3779b9u * (uint32_t)(b + 1)) | 1u;
+  for (int o; (o = take(w, nobj)) >= 0;) {
+    const int b0 = o * Z, zb = c->nblocks - b0 < Z ? c->nblocks - b0 : Z; /* blocks b0 .. b0+zb-1 are this object */
     const uint32_t thresh = (uint32_t)(c->loss * 4294967296.0 > 4294967295.0 ? 4294967295.0 : c->loss * 4294967296.0);
-    /* ---- sender */
-    nanorq *enc = nanorq_encoder_new_ex(F, (uint16_t)T, (uint16_t)K, 0, 8);
-    if (!enc) { w->acc.failures++; continue; }
-    struct ioctx *in = ioctx_from_mem(w->payload[b], F);
+    /* ---- sender and receiver objects (payload and decoded output of an object are contiguous) */
+    nanorq *enc = nanorq_encoder_new_ex(F * (size_t)zb, (uint16_t)T, (uint16_t)K, 0, 8);
+    if (!enc || nanorq_blocks(enc) != (size_t)zb) {
+      w->acc.failures += zb;
+      if (enc) nanorq_free(enc);
+      continue;
+    }
+    struct ioctx *in = ioctx_from_mem(w->payload[b0], F * (size_t)zb);
     if (c->precalc) nanorq_precalculate(enc);
-    double t0 = now_s();
-    bool ok = nanorq_generate_symbols(enc, 0, in);
-    double t1 = now_s();
-    size_t n = 0, lost = 0;
-    for (uint32_t esi = 0; esi < K && ok; esi++) {
-      if (xs32(&rs) < thresh) { lost++; continue; }
-      tags[n] = nanorq_tag(0, esi);
-      ok = nanorq_encode(enc, pk + n * T, esi, 0, in) == T;
-      n++;
+    nanorq *dec = nanorq_decoder_new(nanorq_oti_common(enc), nanorq_oti_scheme_specific(enc));
+    struct ioctx *out = ioctx_from_mem(w->decoded[b0], F * (size_t)zb);
+    if (!dec) {
+      w->acc.failures += zb;
+      in->destroy(in);
+      out->destroy(out);
+      nanorq_free(enc);
+      continue;
     }
-    uint32_t next_rep = (uint32_t)K;
-    for (size_t k = 0; k < lost + (size_t)c->overhead && ok; k++, n++, next_rep++) {
-      tags[n] = nanorq_tag(0, next_rep);
-      ok = nanorq_encode(enc, pk + n * T, next_rep, 0, in) == T;
-    }
-    double t2 = now_s();
-    uint64_t oti_c = nanorq_oti_common(enc);
-    uint32_t oti_s = nanorq_oti_scheme_specific(enc);
-    /* ---- receiver */
-    nanorq *dec = ok ? nanorq_decoder_new(oti_c, oti_s) : NULL;
-    struct ioctx *out = ioctx_from_mem(w->decoded[b], F);
-    bool done = false;
-    double t3 = t2, t4 = t2;
-    if (dec) {
+    for (int z = 0; z < zb; z++) {
+      const uint8_t sbn = (uint8_t)z;
+      uint32_t rs = (c->seed + 0x9e3779b9u * (uint32_t)(b0 + z + 1)) | 1u;
+      double t0 = now_s();
+      bool ok = nanorq_generate_symbols(enc, sbn, in);
+      double t1 = now_s();
+      size_t n = 0, lost = 0;
+      for (uint32_t esi = 0; esi < K && ok; esi++) {
+        if (xs32(&rs) < thresh) { lost++; continue; }
+        tags[n] = nanorq_tag(sbn, esi);
+        ok = nanorq_encode(enc, pk + n * T, esi, sbn, in) == T;
+        n++;
+      }
+      uint32_t next_rep = (uint32_t)K;
+      for (size_t k = 0; k < lost + (size_t)c->overhead && ok; k++, n++, next_rep++) {
+        tags[n] = nanorq_tag(sbn, next_rep);
+        ok = nanorq_encode(enc, pk + n * T, next_rep, sbn, in) == T;
+      }
+      double t2 = now_s();
+      /* ---- receiver */
       for (size_t k = 0; k < n; k++)
         if (nanorq_decoder_add_symbol(dec, pk + k * T, tags[k], out) == NANORQ_SYM_ERR) ok = false;
-      t3 = now_s();
-      done = ok && nanorq_repair_block(dec, out, 0);
-      t4 = now_s();
+      double t3 = now_s();
+      bool done = ok && nanorq_repair_block(dec, out, sbn);
+      double t4 = now_s();
       for (int retry = 0; ok && !done && retry < 8; retry++) {
         if (retry == 0) w->acc.retries++;
         for (int x = 0; x < 2 && n < max_pk; x++, n++, next_rep++) {
-          tags[n] = nanorq_tag(0, next_rep);
-          if (nanorq_encode(enc, pk + n * T, next_rep, 0, in) != T) ok = false;
+          tags[n] = nanorq_tag(sbn, next_rep);
+          if (nanorq_encode(enc, pk + n * T, next_rep, sbn, in) != T) ok = false;
           nanorq_decoder_add_symbol(dec, pk + n * T, tags[n], out);
         }
-        done = ok && nanorq_repair_block(dec, out, 0);
+        done = ok && nanorq_repair_block(dec, out, sbn);
         t4 = now_s();
       }
+      if (!done) w->acc.failures++;
+      w->acc.t_gen += t1 - t0;
+      w->acc.t_emit += t2 - t1;
+      w->acc.t_add += t3 - t2;
+      w->acc.t_repair += t4 - t3;
+      w->acc.n_lost += (long)lost;
+      w->acc.n_sent += (long)n;
+      /* this block is finished on both sides: release its state (the encoder's per-block matrices
+       * in the reference, lib/nanorq.c:437-451; a no-op for a decoder object there) */
+      nanorq_encoder_cleanup(enc, sbn);
+      nanorq_encoder_cleanup(dec, sbn);
     }
-    if (!done) w->acc.failures++;
-    w->acc.t_gen += t1 - t0;
-    w->acc.t_emit += t2 - t1;
-    w->acc.t_add += t3 - t2;
-    w->acc.t_repair += t4 - t3;
-    w->acc.n_lost += (long)lost;
-    w->acc.n_sent += (long)n;
-    if (dec) nanorq_free(dec);
+    nanorq_free(dec);
     out->destroy(out);
     in->destroy(in);
     nanorq_free(enc);
@@ -165,12 +187,15 @@ int rq_roundtrip_run(const rt_config *cfg, rt_result *res) {
   memset(res, 0, sizeof(*res));
   if (cfg->K < 1 || cfg->T < 1 || cfg->nblocks < 1 || cfg->nthreads < 1) return -1;
   const size_t F = (size_t)cfg->K * (size_t)cfg->T;
-  const int nb = cfg->nblocks, nt = cfg->nthreads < nb ? cfg->nthreads : nb;
+  const int nb = cfg->nblocks, nobjs = (nb + (cfg->zblocks > 1 ? cfg->zblocks : 1) - 1) / (cfg->zblocks > 1 ? cfg->zblocks : 1);
+  const int nt = cfg->nthreads < nobjs ? cfg->nthreads : nobjs;
   uint8_t **payload = calloc((size_t)nb, sizeof(*payload)), **decoded = calloc((size_t)nb, sizeof(*decoded));
+  /* the blocks of an object are contiguous: one arena each for payloads and decoded output */
+  uint8_t *pay_arena = malloc((size_t)nb * F + 4), *dec_arena = malloc((size_t)nb * F + 4);
   for (int b = 0; b < nb; b++) {
-    payload[b] = malloc(F + 4);
-    decoded[b] = malloc(F + 4);
-    memset(decoded[b], 0, F + 4); /* faulted in before the clock starts, like the payload and packet buffers */
+    payload[b] = pay_arena + (size_t)b * F;
+    decoded[b] = dec_arena + (size_t)b * F;
+    memset(decoded[b], 0, F); /* faulted in before the clock starts, like the payload and packet buffers */
     uint32_t s = cfg->seed + 42u + (uint32_t)b;
     if (!s) s = 1;
     for (size_t k = 0; k < F; k += 4) {
@@ -213,9 +238,9 @@ int rq_roundtrip_run(const rt_config *cfg, rt_result *res) {
   for (int b = 0; b < nb; b++) {
     if (cfg->verify && memcmp(payload[b], decoded[b], F) != 0) res->mismatches++;
     for (size_t k = 0; k < F; k++) h = (h ^ decoded[b][k]) * 1099511628211ULL;
-    free(payload[b]);
-    free(decoded[b]);
   }
+  free(pay_arena);
+  free(dec_arena);
   res->out_fnv = h;
   pthread_barrier_destroy(&bar);
   free(payload);

@@ -208,6 +208,13 @@ static size_t transfer_symbol(nanorq *rq, uint8_t sbn, uint32_t esi, uint8_t *pt
   return out ? io->write(io, ptr, n) : io->read(io, ptr, n);
 }
 
+#ifdef RQB_EXPERIMENTS
+#include <stdio.h>
+static int xp(const char *name) { const char *e = getenv(name); return e && *e == '1'; }
+#else
+#define xp(name) 0
+#endif
+
 static void block_free(struct block *b) {
   if (!b) return;
   rqb_solver_destroy(b->sv);
@@ -297,7 +304,7 @@ static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *i
     /* page-locked caller memory: the copy engine reads the block where it lies (no staging copy);
      * only a short last symbol goes through a zero-padded staging row */
     const uint32_t full = (uint32_t)(bytes / rq->T);
-    if (rqb_solver_upload_rows(b->sv, 0, full, span, rq->T)) return false;
+    if (!xp("XP_NO_PAYLOAD_H2D") && rqb_solver_upload_rows(b->sv, 0, full, span, rq->T)) return false;
     if (full < b->K) {
       uint8_t *row = rqb_solver_staging(b->sv) + (size_t)full * b->pitch;
       memcpy(row, span + (size_t)full * rq->T, bytes - (size_t)full * rq->T);
@@ -436,7 +443,7 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
    * destination is page-locked) -- the host never touches the bytes */
   if (esi < b->K) {
     const uint32_t m = b->K - esi < left ? b->K - esi : left;
-    if (rqb_solver_fetch_rows(b->sv, 0, esi, m, out, pitch, 0)) return 0;
+    if (!xp("XP_NO_SRC_D2H") && rqb_solver_fetch_rows(b->sv, 0, esi, m, out, pitch, 0)) return 0;
     out += (size_t)m * pitch;
     esi += m;
     left -= m;
@@ -626,7 +633,7 @@ int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *dat
       int st = q < take ? classify(rq, b, esi) : NANORQ_SYM_ERR;
       if (st == NANORQ_SYM_ADDED) {
         if (!copied) { /* first accepted symbol of the run: queue the copy of the run's rows */
-          if (!flush_staged(b) || rqb_solver_upload_rows(b->sv, row0, (uint32_t)take, rows + k * pitch, pitch)) {
+          if (!flush_staged(b) || (!xp("XP_NO_RING_H2D") && rqb_solver_upload_rows(b->sv, row0, (uint32_t)take, rows + k * pitch, pitch))) {
             st = NANORQ_SYM_ERR;
           } else {
             copied = true;
@@ -669,9 +676,9 @@ size_t nanorq_num_repair(nanorq *rq, uint8_t sbn) { /* :519-525 */
  * memory with one copy */
 static bool write_block_image(nanorq *rq, struct block *b, const uint32_t *have_esi, const uint32_t *have_row,
                               uint32_t n_have) {
-  if (rqb_solver_copy_in_to_sym(b->sv, have_esi, have_row, n_have)) return false;
+  if (!xp("XP_NO_COPYROWS") && rqb_solver_copy_in_to_sym(b->sv, have_esi, have_row, n_have)) return false;
   const uint32_t full = (uint32_t)(b->out_bytes / rq->T);
-  if (full && rqb_solver_fetch_rows(b->sv, 1, 0, full, b->out_mem, rq->T, 0)) return false;
+  if (!xp("XP_NO_IMAGE_D2H") && full && rqb_solver_fetch_rows(b->sv, 1, 0, full, b->out_mem, rq->T, 0)) return false;
   if (full < b->K && b->out_bytes > (size_t)full * rq->T) { /* the object's short last symbol */
     if (rqb_solver_fetch_syms(b->sv, full, 1, NULL, 0)) return false;
     memcpy(b->out_mem + (size_t)full * rq->T, rqb_solver_sym_mirror(b->sv) + (size_t)full * b->pitch,

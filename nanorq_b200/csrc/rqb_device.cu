@@ -675,6 +675,20 @@ rqb_copy_rows_kernel(uint8_t *__restrict__ base, size_t pitch, const uint32_t *_
   }
 }
 
+// dst row k (dpitch apart) = src row k (spitch apart), `width` bytes each: re-pitches rows on the device
+// so that host<->device copies are always linear (a 2-D DMA of ~1 KB rows reaches a fifth of the link)
+template <typename V>
+__global__ void __launch_bounds__(256)
+rqb_repitch_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *__restrict__ src, size_t spitch,
+                   uint32_t vpr /* V per row */, uint32_t n) {
+  const uint64_t total = (uint64_t)n * vpr;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(g / vpr), v = (uint32_t)(g - (uint64_t)r * vpr);
+    reinterpret_cast<V *>(dst + (size_t)r * dpitch)[v] = reinterpret_cast<const V *>(src + (size_t)r * spitch)[v];
+  }
+}
+
 // ------------------------------------------------------------------- shim
 static thread_local char g_err[256] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -1013,6 +1027,24 @@ int rqb_launch_copy_rows(uint8_t *base, size_t pitch, const uint32_t *pairs_dev,
   const uint32_t vpr = width / 16;
   rqb_copy_rows_kernel<<<stream_grid((uint64_t)n * vpr, 256), 256, 0, (cudaStream_t)stream>>>(base, pitch, pairs_dev,
                                                                                                n, vpr);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rqb_launch_repitch(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, uint32_t width, uint32_t n,
+                       void *stream) {
+  if (n == 0 || width == 0) return 0;
+  const uintptr_t al = (uintptr_t)dst | (uintptr_t)src | dpitch | spitch | width;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (al % 16 == 0)
+    rqb_repitch_kernel<uint4><<<stream_grid((uint64_t)n * (width / 16), 256), 256, 0, st>>>(dst, dpitch, src, spitch, width / 16, n);
+  else if (al % 8 == 0)
+    rqb_repitch_kernel<uint2><<<stream_grid((uint64_t)n * (width / 8), 256), 256, 0, st>>>(dst, dpitch, src, spitch, width / 8, n);
+  else if (al % 4 == 0)
+    rqb_repitch_kernel<uint32_t><<<stream_grid((uint64_t)n * (width / 4), 256), 256, 0, st>>>(dst, dpitch, src, spitch, width / 4, n);
+  else
+    rqb_repitch_kernel<uint8_t><<<stream_grid((uint64_t)n * width, 256), 256, 0, st>>>(dst, dpitch, src, spitch, width, n);
   g_launches++;
   CK(cudaGetLastError());
   return 0;

@@ -100,6 +100,10 @@ int rqb_launch_gather_rows(uint8_t *dst, size_t dpitch, const uint8_t *src, size
 int rqb_launch_copy_rows(uint8_t *base, size_t pitch, const uint32_t *pairs_dev, uint32_t n, uint32_t width,
                          void *stream);
 
+/* dst row k = src row k for n rows of `width` bytes with different pitches, all on the device */
+int rqb_launch_repitch(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, uint32_t width, uint32_t n,
+                       void *stream);
+
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 unsigned long long rqb_dev_launch_count(void);
 /* bytes moved by rqb_copy* so far */

@@ -9,13 +9,16 @@ import nanorq_b200 as nb
 K, T, loss, oh, nblk, nthr = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 steps = int(sys.argv[7]) if len(sys.argv) > 7 else 5
 nb.lib()
-for name, so, fn in (("per-symbol", "librq_roundtrip.so", "rq_roundtrip_run"), ("batch", "librq_roundtrip_batch.so", "rq_roundtrip_batch_run")):
+ARMS = (("per-symbol", "librq_roundtrip.so", "rq_roundtrip_run"), ("batch", "librq_roundtrip_batch.so", "rq_roundtrip_batch_run"))
+if os.environ.get("XP_NOVERIFY"):
+    ARMS = ARMS[1:]
+for name, so, fn in ARMS:
     L = C.CDLL(os.path.join(nb.api.LIB_DIR, so))
     f = getattr(L, fn)
     f.argtypes = [C.POINTER(bench.RtConfig), C.POINTER(bench.RtResult)]
     vals = []
     for s in range(steps + 2):
-        cfg = bench.RtConfig(K, T, nblk, loss, oh, 100 + s, nthr, 1, 1)
+        cfg = bench.RtConfig(K, T, nblk, loss, oh, 100 + s, nthr, 1, 0 if os.environ.get('XP_NOVERIFY') else 1)
         res = bench.RtResult()
         sp0 = nb.slow_path_counters()
         rc = f(C.byref(cfg), C.byref(res))
