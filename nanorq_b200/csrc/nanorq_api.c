@@ -49,6 +49,7 @@ struct block {
   uint32_t win_first, win_n, win_cap;
   bool win_pending; /* the window's copy to the host is queued but not waited for */
   bool win_on_host; /* the pinned mirror holds the current window */
+  bool deferred;    /* generate_symbols was asked for, the solve is queued when a repair symbol is needed */
   uint32_t loaded_rows; /* staging rows already queued for upload */
   const uint8_t *src_mem; /* encoder loaded by DMA from a page-locked memory ioctx: the block's bytes there */
   size_t src_bytes;
@@ -295,12 +296,15 @@ int nanorq_set_devices(nanorq *rq, int n) {
 }
 
 /* ------------------------------------------------------------------ encoder */
+#define LAZY_MAX_SYMBOLS 256u /* blocks up to this size are solved on demand, see nanorq_generate_symbols */
+#define LAZY_MAX_BYTES (256u << 10)
+
 static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
   b->loaded_rows = 0;
   int pinned = 0;
   size_t bytes = 0;
   uint8_t *span = block_span(rq, sbn, b, io, &bytes, &pinned);
-  if (span && pinned) {
+  if (span && pinned && !(b->K <= LAZY_MAX_SYMBOLS && bytes <= LAZY_MAX_BYTES)) {
     /* page-locked caller memory: the copy engine reads the block where it lies (no staging copy);
      * only a short last symbol goes through a zero-padded staging row */
     const uint32_t full = (uint32_t)(bytes / rq->T);
@@ -333,30 +337,50 @@ static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *i
   return true;
 }
 
-bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :206-232 */
-  struct block *b = get_block(rq, sbn);
-  if (!b) return false;
-  if (b->inverted) return true;
+/* queue the upload of what is still in the staging rows, the solve and the first window of repair
+ * symbols (the program is cached per K: cf. rq->S :219-221); nothing here waits for the device */
+static bool launch_solve(struct block *b) {
   PF_T0;
-  if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
-  if (!b->loaded) return false;
-  PF(RQB_PF_GEN_LOAD);
   if (rqb_solver_upload(b->sv, b->loaded_rows, b->K - b->loaded_rows)) return false;
   b->loaded_rows = b->K;
   PF(RQB_PF_GEN_UPLOAD);
-  /* the program (cached per K: cf. rq->S :219-221) also emits the first window of
-   * repair symbols, ESI K.. ; nothing here waits for the device -- the first
-   * nanorq_encode of a repair symbol does */
   if (rqb_solver_plan_encode(b->sv, 1, b->win_cap)) return false;
   PF(RQB_PF_GEN_PLAN);
   if (rqb_solver_run(b->sv)) return false;
   PF(RQB_PF_GEN_RUN);
   b->inverted = true;
+  b->deferred = false;
   b->win_first = b->K;
   b->win_n = b->win_cap;
   b->win_pending = false;
   b->win_on_host = false; /* the window stays on the device until a per-symbol call asks for one of its symbols */
   return true;
+}
+
+/* Small blocks are solved on demand: a solve that nobody needs -- every transfer without loss -- costs a
+ * launch and a stream wait, more than all the host work on a block of a few KB, and when repair
+ * symbols are asked for after all a solve this small takes tens of microseconds.  Large blocks are
+ * solved right away so that the solve overlaps the emission of the source symbols. */
+bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :206-232 */
+  struct block *b = get_block(rq, sbn);
+  if (!b) return false;
+  if (b->inverted || b->deferred) return true;
+  PF_T0;
+  if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
+  if (!b->loaded) return false;
+  PF(RQB_PF_GEN_LOAD);
+  if (b->K <= LAZY_MAX_SYMBOLS && (size_t)b->K * rq->T <= LAZY_MAX_BYTES) {
+    b->deferred = true;
+    return true;
+  }
+  return launch_solve(b);
+}
+
+/* the intermediate symbols are needed now */
+static bool ensure_solved(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
+  if (b->inverted) return true;
+  if (!b->deferred && !nanorq_generate_symbols(rq, sbn, io)) return false;
+  return b->inverted || launch_solve(b);
 }
 
 bool nanorq_precalculate(nanorq *rq) { /* :393-401 */
@@ -408,7 +432,7 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
     return rq->T;
   }
   if (esi > ((1u << 24) - 1)) return 0;
-  if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  if (!ensure_solved(rq, sbn, b, io)) return 0;
   PF_T0;
   if (b->win_pending) { /* the solve and the copy of the first window were queued by generate_symbols */
     if (rqb_solver_sync(b->sv)) return 0;
@@ -435,7 +459,15 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
   struct block *b = rq ? get_block(rq, sbn) : NULL;
   if (!b || b->mask || !dst || pitch < rq->T || n == 0 || (uint64_t)esi0 + n > (1u << 24)) return 0;
   PF_T0;
-  if (!b->inverted && !nanorq_generate_symbols(rq, sbn, io)) return 0;
+  if (esi0 + n <= b->K && !b->inverted) { /* source symbols only and nothing solved yet: they are the loaded bytes */
+    if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
+    if (!b->loaded) return 0;
+    if (b->K <= LAZY_MAX_SYMBOLS) {
+      for (uint32_t k = 0; k < n; k++) copy_source_symbol(rq, b, esi0 + k, (uint8_t *)dst + (size_t)k * pitch);
+      return n;
+    }
+  }
+  if (!ensure_solved(rq, sbn, b, io)) return 0;
   PF(RQB_PF_RANGE_GEN);
   uint8_t *out = dst;
   uint32_t esi = esi0, left = n;
@@ -477,7 +509,7 @@ void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
   struct block *b = rq->blocks[sbn];
   if (!b) return;
   if (b->win_pending || b->src_mem) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
-  b->loaded = b->inverted = b->win_pending = b->win_on_host = false;
+  b->loaded = b->inverted = b->win_pending = b->win_on_host = b->deferred = false;
   b->win_n = 0;
   b->loaded_rows = 0;
   b->src_mem = NULL;
@@ -557,7 +589,9 @@ static bool deferred_output(nanorq *rq, uint8_t sbn, struct block *b, struct ioc
   size_t bytes = 0;
   uint8_t *span = block_span(rq, sbn, b, io, &bytes, &pinned);
   b->out_decided = true;
-  if (span && pinned) {
+  /* a block of a few KB is written by the CPU as its symbols arrive: handing it back through the
+   * device would cost a kernel, a copy and a stream wait for less than a page of data */
+  if (span && pinned && bytes > LAZY_MAX_BYTES) {
     b->out_mem = span;
     b->out_bytes = bytes;
   }

@@ -342,10 +342,16 @@ static rqb_solver *g_shells, **g_shells_tail = &g_shells;
 
 /* arena rows a fresh context gets: the fixed spaces plus room for the working rows of
  * a typical program (about 3.5 L, up to 6 L with the table rows of the back-substitution; 8 L reserved; the arena is regrown if a program needs more) */
+static long g_ws_reserve = -1; /* NANORQ_B200_WS_RESERVE (tests: start small to exercise the regrowth); -1 = not set */
+static pthread_once_t g_ws_once = PTHREAD_ONCE_INIT;
+static void ws_reserve_init(void) {
+  const char *e = getenv("NANORQ_B200_WS_RESERVE");
+  if (e && *e) g_ws_reserve = (long)strtoul(e, NULL, 10);
+}
 static size_t arena_rows_wanted(uint32_t max_in, uint32_t max_out, const rqb_params *P) {
   size_t ws = 8 * (size_t)P->L + 1024;
-  const char *e = getenv("NANORQ_B200_WS_RESERVE"); /* tests: start small to exercise the regrowth */
-  if (e && *e) ws = (size_t)strtoul(e, NULL, 10);
+  pthread_once(&g_ws_once, ws_reserve_init);
+  if (g_ws_reserve >= 0) ws = (size_t)g_ws_reserve;
   return (size_t)max_in + max_out + (size_t)P->L + 1 + ws;
 }
 
@@ -422,14 +428,28 @@ void rqb_solver_destroy(rqb_solver *s) {
   }
   s->next_shell = NULL;
   rqb_solver *evict = NULL, **evict_tail = &evict;
-  pthread_mutex_lock(&g_shell_mu); /* appended at the tail: the list is oldest-first */
-  *g_shells_tail = s;
-  g_shells_tail = &s->next_shell;
+  pthread_mutex_lock(&g_shell_mu);
+  if (s->busy || !g_shells) { /* work still queued: at the tail (oldest first) */
+    *g_shells_tail = s;
+    g_shells_tail = &s->next_shell;
+  } else { /* idle: at the head (most recently used first) */
+    s->next_shell = g_shells;
+    g_shells = s;
+  }
   g_shell_bytes += solver_bytes(s);
-  while (g_shells && g_shells != s && g_pool_bytes + g_shell_bytes > cache_limit()) {
-    rqb_solver *old = g_shells;
-    g_shells = old->next_shell;
-    if (!g_shells) g_shells_tail = &g_shells;
+  while (g_pool_bytes + g_shell_bytes > cache_limit()) {
+    /* over the limit: the least recently used idle context goes (the last idle one in the list), or,
+     * when none is idle, the oldest one with work still queued; never the one just parked */
+    rqb_solver **victim = NULL;
+    for (rqb_solver **pp = &g_shells; *pp; pp = &(*pp)->next_shell) {
+      if (*pp == s) continue;
+      if (!(*pp)->busy) victim = pp;
+      else if (!victim) victim = pp;
+    }
+    if (!victim) break;
+    rqb_solver *old = *victim;
+    *victim = old->next_shell;
+    if (g_shells_tail == &old->next_shell) g_shells_tail = victim;
     g_shell_bytes -= solver_bytes(old);
     old->next_shell = NULL;
     *evict_tail = old;
@@ -496,25 +516,23 @@ int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, siz
   rqb_solver *s = NULL;
   pthread_mutex_lock(&g_shell_mu);
   {
-    /* best fit, and never a context much larger than asked for: encoders and decoders
-     * of one block size must not keep taking each other's contexts */
+    /* never a context much larger than asked for: encoders and decoders of one block size must not
+     * keep taking each other's contexts.  Idle contexts are parked at the head of the list (most
+     * recently used first: warm, and found at once -- tiny blocks come and go every few microseconds
+     * and this walk happens under a process-wide lock); contexts with work still queued are parked
+     * at the tail (oldest first: most likely done) and only taken when no idle one fits. */
     rqb_solver **best = NULL;
+    const size_t want_bytes = arena_rows_wanted(max_in, max_out, &P);
     for (rqb_solver **pp = &g_shells; *pp; pp = &(*pp)->next_shell) {
       rqb_solver *c = *pp;
       if (c->dev != dev || c->T != T || c->in_cap < max_in || c->out_cap < max_out) continue;
-      if (c->arena_cap < arena_rows_wanted(max_in, max_out, &P) * c->pitch) continue;
+      if (c->arena_cap < want_bytes * c->pitch) continue;
       if ((size_t)c->in_cap > (size_t)max_in + max_in / 4 + 64 || (size_t)c->out_cap > (size_t)max_out + max_out / 4 + 64) continue;
-      /* an idle context before one with work still queued (oldest first: most likely done);
-       * among idle ones the tightest fit */
-      const int c_busy = c->busy;
-      if (!best) {
+      if (!c->busy) {
         best = pp;
-      } else {
-        const rqb_solver *b = *best;
-        const int b_busy = b->busy;
-        if (b_busy && !c_busy) best = pp;
-        else if (b_busy == c_busy && !c_busy && c->in_cap + c->out_cap < b->in_cap + b->out_cap) best = pp;
+        break;
       }
+      if (!best) best = pp;
     }
     if (best) {
       s = *best;

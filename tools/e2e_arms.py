@@ -18,7 +18,7 @@ for name, so, fn in ARMS:
     f.argtypes = [C.POINTER(bench.RtConfig), C.POINTER(bench.RtResult)]
     vals = []
     for s in range(steps + 2):
-        cfg = bench.RtConfig(K, T, nblk, loss, oh, 100 + s, nthr, 1, 0 if os.environ.get('XP_NOVERIFY') else 1)
+        cfg = bench.RtConfig(K, T, nblk, loss, oh, 100 + s, nthr, 1, 0 if os.environ.get('XP_NOVERIFY') else 1, int(os.environ.get('ZBLOCKS', '1')))
         res = bench.RtResult()
         sp0 = nb.slow_path_counters()
         rc = f(C.byref(cfg), C.byref(res))
