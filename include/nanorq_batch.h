@@ -48,6 +48,13 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
 int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *data, size_t pitch, size_t n,
                                int *status, struct ioctx *io);
 
+/* ---- decoder: repair several blocks of the object with ONE solve launch per device.
+ * Replaces n calls of nanorq_repair_block (lib/nanorq.c:591-631): every block's constraint matrix is
+ * analysed on the host, the solves of all blocks on one device run as a single kernel launch
+ * (gridDim.y = blocks), then the recovered symbols are written block by block.  ok[k] (optional)
+ * receives what nanorq_repair_block would have returned for sbns[k]; returns how many are true. */
+size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, size_t n, bool *ok);
+
 /* ---- devices: source blocks of one object are independent, so block sbn is solved on device
  * sbn mod n_devices (the reference's per-block state: lib/nanorq.c:57,130-146).
  * n = 0 selects every visible CUDA device; the default is 1 (the process-wide device of

@@ -107,6 +107,7 @@ def lib():
     sig("nanorq_encode_range", sz, vp, C.c_uint8, C.c_uint32, C.c_uint32, vp, sz, vp)
     sig("nanorq_decoder_add_symbols", C.c_int, vp, u32p, vp, sz, sz, C.POINTER(C.c_int), vp)
     sig("nanorq_set_devices", C.c_int, vp, C.c_int)
+    sig("nanorq_repair_blocks", sz, vp, vp, u8p, sz, C.POINTER(C.c_bool))
     # io.h
     sig("ioctx_from_file", vp, C.c_char_p, C.c_int)
     sig("ioctx_mmap_file", vp, C.c_char_p, C.c_int)
@@ -204,7 +205,7 @@ EXPORTED_SYMBOLS = [
     "rqb_ops_upload", "rqb_ops_free", "rqb_rowops_apply_dev", "rqb_schedule_replay",
     "rqb_schedule_replay_stepwise", "rqb_schedule_plan_blob",
     "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info", "rqb_plan_blob_build_ex", "rqb_smem_budget",
-    "ioctx_from_pinned_mem", "nanorq_encode_range", "nanorq_decoder_add_symbols", "nanorq_set_devices",
+    "ioctx_from_pinned_mem", "nanorq_repair_blocks", "nanorq_encode_range", "nanorq_decoder_add_symbols", "nanorq_set_devices",
     "rqb_solver_create_on", "rqb_solver_device", "rqb_solver_set_flavour", "rqb_solver_upload_rows",
     "rqb_solver_fetch_rows", "rqb_solver_copy_in_to_sym", "rqb_host_alloc", "rqb_host_release", "rqb_host_pin",
     "rqb_host_unpin",
@@ -577,6 +578,13 @@ class Decoder(_Codec):
 
     def repair_block(self, io, sbn):
         return lib().nanorq_repair_block(self.h, io.ptr, sbn)
+
+    def repair_blocks(self, io, sbns):
+        """nanorq_repair_blocks: -> list of per-block results (one solve launch per device)."""
+        arr = np.ascontiguousarray(sbns, dtype=np.uint8)
+        ok = (C.c_bool * max(1, len(arr)))()
+        lib().nanorq_repair_blocks(self.h, io.ptr, arr.ctypes.data_as(u8p), len(arr), ok)
+        return list(ok[:len(arr)])
 
 
 def tag(sbn, esi):

@@ -736,18 +736,43 @@ static bool complete_block(nanorq *rq, struct ioctx *io, uint8_t sbn, struct blo
   return ok;
 }
 
-bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-631 */
+/* One block's repair in three steps, so that several blocks can share a launch:
+ *   repair_prepare  fill_symbol_matrix_gaps + patch_precode_matrix (:527-565): request, host analysis,
+ *                   program upload;  1 = ready to run, 0 = nothing to run (done or not decodable yet:
+ *                   *result says which), -1 = the constraint matrix is singular / an error
+ *   (launch)        rqb_solver_run for one block, rqb_solver_run_batch for several
+ *   repair_finish   decode_repair_rows + write_repair_rows (:567-589) */
+struct repair_job {
+  struct block *b;
+  uint8_t sbn;
+  bool deferred;
+  uint32_t *missing, *have; /* missing ESIs; deferred output: [K] ESIs received, then [K] their input rows */
+  size_t nm, nh;
+};
+
+static void repair_job_free(struct repair_job *j) {
+  free(j->missing);
+  free(j->have);
+  j->missing = j->have = NULL;
+}
+
+static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repair_job *j, bool *result) {
+  memset(j, 0, sizeof(*j));
   struct block *b = get_block(rq, sbn);
-  if (!b || !b->mask) return false;
-  if (b->gaps == 0) return !b->out_mem || complete_block(rq, io, sbn, b);
-  if (b->nrep < b->gaps) return false;
+  *result = false;
+  if (!b || !b->mask) return 0;
+  if (b->gaps == 0) {
+    *result = !b->out_mem || complete_block(rq, io, sbn, b);
+    return 0;
+  }
+  if (b->nrep < b->gaps) return 0;
   const int Kp = rq->P.Kprime;
   const size_t gaps = b->gaps, overhead = b->nrep - gaps;
   const uint32_t pad = (uint32_t)Kp - b->K;
   const bool deferred = deferred_output(rq, sbn, b, io);
   /* the symbol bytes start moving to the GPU while the host analyses the matrix */
   PF_T0;
-  if (!flush_staged(b)) return false;
+  if (!flush_staged(b)) return -1;
   PF(RQB_PF_REP_UPLOAD);
   size_t nlt = (size_t)Kp + overhead;
   uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);
@@ -758,11 +783,10 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
     free(in_row);
     free(missing);
     free(have);
-    return false;
+    return -1;
   }
   size_t rep = 0, nm = 0, nh = 0;
-  /* fill_symbol_matrix_gaps + patch_precode_matrix (:527-565): missing source rows take
-   * the repair symbols in arrival order, the rest become overhead rows */
+  /* missing source rows take the repair symbols in arrival order, the rest become overhead rows */
   for (uint32_t e = 0; e < (uint32_t)Kp; e++) {
     if (e >= b->K) { /* padding symbol: known zero */
       isi[e] = e;
@@ -791,36 +815,114 @@ bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-63
   int rc = rqb_solver_plan(b->sv, &req); /* charges repair.plan / .pages / .args itself */
   free(isi);
   free(in_row);
+  j->b = b;
+  j->sbn = sbn;
+  j->deferred = deferred;
+  j->missing = missing;
+  j->have = have;
+  j->nm = nm;
+  j->nh = nh;
+  if (rc != 0) {
+    rqb_solver_sync(b->sv);
+    repair_job_free(j);
+    return -1;
+  }
+  return 1;
+}
+
+static bool repair_finish(nanorq *rq, struct ioctx *io, struct repair_job *j) {
+  struct block *b = j->b;
   bool ok = false;
-  if (rqb_prof_enabled()) pf_t = rqb_prof_now();
-  if (rc == 0) rc = rqb_solver_run(b->sv);
-  PF(RQB_PF_REP_RUN);
-  if (rc == 0 && deferred) {
-    ok = write_block_image(rq, b, have, have + b->K, (uint32_t)nh);
+  PF_T0;
+  if (j->deferred) {
+    ok = write_block_image(rq, b, j->have, j->have + b->K, (uint32_t)j->nh);
     PF(RQB_PF_REP_FETCH);
     if (ok) {
-      for (size_t k = 0; k < nm; k++) mask_set(b, missing[k]);
+      for (size_t k = 0; k < j->nm; k++) mask_set(b, j->missing[k]);
       b->gaps = 0;
       b->written = true;
     }
-  } else if (rc == 0) {
-    rc = rqb_solver_fetch_syms(b->sv, 0, (uint32_t)nm, NULL, 0);
+  } else if (rqb_solver_fetch_syms(b->sv, 0, (uint32_t)j->nm, NULL, 0) == 0) {
     PF(RQB_PF_REP_FETCH);
-    if (rc == 0) {
-      /* decode_repair_rows + write_repair_rows (:567-589) */
-      const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
-      for (size_t k = 0; k < nm; k++) {
-        transfer_symbol(rq, sbn, missing[k], (uint8_t *)sy + k * b->pitch, io, 1);
-        mask_set(b, missing[k]);
-      }
-      b->gaps = 0;
-      ok = true;
-      rqb_copy_fence();
-      PF(RQB_PF_REP_WRITE);
+    const uint8_t *sy = rqb_solver_sym_mirror(b->sv);
+    for (size_t k = 0; k < j->nm; k++) {
+      transfer_symbol(rq, j->sbn, j->missing[k], (uint8_t *)sy + k * b->pitch, io, 1);
+      mask_set(b, j->missing[k]);
     }
+    b->gaps = 0;
+    ok = true;
+    rqb_copy_fence();
+    PF(RQB_PF_REP_WRITE);
   }
   if (!ok) rqb_solver_sync(b->sv);
-  free(missing);
-  free(have);
+  repair_job_free(j);
   return ok;
+}
+
+bool nanorq_repair_block(nanorq *rq, struct ioctx *io, uint8_t sbn) { /* :591-631 */
+  struct repair_job j;
+  bool result = false;
+  int st = repair_prepare(rq, io, sbn, &j, &result);
+  if (st <= 0) return st == 0 && result;
+  PF_T0;
+  if (rqb_solver_run(j.b->sv) != 0) {
+    rqb_solver_sync(j.b->sv);
+    repair_job_free(&j);
+    return false;
+  }
+  PF(RQB_PF_REP_RUN);
+  return repair_finish(rq, io, &j);
+}
+
+size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, size_t n, bool *ok) {
+  /* every block is analysed first, then the solves of all blocks that live on one device run as ONE
+   * kernel launch (gridDim.y = blocks), then the results are handed back block by block */
+  if (!rq || !sbns) return 0;
+  size_t good = 0;
+  enum { MAXB = 255 };
+  for (size_t at = 0; at < n;) {
+    const size_t m = n - at < MAXB ? n - at : MAXB;
+    struct repair_job *jobs = calloc(m, sizeof(*jobs));
+    rqb_solver **sv = calloc(m, sizeof(*sv));
+    int *state = calloc(m, sizeof(*state));
+    if (!jobs || !sv || !state) {
+      free(jobs);
+      free(sv);
+      free(state);
+      return good;
+    }
+    for (size_t k = 0; k < m; k++) {
+      bool result = false;
+      state[k] = repair_prepare(rq, io, sbns[at + k], &jobs[k], &result);
+      if (state[k] == 0 && ok) ok[at + k] = result;
+      if (state[k] < 0 && ok) ok[at + k] = false;
+      if (state[k] == 0 && result) good++;
+    }
+    /* launches: one per device among the prepared blocks */
+    for (int dev = 0; dev < 64; dev++) {
+      size_t cnt = 0;
+      for (size_t k = 0; k < m; k++)
+        if (state[k] == 1 && rqb_solver_device(jobs[k].b->sv) == dev) sv[cnt++] = jobs[k].b->sv;
+      if (!cnt) continue;
+      if (rqb_solver_run_batch(sv, (int)cnt) != 0)
+        for (size_t k = 0; k < m; k++)
+          if (state[k] == 1 && rqb_solver_device(jobs[k].b->sv) == dev) {
+            rqb_solver_sync(jobs[k].b->sv);
+            repair_job_free(&jobs[k]);
+            state[k] = -1;
+            if (ok) ok[at + k] = false;
+          }
+    }
+    for (size_t k = 0; k < m; k++) {
+      if (state[k] != 1) continue;
+      const bool r = repair_finish(rq, io, &jobs[k]);
+      if (ok) ok[at + k] = r;
+      good += r;
+    }
+    free(jobs);
+    free(sv);
+    free(state);
+    at += m;
+  }
+  return good;
 }

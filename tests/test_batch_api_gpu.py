@@ -244,3 +244,41 @@ def test_receive_ring_with_holes_is_added_with_one_call():
     assert np.array_equal(out, payload)
     for x in (enc, dec, io_in, io_out, pb, ob):
         x.close()
+
+
+@pytest.mark.parametrize("pinned_out", [False, True], ids=["pageable-out", "pinned-out"])
+def test_repair_blocks_one_launch_for_all_blocks_of_an_object(pinned_out):
+    """nanorq_repair_blocks: the 8 blocks of a C4-shaped object are repaired with one solve launch
+    (per device); one block is short of symbols and must come back false, the others true."""
+    F, T, K = 8 * 1024 * 320, 320, 1024
+    payload, oti, tags, rows = make_packets(F, T, K, 0, 0.1, 2, seed=31)
+    # starve block 5: drop its repair symbols
+    keep = np.array([not ((int(t) >> 24) == 5 and (int(t) & 0xFFFFFF) >= K) for t in tags])
+    tags2, rows2 = tags[keep], rows[keep]
+    keepalive = []
+    if pinned_out:
+        ob, out = pinned_array(F)
+        out[:] = 0
+        keepalive.append(ob)
+        io = nb.PinnedMemIO(out)
+    else:
+        out = np.zeros(F, np.uint8)
+        io = nb.MemIO(out)
+    dec = nb.Decoder(*oti)
+    rc, _ = dec.add_symbols(tags2, rows2, io)
+    assert rc >= 0
+    l0 = nb.kernel_launches()
+    res = dec.repair_blocks(io, list(range(8)))
+    solves = nb.kernel_launches() - l0
+    assert res == [True] * 5 + [False] + [True] * 2
+    # ONE solve launch for the seven decodable blocks (+ one row-placement kernel per block with deferred output)
+    assert solves == (8 if pinned_out else 1), solves
+    # the starved block decodes once its repair symbols arrive; repeated calls are idempotent
+    late = np.array([(int(t) >> 24) == 5 and (int(t) & 0xFFFFFF) >= K for t in tags])
+    rc, _ = dec.add_symbols(tags[late], rows[late], io)
+    assert rc > 0
+    assert dec.repair_blocks(io, [5, 0, 3]) == [True, True, True]
+    assert np.array_equal(out, payload)
+    dec.close(); io.close()
+    for b in keepalive:
+        b.close()
