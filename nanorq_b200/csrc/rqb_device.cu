@@ -317,11 +317,13 @@ rqb_solve_kernel(const rqb_solve_args *__restrict__ args_list) {
 // every page wait and every level barrier; rqb_dev_trace_fetch reads the log back
 __device__ unsigned long long g_trace[16384];
 __device__ unsigned g_trace_n;
+// the event counter lives in a register of thread 0 (a counter in global memory would put an L2
+// round trip into every event); stores are fire-and-forget
 #define TRACE(tag, val)                                                                          \
   do {                                                                                           \
-    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && g_trace_n < 16384)                     \
-      g_trace[g_trace_n++] = ((unsigned long long)(tag) << 62) | ((unsigned long long)(val) << 40) | \
-                             (clock64() & 0xFFFFFFFFFFull);                                       \
+    if (trace_on && trace_n < 16384u)                                                            \
+      g_trace[trace_n++] = ((unsigned long long)(tag) << 62) | ((unsigned long long)(val) << 40) | \
+                           (clock64() & 0xFFFFFFFFFFull);                                         \
   } while (0)
 #else
 #define TRACE(tag, val) do { } while (0)
@@ -502,7 +504,8 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
   }
   const bool active = col0 + lane * 16u < width; // the last slice of a row may be narrower
 #ifdef RQB_TRACE
-  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_trace_n = 0;
+  const bool trace_on = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+  uint32_t trace_n = 0;
 #endif
   TRACE(0, 0);
 
@@ -595,6 +598,9 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
                    RQB_PAGE_BYTES, &bars[st]);
     }
   }
+#ifdef RQB_TRACE
+  if (trace_on) g_trace_n = trace_n;
+#endif
 }
 
 // ---------------------------------------------------------------- LT kernel

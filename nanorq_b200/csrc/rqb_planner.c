@@ -709,6 +709,9 @@ typedef struct {
  *                     partial sums of long output rows
  * Returns 0, -7 (out of memory) or -8 (does not fit the slot budget: use the HBM flavour). */
 static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n_slots_out, uint32_t *tab_bits_out) {
+#ifdef RQB_PLAN_FINE
+  double fine_t = now_s();
+#endif
   const rqb_plan_request *req = v->req;
   const int S = v->P.S, H = v->P.H, L = v->P.L, R = v->R, U = v->U, I = v->I, n = v->n, nb = v->nb;
   const int uw = v->uw, nbw = v->nbw, nfree = v->nfree;
@@ -756,6 +759,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
     k += len;
   }
 
+  FINE(15);
   /* A + B: the triangular solve Y = X^-1 b_top and the residual rows r_m = b_m ^ X_low Y, all in place */
   uint32_t endA = (uint32_t)v->maxlevel;
   for (int idx = 0; idx < I + nb; idx++) {
@@ -774,6 +778,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
   }
   const uint32_t lvB = (uint32_t)v->maxlevel + 1;
   const uint32_t endB = endA > lvB ? endA : lvB;
+  FINE(16);
 
   /* alpha-scans over the columns 0..n-1 in NC chunks, HDPC sums accumulated on the way (SCAN2) */
   int NC = n / 32;
@@ -926,6 +931,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
   }
   lv = end + 1;
 
+  FINE(17);
   /* F: x_p = Y_p ^ (G z)_p through XOR tables over groups of `bits` inactive symbols, the largest
    * group size whose tables fit the scratch slots (everything that lived there is dead by now).
    * Level lv: entries made of the z themselves (one half of the group's bits); lv+1: entries
@@ -998,6 +1004,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
     b_tab_ex(bd, slot, crow, bits, lv + 2, gv, (uint32_t)ngr);
   }
 #undef GROUP_VAL
+  FINE(18);
   if (req->want_c)
     for (int t = 0; t < U; t++) { /* the inactive symbols themselves */
       uint32_t ns = 0;
@@ -1025,6 +1032,7 @@ static int emit_smem(const plan_view *v, builder *bd, scratch_t *sc, uint32_t *n
     b_tree(bd, RQB_T_XOR, SM_G(v->row0[RQB_SP_SYM] + (req->out_row ? req->out_row[k] : (uint32_t)k)), tmp, ns, lv);
     if (bd->ws_next > peak) peak = bd->ws_next;
   }
+  FINE(19);
   if (peak > v->slot_budget) return -8;
   *n_slots_out = peak;
   *tab_bits_out = (uint32_t)bits;
