@@ -660,8 +660,25 @@ typedef struct {
 } chains;
 
 static int chain_row(chains *ch, int *rd, int *it, int cnt, int has_self, int maxkey, uint64_t *sortbuf) {
-  if (cnt > 1) sort_by_level(rd, it, cnt, maxkey, sortbuf);
   int prev = 0, idx = 0, cap = has_self ? (int)RQB_MAX_SRCS - 1 : (int)RQB_MAX_SRCS;
+  if (cnt <= cap) { /* the common case: one task, only the latest term matters */
+    if (cnt == 0) {
+      ch->ptr[ch->ng] = ch->nitems;
+      return 0;
+    }
+    int mx = rd[0];
+    for (int k = 0; k < cnt; k++) {
+      ch->items[ch->nitems + k] = it[k];
+      if (rd[k] > mx) mx = rd[k];
+    }
+    ch->level[ch->ng] = mx + 1;
+    ch->ptr[ch->ng] = ch->nitems;
+    ch->nitems += cnt;
+    ch->ng++;
+    ch->ptr[ch->ng] = ch->nitems;
+    return mx + 1;
+  }
+  sort_by_level(rd, it, cnt, maxkey, sortbuf);
   while (idx < cnt) {
     const int take = cnt - idx < cap ? cnt - idx : cap;
     const int lv = (rd[idx + take - 1] > prev ? rd[idx + take - 1] : prev) + 1;

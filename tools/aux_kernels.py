@@ -53,3 +53,24 @@ try:
     oracle().orc_sched_free(S)
 except Exception as e:  # the capture of the LT kernel above is what matters
     print("replay skipped:", e)
+
+# rqb_copy_rows_kernel (block image of a decoder with deferred output) and rqb_repitch_kernel
+# (host<->device copies stay linear when the caller's row pitch differs from the arena's): one batch
+# round trip at T = 1000 through nanorq_batch.h with page-locked buffers
+Kb, Tb = 1000, 1000
+Fb = Kb * Tb
+pay = nb.PinnedBuffer(Fb)
+pay.arr[:] = workload.payload(Kb, Tb, 3).reshape(-1)
+ring = nb.PinnedBuffer((Kb + 64) * Tb)
+out = nb.PinnedBuffer(Fb)
+enc = nb.Encoder(Fb, Tb, Kb, 0, 8)
+io_in, io_out = nb.PinnedMemIO(pay.arr), nb.PinnedMemIO(out.arr)
+rows = ring.arr.reshape(Kb + 64, Tb)
+assert enc.encode_range(0, 0, Kb + 64, io_in, out=rows) is not None
+tags = np.array([0xFFFFFFFF if e % 10 == 3 else nb.api.tag(0, e) for e in range(Kb + 64)], np.uint32)
+dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+assert dec.add_symbols(tags, rows, io_out)[0] > 0 and dec.repair_block(io_out, 0)
+assert np.array_equal(out.arr, pay.arr)
+print("batch round trip K=%d T=%d through page-locked buffers: ok" % (Kb, Tb))
+for x in (enc, dec, io_in, io_out, pay, ring, out):
+    x.close()

@@ -11,6 +11,7 @@ writes profiles/<round>_launches.csv          the per-launch device times (ncu l
        profiles/<round>_solve_traffic.json    DRAM bytes per launch (bench.py's roofline.traffic)
 """
 import csv
+import hashlib
 import io
 import json
 import os
@@ -54,6 +55,14 @@ def raw(rep):
     return out
 
 
+def source_stamp():
+    """Same stamp as bench.py's traffic_stamp(): the sources that decide what the solve kernel moves."""
+    h = hashlib.sha256()
+    for f in ("nanorq_b200/csrc/rqb_device.cu", "nanorq_b200/csrc/rqb_planner.c", "nanorq_b200/csrc/rqb_program.h"):
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def to_bytes(m):
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     return m["value"] * scale[m["unit"]]
@@ -80,7 +89,7 @@ def main():
                    "note": "per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes",
                    "kernels": shares}, open(os.path.join(PROF, rnd + "_launch_shares.json"), "w"), indent=1)
         print(json.dumps(shares, indent=1))
-    for name in ("solve", "rowops", "aux"):
+    for name in ("solve", "smem", "rowops", "aux"):
         rep = os.path.join(OUT, "prof_%s.ncu-rep" % name)
         if not os.path.exists(rep):
             continue
@@ -89,8 +98,11 @@ def main():
                    "launches": rows}, open(os.path.join(PROF, "%s_%s_ncu.json" % (rnd, name)), "w"), indent=1)
         if name == "solve":
             per = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows]
+            grid = rows[0].get("launch__grid_size")
+            slices = 5  # T = 1280 in 256-byte column slices
             json.dump({"dram_bytes_per_launch": sum(per) / len(per), "launches_captured": len(per),
-                       "grid": rows[0].get("launch__grid_size"),
+                       "grid": grid, "blocks_per_launch": int(grid["value"] // slices) if isinstance(grid, dict) else None,
+                       "source_stamp": source_stamp(),
                        "source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/%s_solve_ncu.json" % rnd},
                       open(os.path.join(PROF, rnd + "_solve_traffic.json"), "w"), indent=1)
             print("solve: DRAM bytes per launch", sum(per) / len(per))
