@@ -96,6 +96,12 @@ int rqb_solver_fetch_rows(rqb_solver *s, int space, uint32_t first, uint32_t n, 
 /* emitted-symbol row sym_row[k] = input row in_row[k], k < n, on the device (a decoder places the
  * source symbols it received into the block image next to the recovered ones) */
 int rqb_solver_copy_in_to_sym(rqb_solver *s, const uint32_t *sym_row, const uint32_t *in_row, uint32_t n);
+/* where the u x u Schur system of a block is eliminated while its program is built (the reference's
+ * precode_matrix_solve_gf2 / _solve_gf256, lib/precode.c:264-315): 0 = on the device
+ * (rqb_usolve_kernel: one CTA, warp-level min reductions for the pivot search) when the system has at
+ * least 256 columns -- smaller ones are done faster on the host than a kernel round trip takes --,
+ * 1 = always on the host, 2 = on the device whenever it fits.  Same pivots and results either way. */
+void rqb_set_usolve_mode(int mode);
 /* page-locked host memory for symbol buffers: copies to and from it are DMA without a staging copy */
 void *rqb_host_alloc(size_t bytes);
 void rqb_host_release(void *p);

@@ -157,6 +157,7 @@ def lib():
     sig("rqb_solver_upload_rows", C.c_int, vp, C.c_uint32, C.c_uint32, vp, sz)
     sig("rqb_solver_fetch_rows", C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, vp, sz, C.c_int)
     sig("rqb_solver_copy_in_to_sym", C.c_int, vp, u32p, u32p, C.c_uint32)
+    sig("rqb_set_usolve_mode", None, C.c_int)
     sig("rqb_host_alloc", vp, sz)
     sig("rqb_host_release", None, vp)
     sig("rqb_host_pin", C.c_int, vp, sz)
@@ -207,7 +208,7 @@ EXPORTED_SYMBOLS = [
     "rqb_set_cache_limit", "rqb_cache_stats", "rqb_device_mem_info", "rqb_plan_blob_build_ex", "rqb_smem_budget",
     "ioctx_from_pinned_mem", "nanorq_repair_blocks", "nanorq_encode_range", "nanorq_decoder_add_symbols", "nanorq_set_devices",
     "rqb_solver_create_on", "rqb_solver_device", "rqb_solver_set_flavour", "rqb_solver_upload_rows",
-    "rqb_solver_fetch_rows", "rqb_solver_copy_in_to_sym", "rqb_host_alloc", "rqb_host_release", "rqb_host_pin",
+    "rqb_solver_fetch_rows", "rqb_solver_copy_in_to_sym", "rqb_host_alloc", "rqb_host_release", "rqb_host_pin", "rqb_set_usolve_mode",
     "rqb_host_unpin",
 ]
 

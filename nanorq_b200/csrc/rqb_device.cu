@@ -603,6 +603,180 @@ rqb_solve_smem_kernel(const rqb_solve_args *__restrict__ args_list) {
 #endif
 }
 
+// ------------------------------------------------------------- U-solve kernel
+// The elimination of the u x u Schur system of one block (the reference's
+// precode_matrix_solve_gf2 / precode_matrix_solve_gf256, lib/precode.c:264-315; steps 3d/3e of
+// rqb_plan_build): Gauss-Jordan over GF(2) on the nb binary residual rows with the transformation
+// tracked, then the H x nfree system of the HDPC rows over GF(256).  One CTA; the rows live in shared
+// memory, every thread owns rows tid, tid + blockDim, ...  Pivot search = lowest row that is not a pivot
+// yet and has the column's bit set: each thread offers its lowest such row, a warp-level min reduction
+// (__reduce_min_sync) and a second one over the warps' results give the pivot.  The same rule as the
+// host code, so both produce identical results.
+struct rqb_usolve_hdr {
+  int32_t nb, U, uw, nbw, H, sh_stride;
+  // outputs
+  int32_t status, nfree, rho, pad;
+  int32_t qrow_of_f[16];
+  uint8_t TQ[256];
+};
+// buffer layout after the header (all 16-byte aligned): Sb [nb*uw u64] | Tb [nb*nbw u64] | Sh [H*sh_stride] | pivrow [U i32]
+
+__device__ __forceinline__ uint32_t gf_mul1(uint32_t a, uint32_t b) { // GF(256), poly 0x11D, shift-and-add
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    r ^= (b & 1u) ? a : 0u;
+    a = xtime1(a);
+    b >>= 1;
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t gf_inv1(uint32_t a) { // a^254
+  uint32_t r = 1, p = a;
+#pragma unroll
+  for (int k = 1; k < 8; k++) { // 254 = 2 + 4 + ... + 128
+    p = gf_mul1(p, p);
+    r = gf_mul1(r, p);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+rqb_usolve_kernel(uint8_t *__restrict__ buf) {
+  extern __shared__ __align__(16) uint8_t usm[];
+  rqb_usolve_hdr *hdr = reinterpret_cast<rqb_usolve_hdr *>(buf);
+  const int nb = hdr->nb, U = hdr->U, uw = hdr->uw, nbw = hdr->nbw, H = hdr->H, shs = hdr->sh_stride;
+  const int rw = uw + nbw; // words per row in shared memory: [Schur bits | transformation bits]
+  uint64_t *g_sb = reinterpret_cast<uint64_t *>(buf + sizeof(rqb_usolve_hdr));
+  uint64_t *g_tb = g_sb + (size_t)nb * uw;
+  const uint8_t *g_sh = reinterpret_cast<const uint8_t *>(g_tb + (size_t)nb * nbw);
+  int32_t *g_piv = reinterpret_cast<int32_t *>(const_cast<uint8_t *>(g_sh) + (((size_t)H * shs + 15) & ~(size_t)15));
+  uint64_t *rows = reinterpret_cast<uint64_t *>(usm);                 // [nb][rw]
+  uint8_t *used = reinterpret_cast<uint8_t *>(rows + (size_t)nb * rw); // [nb]
+  int32_t *piv = reinterpret_cast<int32_t *>(used + ((nb + 15) & ~15)); // [U]
+  __shared__ int s_first[32];
+  __shared__ int s_pr, s_nfree, s_rho;
+  __shared__ uint8_t s_m[16][32]; // the HDPC system [Q | TQ], one column per lane
+  __shared__ int s_free[16];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+
+  for (int m = tid; m < nb; m += nthr) {
+    for (int w = 0; w < uw; w++) rows[(size_t)m * rw + w] = g_sb[(size_t)m * uw + w];
+    for (int w = 0; w < nbw; w++) rows[(size_t)m * rw + uw + w] = (w == (m >> 6)) ? (1ull << (m & 63)) : 0ull;
+    used[m] = 0;
+  }
+  if (tid == 0) s_nfree = s_rho = 0;
+  __syncthreads();
+
+  for (int t = 0; t < U; t++) {
+    int cand = 0x7fffffff;
+    for (int m = tid; m < nb; m += nthr)
+      if (!used[m] && ((rows[(size_t)m * rw + (t >> 6)] >> (t & 63)) & 1ull)) {
+        cand = m;
+        break;
+      }
+    const int wmin = __reduce_min_sync(0xffffffffu, cand); // warp-level reduction for the pivot search
+    if (lane == 0) s_first[warp] = wmin;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = __reduce_min_sync(0xffffffffu, lane < nwarps ? s_first[lane] : 0x7fffffff);
+      if (lane == 0) {
+        s_pr = v;
+        if (v == 0x7fffffff) {
+          piv[t] = -1;
+          if (s_nfree < 16) s_free[s_nfree] = t;
+          s_nfree++;
+        } else {
+          piv[t] = v;
+          used[v] = 1;
+          s_rho++;
+        }
+      }
+    }
+    __syncthreads();
+    const int pr = s_pr;
+    if (pr == 0x7fffffff) {
+      if (s_nfree > H) break; // more free columns than HDPC rows: singular (uniform: s_nfree is shared)
+      continue;
+    }
+    const uint64_t *prow = rows + (size_t)pr * rw;
+    for (int m = tid; m < nb; m += nthr)
+      if (m != pr && ((rows[(size_t)m * rw + (t >> 6)] >> (t & 63)) & 1ull)) {
+        uint64_t *r = rows + (size_t)m * rw;
+        for (int w = 0; w < rw; w++) r[w] ^= prow[w];
+      }
+    __syncthreads();
+  }
+  const int nfree = s_nfree;
+  if (nfree > H) {
+    if (tid == 0) {
+      hdr->status = 1;
+      hdr->nfree = nfree;
+      hdr->rho = s_rho;
+    }
+    return;
+  }
+  // HDPC rows: Q[h][f] = Sh[h][free f] ^ sum over pivot columns t of Sh[h][t] * (bit `free f` of t's pivot row)
+  for (int e = tid; e < H * 32; e += nthr) {
+    const int h = e >> 5, k = e & 31;
+    uint32_t q = 0;
+    if (k < nfree) {
+      const int fc = s_free[k];
+      const uint8_t *row = g_sh + (size_t)h * shs;
+      q = row[fc];
+      for (int t = 0; t < U; t++) {
+        const uint32_t beta = row[t];
+        if (beta && piv[t] >= 0 && ((rows[(size_t)piv[t] * rw + (fc >> 6)] >> (fc & 63)) & 1ull)) q ^= beta;
+      }
+    } else if (k < nfree + H) {
+      q = (k - nfree == h) ? 1u : 0u; // the tracked transformation starts as the identity
+    }
+    s_m[h][k] = (uint8_t)q;
+  }
+  __syncthreads();
+  // Gauss-Jordan over GF(256) on [Q | TQ]: warp 0, one column per lane
+  if (warp == 0) {
+    uint32_t usedmask = 0;
+    int status = 0;
+    for (int f = 0; f < nfree; f++) {
+      int pr = -1;
+      for (int h = 0; h < H; h++)
+        if (!((usedmask >> h) & 1u) && s_m[h][f]) {
+          pr = h;
+          break;
+        }
+      if (pr < 0) {
+        status = 1; // rank(A) < L
+        break;
+      }
+      usedmask |= 1u << pr;
+      if (lane == 0) hdr->qrow_of_f[f] = pr;
+      const uint32_t inv = gf_inv1(s_m[pr][f]);
+      uint32_t bcol[16];
+      for (int h = 0; h < H; h++) bcol[h] = s_m[h][f]; // column f before it is updated
+      __syncwarp();
+      const uint32_t pk = gf_mul1(s_m[pr][lane], inv);
+      s_m[pr][lane] = (uint8_t)pk;
+      for (int h = 0; h < H; h++)
+        if (h != pr && bcol[h]) s_m[h][lane] ^= (uint8_t)gf_mul1(bcol[h], pk);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      hdr->status = status;
+      hdr->nfree = nfree;
+      hdr->rho = s_rho;
+    }
+    for (int h = 0; h < H; h++)
+      if (lane < H) hdr->TQ[h * H + lane] = s_m[h][nfree + lane];
+  }
+  __syncthreads();
+  for (int m = tid; m < nb; m += nthr) {
+    for (int w = 0; w < uw; w++) g_sb[(size_t)m * uw + w] = rows[(size_t)m * rw + w];
+    for (int w = 0; w < nbw; w++) g_tb[(size_t)m * nbw + w] = rows[(size_t)m * rw + uw + w];
+  }
+  for (int t = tid; t < U; t += nthr) g_piv[t] = piv[t];
+}
+
 // ---------------------------------------------------------------- LT kernel
 // one CTA per output symbol; lane 0 expands Tuple[K', isi] into row indices.
 __global__ void __launch_bounds__(128)
@@ -997,6 +1171,34 @@ int rqb_dev_trace_fetch(unsigned long long *out, unsigned cap) {
   return (int)n;
 }
 #endif
+
+size_t rqb_usolve_buffer_bytes(int nb, int U, int uw, int nbw, int H, int sh_stride) {
+  (void)U;
+  return sizeof(rqb_usolve_hdr) + (size_t)nb * (size_t)(uw + nbw) * 8 + (((size_t)H * (size_t)sh_stride + 15) & ~(size_t)15) +
+         (((size_t)U * 4 + 15) & ~(size_t)15);
+}
+size_t rqb_usolve_header_bytes(void) { return sizeof(rqb_usolve_hdr); }
+
+/* buf_dev holds the header and the matrices (see rqb_usolve_kernel); returns cudaErrorInvalidValue when the
+ * rows do not fit a CTA's shared memory (the host code runs then) */
+int rqb_launch_usolve(uint8_t *buf_dev, int nb, int U, int uw, int nbw, void *stream) {
+  const size_t smem = (size_t)nb * (size_t)(uw + nbw) * 8 + (size_t)((nb + 15) & ~15) + (size_t)U * 4 + 64;
+  if (smem > 200u * 1024u) return (int)cudaErrorInvalidValue;
+  static std::atomic<int> configured[64];
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+    CK(cudaFuncSetAttribute(rqb_usolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (dev < 64) configured[dev].store(1, std::memory_order_release);
+  }
+  int threads = ((nb + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
+  if (threads > 1024) threads = 1024;
+  rqb_usolve_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(buf_dev);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
 
 int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const uint32_t *isi_dev, uint32_t n,
                   uint8_t *out, uint32_t out_pitch, uint32_t width, void *stream) {

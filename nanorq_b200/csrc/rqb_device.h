@@ -104,6 +104,12 @@ int rqb_launch_copy_rows(uint8_t *base, size_t pitch, const uint32_t *pairs_dev,
 int rqb_launch_repitch(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, uint32_t width, uint32_t n,
                        void *stream);
 
+/* the u x u Schur elimination of one block on the device (rqb_usolve_kernel): buf_dev = header +
+ * matrices, laid out as rqb_solver.c's usolve hook packs them */
+size_t rqb_usolve_buffer_bytes(int nb, int U, int uw, int nbw, int H, int sh_stride);
+size_t rqb_usolve_header_bytes(void);
+int rqb_launch_usolve(uint8_t *buf_dev, int nb, int U, int uw, int nbw, void *stream);
+
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 unsigned long long rqb_dev_launch_count(void);
 /* bytes moved by rqb_copy* so far */

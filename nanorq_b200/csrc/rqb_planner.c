@@ -1075,6 +1075,9 @@ static uint64_t row0_ws_rows(const rqb_plan_request *req, int L) {
   return (uint64_t)req->in_rows + req->sym_rows + (uint64_t)L + 1u;
 }
 
+int (*rqb_plan_usolve_hook)(rqb_usolve_io *io);
+int rqb_plan_usolve_mode;
+
 /* ---------------------------------------------------------------- planner */
 #define NONE_REF RQB_REF_NONE /* "this row is all zero / has no location" */
 
@@ -1465,7 +1468,24 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   int *pivcol_of_row = sc_buf(sc, SC_PIVCOL, sizeof(int) * (size_t)(nb ? nb : 1), 0);
   int *freecols = sc_buf(sc, SC_FREECOLS, sizeof(int) * (size_t)(U ? U : 1), 0);
   int rho = 0, nfree = 0;
+  uint8_t *TQ = sc_buf(sc, SC_TQ, (size_t)H * (size_t)H, 1);
+  int qrow_of_f[RQB_MAX_H];
   OOM_CHECK();
+  /* on the device when that pays (rqb_planner.h): same pivots, same results */
+  int on_device = 0;
+  if (rqb_plan_usolve_hook && rqb_plan_usolve_mode != 1 && nb > 0 && (rqb_plan_usolve_mode == 2 || U >= 256)) {
+    rqb_usolve_io uio = {nb, U, uw, nbw, H, (size_t)uq * 8, Sb, Tb, Sh, pivrow, TQ, qrow_of_f, 0, 0};
+    const int ur = rqb_plan_usolve_hook(&uio);
+    if (ur == 1) return 1; /* rank(A) < L */
+    if (ur == 0) {
+      on_device = 1;
+      nfree = uio.nfree;
+      rho = uio.rho;
+      for (int t = 0, f = 0; t < U; t++)
+        if (pivrow[t] < 0) freecols[f++] = t;
+    }
+  }
+  if (!on_device) {
   for (int m = 0; m < nb; m++) pivcol_of_row[m] = -1;
   for (int t = 0; t < U; t++) {
     int pr = -1;
@@ -1493,7 +1513,6 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
   /* ---- 3e. HDPC rows: eliminate pivot columns (beta = Sh[h][t]), then solve the
    *          H x nfree system Q over GF(256) with a tracked transformation TQ (H x H) */
   uint8_t *Q = sc_buf(sc, SC_Q, (size_t)H * (size_t)(nfree ? nfree : 1), 1);
-  uint8_t *TQ = sc_buf(sc, SC_TQ, (size_t)H * (size_t)H, 1);
   OOM_CHECK();
   for (int h = 0; h < H; h++) {
     const uint8_t *row = Sh + (size_t)h * (size_t)uq * 8;
@@ -1507,7 +1526,6 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
     TQ[h * H + h] = 1;
   }
-  int qrow_of_f[RQB_MAX_H];
   {
     uint8_t used[RQB_MAX_H] = {0};
     for (int f = 0; f < nfree; f++) {
@@ -1531,6 +1549,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       }
     }
   }
+  } /* !on_device */
   double t3 = now_s();
 
   FINE(4);

@@ -81,6 +81,29 @@ void rqb_plan_pool_drain(void); /* really free recycled plans and cached per-K' 
 int rqb_plan_from_schedule(const void *ops, size_t nops, uint32_t nrows, const uint32_t *gather_map, uint32_t base,
                            uint32_t out_base, uint32_t zero_row, rqb_plan **out);
 
+/* The elimination of the u x u Schur system (step 3d/3e of rqb_plan_build: GF(2) Gauss-Jordan on the
+ * binary residual rows with a tracked transformation, then the H x nfree GF(256) system of the HDPC
+ * rows; the reference's precode_matrix_solve_gf2 / _solve_gf256, lib/precode.c:264-315) can run on
+ * the device: rqb_solver.c installs this hook when a GPU is present and rqb_plan_build calls it for
+ * blocks whose system is large enough to pay for the round trip (rqb_set_usolve_mode).  The kernel
+ * picks the same pivots as the host code (lowest unused row with the bit set), so programs are
+ * identical either way.  Returns 0 = solved, 1 = singular (rank < L), -1 = not available (host code
+ * runs instead). */
+typedef struct {
+  int nb, U, uw, nbw, H;
+  size_t sh_stride;    /* bytes between the HDPC Schur rows in Sh */
+  uint64_t *Sb;        /* [nb x uw]  in: binary Schur rows; out: reduced rows                  */
+  uint64_t *Tb;        /* [nb x nbw] out: the transformation (in: ignored, starts as identity)  */
+  const uint8_t *Sh;   /* [H x sh_stride] HDPC Schur rows (bytes)                               */
+  int *pivrow;         /* [U]  out: pivot row of column t or -1                                 */
+  uint8_t *TQ;         /* [H x H] out                                                          */
+  int *qrow_of_f;      /* [<= H] out                                                           */
+  int nfree, rho;      /* out */
+} rqb_usolve_io;
+extern int (*rqb_plan_usolve_hook)(rqb_usolve_io *io);
+/* 0 = auto (device when U >= 256 and a hook is installed), 1 = always host, 2 = device whenever possible */
+extern int rqb_plan_usolve_mode;
+
 int rqb_params_init(int K, rqb_params *P);
 /* host-side Tuple / index helpers over the built-in tables */
 int rqb_host_lt_indices(const rqb_params *P, uint32_t X, uint32_t *out);

@@ -282,6 +282,93 @@ static void enc_plans_trim(int keep) {
   }
 }
 
+/* ------------------------------------------------- U-solve on the device
+ * rqb_plan_build's hook (rqb_planner.h): the Schur elimination of one block as ONE kernel launch
+ * on the calling thread's current device.  Every planning thread keeps a small context of its own
+ * (stream, pinned and device buffer, grown on demand) for the lifetime of the thread. */
+typedef struct {
+  void *stream;
+  uint8_t *h_buf, *d_buf;
+  size_t cap;
+  int dev;
+} usolve_ctx;
+static pthread_key_t g_usolve_key;
+static pthread_once_t g_usolve_once = PTHREAD_ONCE_INIT;
+static void usolve_ctx_free(void *v) {
+  usolve_ctx *c = v;
+  if (!c) return;
+  if (rqb_dev_get() != c->dev) rqb_dev_set(c->dev);
+  if (c->stream) rqb_stream_sync(c->stream);
+  if (c->h_buf) rqb_host_free(c->h_buf);
+  if (c->d_buf) rqb_dev_free(c->d_buf);
+  if (c->stream) rqb_stream_destroy(c->stream);
+  free(c);
+}
+static void usolve_make_key(void) { pthread_key_create(&g_usolve_key, usolve_ctx_free); }
+
+static int usolve_on_device(rqb_usolve_io *io) {
+  const int dev = rqb_dev_get();
+  if (dev < 0) return -1;
+  pthread_once(&g_usolve_once, usolve_make_key);
+  usolve_ctx *c = pthread_getspecific(g_usolve_key);
+  if (c && c->dev != dev) { /* the thread moved to another device: start over there */
+    usolve_ctx_free(c);
+    c = NULL;
+    pthread_setspecific(g_usolve_key, NULL);
+  }
+  if (!c) {
+    c = calloc(1, sizeof(*c));
+    if (!c) return -1;
+    c->dev = dev;
+    if (rqb_stream_create(&c->stream)) {
+      free(c);
+      return -1;
+    }
+    pthread_setspecific(g_usolve_key, c);
+  }
+  const size_t hdr = rqb_usolve_header_bytes();
+  const size_t need = rqb_usolve_buffer_bytes(io->nb, io->U, io->uw, io->nbw, io->H, (int)io->sh_stride);
+  if (need > c->cap) {
+    if (c->h_buf) rqb_host_free(c->h_buf);
+    if (c->d_buf) rqb_dev_free(c->d_buf);
+    c->h_buf = c->d_buf = NULL;
+    c->cap = 0;
+    const size_t cap = need + need / 2;
+    g_cnt_alloc_pinned++;
+    g_cnt_alloc_dev++;
+    if (rqb_host_malloc((void **)&c->h_buf, cap) || rqb_dev_malloc((void **)&c->d_buf, cap)) return -1;
+    c->cap = cap;
+  }
+  /* pack: header | Sb | Tb (device fills it) | Sh | pivrow (device fills it) */
+  int32_t *h = (int32_t *)c->h_buf;
+  memset(c->h_buf, 0, hdr);
+  h[0] = io->nb; h[1] = io->U; h[2] = io->uw; h[3] = io->nbw; h[4] = io->H; h[5] = (int32_t)io->sh_stride;
+  uint8_t *p_sb = c->h_buf + hdr;
+  uint8_t *p_tb = p_sb + (size_t)io->nb * io->uw * 8;
+  uint8_t *p_sh = p_tb + (size_t)io->nb * io->nbw * 8;
+  uint8_t *p_piv = p_sh + (((size_t)io->H * io->sh_stride + 15) & ~(size_t)15);
+  memcpy(p_sb, io->Sb, (size_t)io->nb * io->uw * 8);
+  memcpy(p_sh, io->Sh, (size_t)io->H * io->sh_stride);
+  const size_t in_bytes = (size_t)(p_piv - c->h_buf);
+  int e = rqb_copy_h2d(c->d_buf, c->h_buf, in_bytes, c->stream);
+  e = e ? e : rqb_launch_usolve(c->d_buf, io->nb, io->U, io->uw, io->nbw, c->stream);
+  if (e) return -1; /* e.g. the rows do not fit a CTA's shared memory: the host code runs */
+  e = rqb_copy_d2h(c->h_buf, c->d_buf, need, c->stream);
+  e = e ? e : rqb_stream_sync(c->stream);
+  if (e) return -1;
+  if (h[6] != 0) return 1; /* singular */
+  io->nfree = h[7];
+  io->rho = h[8];
+  memcpy(io->qrow_of_f, h + 10, sizeof(int) * 16 < sizeof(int) * (size_t)io->H ? sizeof(int) * 16 : sizeof(int) * (size_t)io->H);
+  memcpy(io->TQ, c->h_buf + 10 * 4 + 16 * 4, (size_t)io->H * io->H);
+  memcpy(io->Sb, p_sb, (size_t)io->nb * io->uw * 8);
+  memcpy(io->Tb, p_tb, (size_t)io->nb * io->nbw * 8);
+  memcpy(io->pivrow, p_piv, (size_t)io->U * 4);
+  return 0;
+}
+
+void rqb_set_usolve_mode(int mode) { rqb_plan_usolve_mode = mode >= 0 && mode <= 2 ? mode : 0; }
+
 /* ------------------------------------------------------------- solver */
 struct rqb_solver {
   int K, Kparams, dev;
@@ -508,6 +595,7 @@ int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, siz
     return RQB_E_NODEVICE;
   }
   if (!max_out) max_out = 1;
+  if (!rqb_plan_usolve_hook) rqb_plan_usolve_hook = usolve_on_device; /* a GPU is present: the planner may use it */
   const int dev = want_dev >= 0 ? want_dev : rqb_dev_default();
   if (dev >= rqb_dev_count()) {
     snprintf(g_err, sizeof(g_err), "rqb_solver_create: no CUDA device %d", dev);
@@ -1151,6 +1239,7 @@ int rqb_plan_blob_build(int K, const rqb_solve_request *req, rqb_plan_blob *out)
 
 int rqb_plan_blob_build_ex(int K, const rqb_solve_request *req, uint32_t smem_budget, rqb_plan_blob *out) {
   rqb_params P;
+  if (!rqb_plan_usolve_hook && rqb_plan_usolve_mode == 2 && rqb_dev_count() > 0) rqb_plan_usolve_hook = usolve_on_device;
   memset(out, 0, sizeof(*out));
   if (rqb_params_init(K, &P) || req->overhead < 0) return RQB_E_ARG;
   uint32_t in_rows = 1; /* the smallest input space that holds every row the request names */
