@@ -257,6 +257,7 @@ def run_own(args, rank, world, local_rank):
 
     if nb.device_count() <= 0:
         raise SystemExit("no CUDA device: the nanorq_b200 hot path has no CPU fallback")
+    torch.set_num_threads(1)  # torch is only here for the rendezvous: no OpenMP pool next to the worker threads
     torch.cuda.set_device(local_rank)
     nb.set_device(local_rank)
     if world > 1:

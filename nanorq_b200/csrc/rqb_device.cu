@@ -50,7 +50,7 @@ static constexpr int kSolveMinCtas = RQB_SOLVE_MIN_CTAS;       // CTAs per SM th
 // big batches (the thin levels of the triangular solve keep more of the CTA's lanes busy and
 // every barrier covers twice the bytes); 4 lanes = 64-byte slices when only a few blocks are
 // in flight (twice the CTAs for the fat levels).
-static constexpr int kRingStages = 8; // 8 x 4 KiB pages in flight per CTA
+static constexpr int kRingStages = 4; // 4 x 8 KiB pages in flight per CTA
 static constexpr uint32_t kRingBytes = kRingStages * RQB_PAGE_BYTES;
 static constexpr uint32_t kSolveSmem = kRingBytes + 128;       // ring + mbarriers
 
@@ -336,10 +336,10 @@ __device__ unsigned g_trace_n;
 // the elimination runs in place on the slots -- ~30-cycle shared-memory latency per
 // dependency level instead of an L2/HBM round trip -- and only results go back to HBM, so
 // DRAM traffic is the compulsory traffic.  One CTA per SM (the slots take most of the 227 KB),
-// 512 threads = 512 / kLanes tasks at a time; program pages arrive through a 6-deep TMA ring.
+// 512 threads = 512 / kLanes tasks at a time; program pages arrive through a 3-deep TMA ring.
 // grid = (ceil(width / (16 kLanes)), nblocks); dynamic smem = ring + barriers + n_slots * 16 kLanes.
 static constexpr int kSmemThreads = 512;
-static constexpr int kSmemRingStages = RQB_SMEM_RING_STAGES; // the thin levels consume ~6 B/cycle, a page takes 1-2 us to arrive
+static constexpr int kSmemRingStages = RQB_SMEM_RING_STAGES; // the program stream is not the limit (a 6-deep ring of 4 KiB pages measured the same)
 static constexpr uint32_t kSmemRingBytes = kSmemRingStages * RQB_PAGE_BYTES;
 static constexpr uint32_t kSmemFixedBytes = kSmemRingBytes + 128; // ring + mbarriers, then the slots
 
