@@ -111,7 +111,7 @@ int rqb_host_unpin(void *p);
  * as it is -- work may still be queued on its stream -- for the next create of the same
  * shape, because CUDA object creation is too slow for blocks that come and go at wire rate;
  * whoever takes a parked context waits for its stream first.  Parked contexts and pooled
- * buffers count against a byte limit (default 8 GiB, NANORQ_B200_CACHE_MB or
+ * buffers count against a byte limit (default 48 GiB, NANORQ_B200_CACHE_MB or
  * rqb_set_cache_limit); beyond it the oldest parked contexts are handed back to the driver
  * (cudaFree / cudaFreeHost).  The cache of encoder programs is limited to 48 entries (LRU).
  * rqb_release_cached() hands EVERYTHING cached back: parked contexts, pooled buffers, cached

@@ -53,6 +53,11 @@ struct block {
   uint32_t loaded_rows; /* staging rows already queued for upload */
   const uint8_t *src_mem; /* encoder loaded by DMA from a page-locked memory ioctx: the block's bytes there */
   size_t src_bytes;
+  /* small blocks get their device context only when a solve is needed (need_ctx): until then their
+   * symbols sit in plain host rows -- a transfer without loss never touches the GPU */
+  uint8_t *lazy_stage;
+  uint32_t max_out;
+  int dev;
 };
 
 struct nanorq {
@@ -209,16 +214,10 @@ static size_t transfer_symbol(nanorq *rq, uint8_t sbn, uint32_t esi, uint8_t *pt
   return out ? io->write(io, ptr, n) : io->read(io, ptr, n);
 }
 
-#ifdef RQB_EXPERIMENTS
-#include <stdio.h>
-static int xp(const char *name) { const char *e = getenv(name); return e && *e == '1'; }
-#else
-#define xp(name) 0
-#endif
-
 static void block_free(struct block *b) {
   if (!b) return;
   rqb_solver_destroy(b->sv);
+  free(b->lazy_stage);
   free(b->mask);
   free(b->rep_esi);
   free(b->rep_row);
@@ -249,6 +248,33 @@ static uint8_t *block_span(nanorq *rq, uint8_t sbn, const struct block *b, struc
   return base + off;
 }
 
+#define LAZY_MAX_SYMBOLS 256u /* blocks up to this size get a device context, and are solved, on demand */
+#define LAZY_MAX_BYTES (256u << 10)
+
+/* the host rows a block's symbols are collected in: the context's pinned staging area, or plain
+ * memory while the block has no context yet */
+static inline uint8_t *stage(const struct block *b) { return b->sv ? rqb_solver_staging(b->sv) : b->lazy_stage; }
+
+/* the block needs the GPU now: take a device context and move what was collected so far into its
+ * staging rows (nothing of it has been uploaded yet) */
+static bool need_ctx(nanorq *rq, struct block *b) {
+  if (b->sv) return true;
+  if (rqb_solver_create_on(&b->sv, b->dev, (int)b->K, rq->P.Kprime, rq->T, b->in_cap, b->max_out) != 0) {
+    b->sv = NULL;
+    return false;
+  }
+  if (b->lazy_stage) {
+    const uint32_t rows = b->mask ? b->landed : (b->loaded ? b->K : 0);
+    memcpy(rqb_solver_staging(b->sv), b->lazy_stage, (size_t)rows * b->pitch);
+    free(b->lazy_stage);
+    b->lazy_stage = NULL;
+    b->loaded_rows = 0;
+    b->staged_lo = 0;
+    b->staged_hi = b->mask ? b->landed : 0;
+  }
+  return true;
+}
+
 static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :130-146 */
   if (rq->blocks[sbn]) return rq->blocks[sbn];
   size_t K = nanorq_block_symbols(rq, sbn);
@@ -275,14 +301,25 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
     max_out = b->win_cap;
   }
   b->in_cap = max_in;
+  b->max_out = max_out;
   /* independent source blocks shard over the devices of the box, block sbn on device sbn mod n
    * (SURVEY 8(e)); one device unless nanorq_set_devices asked for more */
-  const int dev = rq->n_dev > 1 ? (int)(sbn % (unsigned)rq->n_dev) : -1;
-  if (rqb_solver_create_on(&b->sv, dev, (int)K, rq->P.Kprime, rq->T, max_in, max_out) != 0) {
+  b->dev = rq->n_dev > 1 ? (int)(sbn % (unsigned)rq->n_dev) : -1;
+  b->pitch = (rq->T + 63) / 64 * 64; /* = rqb_solver_pitch of the context this block gets */
+  if (K <= LAZY_MAX_SYMBOLS && K * rq->T <= LAZY_MAX_BYTES) {
+    if (rqb_device_count() <= 0) { /* no device: fail here like a block that needs its context at once */
+      block_free(b);
+      return NULL;
+    }
+    b->lazy_stage = malloc((size_t)max_in * b->pitch);
+    if (!b->lazy_stage) {
+      block_free(b);
+      return NULL;
+    }
+  } else if (!need_ctx(rq, b)) {
     block_free(b);
     return NULL;
   }
-  b->pitch = rqb_solver_pitch(b->sv);
   rq->blocks[sbn] = b;
   return b;
 }
@@ -296,19 +333,16 @@ int nanorq_set_devices(nanorq *rq, int n) {
 }
 
 /* ------------------------------------------------------------------ encoder */
-#define LAZY_MAX_SYMBOLS 256u /* blocks up to this size are solved on demand, see nanorq_generate_symbols */
-#define LAZY_MAX_BYTES (256u << 10)
-
 static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
   b->loaded_rows = 0;
   int pinned = 0;
   size_t bytes = 0;
   uint8_t *span = block_span(rq, sbn, b, io, &bytes, &pinned);
-  if (span && pinned && !(b->K <= LAZY_MAX_SYMBOLS && bytes <= LAZY_MAX_BYTES)) {
+  if (span && pinned && b->sv) { /* (a block without a context yet is small: its rows are copied by the CPU) */
     /* page-locked caller memory: the copy engine reads the block where it lies (no staging copy);
      * only a short last symbol goes through a zero-padded staging row */
     const uint32_t full = (uint32_t)(bytes / rq->T);
-    if (!xp("XP_NO_PAYLOAD_H2D") && rqb_solver_upload_rows(b->sv, 0, full, span, rq->T)) return false;
+    if (rqb_solver_upload_rows(b->sv, 0, full, span, rq->T)) return false;
     if (full < b->K) {
       uint8_t *row = rqb_solver_staging(b->sv) + (size_t)full * b->pitch;
       memcpy(row, span + (size_t)full * rq->T, bytes - (size_t)full * rq->T);
@@ -323,13 +357,13 @@ static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *i
   }
   /* load_symbol_matrix :175-182: K reads of one symbol each into the (pinned) staging
    * rows; the rows start moving to the GPU while the rest is still being read */
-  uint8_t *st = rqb_solver_staging(b->sv);
+  uint8_t *st = stage(b);
   b->src_mem = NULL;
   for (uint32_t esi = 0; esi < b->K; esi++) {
     uint8_t *row = st + (size_t)esi * b->pitch;
     size_t got = transfer_symbol(rq, sbn, esi, row, io, 0);
     if (got < rq->T) memset(row + got, 0, rq->T - got);
-    if (esi + 1 - b->loaded_rows == UPLOAD_CHUNK) {
+    if (b->sv && esi + 1 - b->loaded_rows == UPLOAD_CHUNK) {
       if (rqb_solver_upload(b->sv, b->loaded_rows, UPLOAD_CHUNK)) return false;
       b->loaded_rows = esi + 1;
     }
@@ -339,8 +373,9 @@ static bool load_block(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *i
 
 /* queue the upload of what is still in the staging rows, the solve and the first window of repair
  * symbols (the program is cached per K: cf. rq->S :219-221); nothing here waits for the device */
-static bool launch_solve(struct block *b) {
+static bool launch_solve(nanorq *rq, struct block *b) {
   PF_T0;
+  if (!need_ctx(rq, b)) return false;
   if (rqb_solver_upload(b->sv, b->loaded_rows, b->K - b->loaded_rows)) return false;
   b->loaded_rows = b->K;
   PF(RQB_PF_GEN_UPLOAD);
@@ -369,30 +404,31 @@ bool nanorq_generate_symbols(nanorq *rq, uint8_t sbn, struct ioctx *io) { /* :20
   if (!b->loaded) b->loaded = load_block(rq, sbn, b, io);
   if (!b->loaded) return false;
   PF(RQB_PF_GEN_LOAD);
-  if (b->K <= LAZY_MAX_SYMBOLS && (size_t)b->K * rq->T <= LAZY_MAX_BYTES) {
+  if (!b->sv) { /* a small block: solved when a repair symbol is asked for */
     b->deferred = true;
     return true;
   }
-  return launch_solve(b);
+  return launch_solve(rq, b);
 }
 
 /* the intermediate symbols are needed now */
 static bool ensure_solved(nanorq *rq, uint8_t sbn, struct block *b, struct ioctx *io) {
   if (b->inverted) return true;
   if (!b->deferred && !nanorq_generate_symbols(rq, sbn, io)) return false;
-  return b->inverted || launch_solve(b);
+  return b->inverted || launch_solve(rq, b);
 }
 
 bool nanorq_precalculate(nanorq *rq) { /* :393-401 */
   struct block *b = get_block(rq, 0);
   if (!b) return false;
+  if (!b->sv) return true; /* small blocks: the program is built (and cached per K) with the first solve */
   return rqb_solver_plan_encode(b->sv, 1, b->win_cap) == 0;
 }
 
 /* source symbol esi as the block was loaded (zero-padded past the end of the object) */
 static void copy_source_symbol(nanorq *rq, const struct block *b, uint32_t esi, uint8_t *dst) {
   if (!b->src_mem) {
-    memcpy(dst, rqb_solver_staging(b->sv) + (size_t)esi * b->pitch, rq->T);
+    memcpy(dst, stage(b) + (size_t)esi * b->pitch, rq->T);
     return;
   }
   const size_t off = (size_t)esi * rq->T;
@@ -475,7 +511,7 @@ size_t nanorq_encode_range(nanorq *rq, uint8_t sbn, uint32_t esi0, uint32_t n, v
    * destination is page-locked) -- the host never touches the bytes */
   if (esi < b->K) {
     const uint32_t m = b->K - esi < left ? b->K - esi : left;
-    if (!xp("XP_NO_SRC_D2H") && rqb_solver_fetch_rows(b->sv, 0, esi, m, out, pitch, 0)) return 0;
+    if (rqb_solver_fetch_rows(b->sv, 0, esi, m, out, pitch, 0)) return 0;
     out += (size_t)m * pitch;
     esi += m;
     left -= m;
@@ -508,7 +544,7 @@ void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn) { /* :437-451 */
 void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
   struct block *b = rq->blocks[sbn];
   if (!b) return;
-  if (b->win_pending || b->src_mem) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
+  if (b->sv) rqb_solver_sync(b->sv); /* the staging rows are about to be rewritten */
   b->loaded = b->inverted = b->win_pending = b->win_on_host = b->deferred = false;
   b->win_n = 0;
   b->loaded_rows = 0;
@@ -540,6 +576,7 @@ static inline void mask_set(struct block *b, uint32_t id) { b->mask[id / 32] |= 
 
 /* staging rows [staged_lo, staged_hi) hold symbols not yet queued for upload */
 static bool flush_staged(struct block *b) {
+  if (!b->sv) return true; /* no context yet: the rows wait in plain memory (need_ctx moves them) */
   if (b->staged_hi > b->staged_lo && rqb_solver_upload(b->sv, b->staged_lo, b->staged_hi - b->staged_lo)) return false;
   b->staged_lo = b->staged_hi = b->landed;
   return true;
@@ -607,7 +644,10 @@ int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx
   int st = classify(rq, b, esi);
   if (st != NANORQ_SYM_ADDED) return st;
   const uint32_t row = b->landed;
-  rqb_copy_stream(rqb_solver_staging(b->sv) + (size_t)row * b->pitch, data, rq->T);
+  if (b->sv)
+    rqb_copy_stream(rqb_solver_staging(b->sv) + (size_t)row * b->pitch, data, rq->T);
+  else
+    memcpy(b->lazy_stage + (size_t)row * b->pitch, data, rq->T);
   PF(RQB_PF_ADD_COPY);
   if (b->staged_hi != row) { /* rows of a batch call lie in between: start a new pending range */
     if (!flush_staged(b)) return NANORQ_SYM_ERR;
@@ -667,7 +707,12 @@ int nanorq_decoder_add_symbols(nanorq *rq, const uint32_t *tags, const void *dat
       int st = q < take ? classify(rq, b, esi) : NANORQ_SYM_ERR;
       if (st == NANORQ_SYM_ADDED) {
         if (!copied) { /* first accepted symbol of the run: queue the copy of the run's rows */
-          if (!flush_staged(b) || (!xp("XP_NO_RING_H2D") && rqb_solver_upload_rows(b->sv, row0, (uint32_t)take, rows + k * pitch, pitch))) {
+          if (!b->sv) { /* a small block without a context: its rows are collected by the CPU */
+            for (size_t r = 0; r < take; r++)
+              memcpy(b->lazy_stage + (size_t)(row0 + r) * b->pitch, rows + (k + r) * pitch, rq->T);
+            copied = true;
+            b->landed = row0 + (uint32_t)take;
+          } else if (!flush_staged(b) || rqb_solver_upload_rows(b->sv, row0, (uint32_t)take, rows + k * pitch, pitch)) {
             st = NANORQ_SYM_ERR;
           } else {
             copied = true;
@@ -710,9 +755,9 @@ size_t nanorq_num_repair(nanorq *rq, uint8_t sbn) { /* :519-525 */
  * memory with one copy */
 static bool write_block_image(nanorq *rq, struct block *b, const uint32_t *have_esi, const uint32_t *have_row,
                               uint32_t n_have) {
-  if (!xp("XP_NO_COPYROWS") && rqb_solver_copy_in_to_sym(b->sv, have_esi, have_row, n_have)) return false;
+  if (rqb_solver_copy_in_to_sym(b->sv, have_esi, have_row, n_have)) return false;
   const uint32_t full = (uint32_t)(b->out_bytes / rq->T);
-  if (!xp("XP_NO_IMAGE_D2H") && full && rqb_solver_fetch_rows(b->sv, 1, 0, full, b->out_mem, rq->T, 0)) return false;
+  if (full && rqb_solver_fetch_rows(b->sv, 1, 0, full, b->out_mem, rq->T, 0)) return false;
   if (full < b->K && b->out_bytes > (size_t)full * rq->T) { /* the object's short last symbol */
     if (rqb_solver_fetch_syms(b->sv, full, 1, NULL, 0)) return false;
     memcpy(b->out_mem + (size_t)full * rq->T, rqb_solver_sym_mirror(b->sv) + (size_t)full * b->pitch,
@@ -772,7 +817,7 @@ static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repa
   const bool deferred = deferred_output(rq, sbn, b, io);
   /* the symbol bytes start moving to the GPU while the host analyses the matrix */
   PF_T0;
-  if (!flush_staged(b)) return -1;
+  if (!need_ctx(rq, b) || !flush_staged(b)) return -1;
   PF(RQB_PF_REP_UPLOAD);
   size_t nlt = (size_t)Kp + overhead;
   uint32_t *isi = malloc(sizeof(uint32_t) * nlt), *in_row = malloc(sizeof(uint32_t) * nlt);

@@ -123,10 +123,12 @@ typedef struct pool_ent {
 static pool_ent *g_pool;
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 /* bytes parked in the pool and in recycled solver contexts, and their limit
- * (rqb_set_cache_limit / NANORQ_B200_CACHE_MB; default 8 GiB).  What would go over the
- * limit is handed back to the driver instead of being kept. */
+ * (rqb_set_cache_limit / NANORQ_B200_CACHE_MB; default 48 GiB of the B200's 180: sixteen threads
+ * working on maximum-size blocks, K = 56403, keep 10 GiB of contexts in rotation, and a limit below
+ * the working set turns every block into cudaMalloc + cudaFree).  What would go over the limit is
+ * handed back to the driver instead of being kept. */
 static _Atomic size_t g_pool_bytes, g_shell_bytes;
-static _Atomic size_t g_cache_limit = (size_t)8 << 30;
+static _Atomic size_t g_cache_limit = (size_t)48 << 30;
 static pthread_once_t g_cache_once = PTHREAD_ONCE_INIT;
 static void cache_limit_init(void) {
   const char *e = getenv("NANORQ_B200_CACHE_MB");

@@ -54,7 +54,7 @@ def test_soak_1000_objects_of_mixed_shapes_keeps_memory_flat():
         nb.release_cached()
         assert nb.cache_stats()[0] == 0
     finally:
-        nb.set_cache_limit(8 << 30)
+        nb.set_cache_limit(48 << 30)
 
 
 def test_release_cached_returns_memory_to_the_driver():
