@@ -1805,11 +1805,25 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
      * nothing but the bytes of its row of G; only the entries some row uses (and the two
      * half-table entries they are made of) are computed */
     uint8_t *used8 = sc_buf(sc, SC_FRUSED, (size_t)ng * 256 + 64, 1);
+    /* a decoder only back-substitutes the peeled rows whose symbol is a term of one of its outputs
+     * (at 10 % loss about two thirds of them) */
+    uint8_t *needed = sc_buf(sc, SC_NEEDED, (size_t)L + 8, 0);
     OOM_CHECK();
+    if (req->want_c) {
+      memset(needed, 1, (size_t)L);
+    } else {
+      memset(needed, 0, (size_t)L);
+      for (int k = 0; k < req->n_out; k++) {
+        uint32_t idx[RQB_MAX_LT_DEGREE];
+        int cnt = rqb_host_lt_indices(&P, req->out_isi[k], idx);
+        for (int q = 0; q < cnt; q++) needed[idx[q]] = 1;
+      }
+    }
     const uint32_t tab0 = bd.ws_next;
     bd.tab_base = bd.ws_base + tab0;
     bd.ws_next += (uint32_t)ng * 256u;
     for (int p = 0; p < I; p++) {
+      if (!needed[pcol[p]]) continue;
       const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
       for (int j = 0; j < ng; j++) used8[(size_t)j * 256 + g[j]] = 1;
     }
@@ -1840,6 +1854,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
     end = lv + 2;
     for (int p = 0; p < I; p++) {
+      if (!needed[pcol[p]]) continue; /* nobody reads this x_p */
       const uint8_t *g = (const uint8_t *)(G + (size_t)p * uw);
       int any = 0;
       for (int j = 0; j < ng; j++) any |= g[j];
