@@ -303,11 +303,9 @@ def run_own(args, rank, world, local_rank):
     for sd in range(seed_ctr[0], seed_ctr[0] + n_sets * NB):
         request_for(sd)
 
-    def plan_one(which, b, seed):
+    def plan_one(which, b, seed, extra=0):
         # host analysis of the block's constraint matrix + program emission + upload of the program
-        # (rqb_solver_plan; ctypes releases the GIL, so the pool's threads plan in parallel)
         d = dsets[which][b]
-        extra = 0
         while True:
             req, missing = request_for(seed, extra)
             if d.plan(req) == 0:
@@ -315,10 +313,23 @@ def run_own(args, rank, world, local_rank):
             extra += 2  # singular at overhead 0 (~1 % of patterns): two more repair symbols, like the e2e harness
         missing_of[which][b] = missing
 
+    def plan_all(which, seeds):
+        # rqb_solver_plan_batch: one C call plans the NB blocks on `threads` host threads (no interpreter
+        # in the way); the few patterns that are singular at overhead 0 are re-planned with two more symbols
+        reqs = [request_for(sd) for sd in seeds]
+        rcs = nb.Solver.plan_batch(dsets[which], [r for r, _ in reqs], threads)
+        for b, rc in enumerate(rcs):
+            if rc == 0:
+                missing_of[which][b] = reqs[b][1]
+            elif rc == 1:
+                plan_one(which, b, seeds[b], extra=2)
+            else:
+                raise SystemExit("rqb_solver_plan failed (%d)" % rc)
+
     def plan_set(which):
         seeds = [seed_ctr[0] + b for b in range(NB)]
         seed_ctr[0] += NB
-        return [pool.submit(plan_one, which, b, seeds[b]) for b in range(NB)]
+        return [pool.submit(plan_all, which, seeds)]  # one helper thread makes the call; the main thread launches kernels
 
     def wait_all(futs):
         for f in futs:

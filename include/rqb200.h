@@ -146,6 +146,15 @@ typedef struct {
  * process-wide, per K) the plan of an encoder: isi = identity, rows 0..K-1. */
 int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req);
 int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_repair_with_solve);
+/* rqb_solver_plan for n independent blocks on up to nthreads host threads (the analysis of one block
+ * is single-threaded: ~2 ms at K=4096, ~40 ms at K=56403; blocks are independent, so a caller that
+ * holds several plans them side by side).  rc[k] receives what rqb_solver_plan(solvers[k], &reqs[k])
+ * returns; the function returns the number of blocks whose rc is 0.  nthreads <= 1: in the calling
+ * thread. */
+int rqb_solver_plan_batch(rqb_solver **solvers, const rqb_solve_request *reqs, int n, int nthreads, int *rc);
+/* host threads nanorq_repair_blocks uses for the analysis of its blocks (default 1) */
+void rqb_set_plan_threads(int n);
+int rqb_get_plan_threads(void);
 /* launch the solve kernel (asynchronous on the solver's stream) */
 int rqb_solver_run(rqb_solver *s);
 /* LT-combine further symbols from the intermediate symbols kept by want_c */

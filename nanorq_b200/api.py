@@ -138,6 +138,9 @@ def lib():
     sig("rqb_solver_upload", C.c_int, vp, C.c_uint32, C.c_uint32)
     sig("rqb_solver_plan", C.c_int, vp, C.POINTER(_SolveRequest))
     sig("rqb_solver_plan_encode", C.c_int, vp, C.c_int, C.c_uint32)
+    sig("rqb_solver_plan_batch", C.c_int, C.POINTER(vp), C.POINTER(_SolveRequest), C.c_int, C.c_int, C.POINTER(C.c_int))
+    sig("rqb_set_plan_threads", None, C.c_int)
+    sig("rqb_get_plan_threads", C.c_int)
     sig("rqb_solver_run", C.c_int, vp)
     sig("rqb_solver_emit", C.c_int, vp, u32p, C.c_uint32)
     sig("rqb_solver_sync", C.c_int, vp)
@@ -209,6 +212,7 @@ EXPORTED_SYMBOLS = [
     "ioctx_from_pinned_mem", "nanorq_repair_blocks", "nanorq_encode_range", "nanorq_decoder_add_symbols", "nanorq_set_devices",
     "rqb_solver_create_on", "rqb_solver_device", "rqb_solver_set_flavour", "rqb_solver_upload_rows",
     "rqb_solver_fetch_rows", "rqb_solver_copy_in_to_sym", "rqb_host_alloc", "rqb_host_release", "rqb_host_pin", "rqb_set_usolve_mode",
+    "rqb_solver_plan_batch", "rqb_set_plan_threads", "rqb_get_plan_threads",
     "rqb_host_unpin",
 ]
 
@@ -672,6 +676,17 @@ class Solver:
         st = SolverStats()
         _check(lib().rqb_solver_get_stats(self.h, C.byref(st)), "rqb_solver_get_stats")
         return st.as_dict()
+
+    @staticmethod
+    def plan_batch(solvers, requests, nthreads):
+        """rqb_solver_plan_batch: plan requests[k] on solvers[k], up to nthreads host threads in C.
+        -> list of per-block return codes (0 ok, 1 = needs more symbols)."""
+        n = len(solvers)
+        arr = (vp * n)(*[s.h for s in solvers])
+        reqs = (_SolveRequest * n)(*[r.c for r in requests])
+        rc = (C.c_int * n)()
+        lib().rqb_solver_plan_batch(arr, reqs, n, int(nthreads), rc)
+        return list(rc)
 
     @staticmethod
     def run_batch(solvers, owner=None):

@@ -793,15 +793,21 @@ struct repair_job {
   bool deferred;
   uint32_t *missing, *have; /* missing ESIs; deferred output: [K] ESIs received, then [K] their input rows */
   size_t nm, nh;
+  rqb_solve_request req; /* valid between repair_request and repair_planned */
+  uint32_t *isi, *in_row;
 };
 
 static void repair_job_free(struct repair_job *j) {
   free(j->missing);
   free(j->have);
-  j->missing = j->have = NULL;
+  free(j->isi);
+  free(j->in_row);
+  j->missing = j->have = j->isi = j->in_row = NULL;
 }
 
-static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repair_job *j, bool *result) {
+/* step 1a: the request (which symbol is where).  1 = built (j->req is valid until repair_job_free),
+ * 0 = nothing to run (*result), -1 = error */
+static int repair_request(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repair_job *j, bool *result) {
   memset(j, 0, sizeof(*j));
   struct block *b = get_block(rq, sbn);
   *result = false;
@@ -855,11 +861,11 @@ static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repa
     in_row[Kp + x] = b->rep_row[rep];
   }
   /* deferred output: the recovered symbol of ESI e is written to emitted-symbol row e */
-  rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing, deferred ? missing : NULL};
+  const rqb_solve_request req = {(int)overhead, isi, in_row, 0, (uint32_t)nm, missing, deferred ? missing : NULL};
   PF(RQB_PF_REP_REQUEST);
-  int rc = rqb_solver_plan(b->sv, &req); /* charges repair.plan / .pages / .args itself */
-  free(isi);
-  free(in_row);
+  j->req = req;
+  j->isi = isi;
+  j->in_row = in_row;
   j->b = b;
   j->sbn = sbn;
   j->deferred = deferred;
@@ -867,12 +873,26 @@ static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repa
   j->have = have;
   j->nm = nm;
   j->nh = nh;
+  return 1;
+}
+
+/* step 1b after rqb_solver_plan returned rc for j->req: 1 = ready to run, -1 = singular / error */
+static int repair_planned(struct repair_job *j, int rc) {
+  free(j->isi);
+  free(j->in_row);
+  j->isi = j->in_row = NULL;
   if (rc != 0) {
-    rqb_solver_sync(b->sv);
+    rqb_solver_sync(j->b->sv);
     repair_job_free(j);
     return -1;
   }
   return 1;
+}
+
+static int repair_prepare(nanorq *rq, struct ioctx *io, uint8_t sbn, struct repair_job *j, bool *result) {
+  int st = repair_request(rq, io, sbn, j, result);
+  if (st <= 0) return st;
+  return repair_planned(j, rqb_solver_plan(j->b->sv, &j->req)); /* charges repair.plan / .pages / .args itself */
 }
 
 static bool repair_finish(nanorq *rq, struct ioctx *io, struct repair_job *j) {
@@ -936,12 +956,45 @@ size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, s
       free(state);
       return good;
     }
+    /* requests first (cheap), then the analysis of all blocks side by side on the planning threads
+     * (rqb_set_plan_threads; 1 = in this thread) */
+    size_t np = 0;
     for (size_t k = 0; k < m; k++) {
       bool result = false;
-      state[k] = repair_prepare(rq, io, sbns[at + k], &jobs[k], &result);
+      state[k] = repair_request(rq, io, sbns[at + k], &jobs[k], &result);
       if (state[k] == 0 && ok) ok[at + k] = result;
       if (state[k] < 0 && ok) ok[at + k] = false;
       if (state[k] == 0 && result) good++;
+      if (state[k] == 1) np++;
+    }
+    if (np) {
+      rqb_solve_request *reqs = malloc(sizeof(*reqs) * np);
+      int *rcs = malloc(sizeof(int) * np);
+      if (!reqs || !rcs) {
+        free(reqs);
+        free(rcs);
+        for (size_t k = 0; k < m; k++)
+          if (state[k] == 1) repair_job_free(&jobs[k]);
+        free(jobs);
+        free(sv);
+        free(state);
+        return good;
+      }
+      size_t q = 0;
+      for (size_t k = 0; k < m; k++)
+        if (state[k] == 1) {
+          reqs[q] = jobs[k].req;
+          sv[q++] = jobs[k].b->sv;
+        }
+      rqb_solver_plan_batch(sv, reqs, (int)np, rqb_get_plan_threads(), rcs);
+      q = 0;
+      for (size_t k = 0; k < m; k++)
+        if (state[k] == 1) {
+          state[k] = repair_planned(&jobs[k], rcs[q++]);
+          if (state[k] < 0 && ok) ok[at + k] = false;
+        }
+      free(reqs);
+      free(rcs);
     }
     /* launches: one per device among the prepared blocks */
     for (int dev = 0; dev < 64; dev++) {

@@ -5,6 +5,7 @@
  * file: symbol bytes are only ever combined on the GPU. */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -991,6 +992,96 @@ int rqb_solver_plan(rqb_solver *s, const rqb_solve_request *req) {
   PF(RQB_PF_REP_ARGS);
   return rc;
 }
+
+/* ---------------------------------------------------- planning several blocks */
+typedef struct {
+  rqb_solver **sv;
+  const rqb_solve_request *reqs;
+  int n, *rc;
+  _Atomic int next, good;
+} plan_batch;
+
+static void *plan_batch_worker(void *arg) {
+  plan_batch *pb = arg;
+  for (;;) {
+    const int k = pb->next++;
+    if (k >= pb->n) break;
+    const int rc = rqb_solver_plan(pb->sv[k], &pb->reqs[k]);
+    if (pb->rc) pb->rc[k] = rc;
+    if (rc == 0) pb->good++;
+  }
+  return NULL;
+}
+
+/* Worker threads are kept (the planner's per-thread scratch arenas and the u-solve contexts stay warm:
+ * a fresh thread would allocate and fault in megabytes for every call).  One batch at a time uses the
+ * pool; a caller that finds it taken plans in its own thread. */
+#define PLAN_POOL_MAX 64
+static struct {
+  pthread_t th;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  plan_batch *job;
+} g_pw[PLAN_POOL_MAX];
+static int g_npw;
+static pthread_mutex_t g_pool_use = PTHREAD_MUTEX_INITIALIZER, g_done_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_done_cv = PTHREAD_COND_INITIALIZER;
+static int g_pending;
+
+static void *plan_pool_worker(void *arg) {
+  const int me = (int)(intptr_t)arg;
+  for (;;) {
+    pthread_mutex_lock(&g_pw[me].mu);
+    while (!g_pw[me].job) pthread_cond_wait(&g_pw[me].cv, &g_pw[me].mu);
+    plan_batch *job = g_pw[me].job;
+    g_pw[me].job = NULL;
+    pthread_mutex_unlock(&g_pw[me].mu);
+    plan_batch_worker(job);
+    pthread_mutex_lock(&g_done_mu);
+    if (--g_pending == 0) pthread_cond_signal(&g_done_cv);
+    pthread_mutex_unlock(&g_done_mu);
+  }
+  return NULL;
+}
+
+int rqb_solver_plan_batch(rqb_solver **solvers, const rqb_solve_request *reqs, int n, int nthreads, int *rc) {
+  if (n <= 0 || !solvers || !reqs) return 0;
+  plan_batch pb = {solvers, reqs, n, rc, 0, 0};
+  if (nthreads > n) nthreads = n;
+  if (nthreads > PLAN_POOL_MAX + 1) nthreads = PLAN_POOL_MAX + 1;
+  if (nthreads > 1 && pthread_mutex_trylock(&g_pool_use) == 0) {
+    while (g_npw < nthreads - 1) { /* the calling thread is worker 0 */
+      pthread_mutex_init(&g_pw[g_npw].mu, NULL);
+      pthread_cond_init(&g_pw[g_npw].cv, NULL);
+      g_pw[g_npw].job = NULL;
+      if (pthread_create(&g_pw[g_npw].th, NULL, plan_pool_worker, (void *)(intptr_t)g_npw) != 0) break;
+      pthread_detach(g_pw[g_npw].th);
+      g_npw++;
+    }
+    const int helpers = g_npw < nthreads - 1 ? g_npw : nthreads - 1;
+    pthread_mutex_lock(&g_done_mu);
+    g_pending = helpers;
+    pthread_mutex_unlock(&g_done_mu);
+    for (int t = 0; t < helpers; t++) {
+      pthread_mutex_lock(&g_pw[t].mu);
+      g_pw[t].job = &pb;
+      pthread_cond_signal(&g_pw[t].cv);
+      pthread_mutex_unlock(&g_pw[t].mu);
+    }
+    plan_batch_worker(&pb);
+    pthread_mutex_lock(&g_done_mu);
+    while (g_pending > 0) pthread_cond_wait(&g_done_cv, &g_done_mu);
+    pthread_mutex_unlock(&g_done_mu);
+    pthread_mutex_unlock(&g_pool_use);
+  } else {
+    plan_batch_worker(&pb);
+  }
+  return pb.good;
+}
+
+static _Atomic int g_plan_threads = 1;
+void rqb_set_plan_threads(int n) { g_plan_threads = n < 1 ? 1 : n; }
+int rqb_get_plan_threads(void) { return g_plan_threads; }
 
 int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
   BIND(s->dev);

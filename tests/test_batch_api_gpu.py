@@ -282,3 +282,54 @@ def test_repair_blocks_one_launch_for_all_blocks_of_an_object(pinned_out):
     dec.close(); io.close()
     for b in keepalive:
         b.close()
+
+
+def test_plan_batch_on_several_threads_gives_the_same_results():
+    """rqb_solver_plan_batch: 24 decode blocks planned on 6 host threads, one batched launch, results
+    against the source; a singular request in the batch comes back as 1 without disturbing the others."""
+    from nanorq_b200 import workload
+    K, T, n = 1024, 256, 24
+    p = nb.block_params(K)
+    srcs, decs, reqs, miss = [], [], [], []
+    for b in range(n):
+        src = workload.payload(K, T, 50 + b)
+        e = nb.Solver(K, T, max_in=K, max_out=128)
+        e.staging[:K, :T] = src
+        e.upload(0, K)
+        e.plan_encode(True, 128)
+        e.run()
+        rep = e.fetch_syms(128)
+        e.close()
+        drop = workload.loss_pattern(K, 0.08, b)
+        esis = workload.received_esis(K, drop, 2, 0)
+        req, missing = nb.SolveRequest.for_decoder(K, esis, want_c=False)
+        if b == 7:  # make this one singular: the same repair symbol for two missing source symbols
+            isi = req.isi.copy()
+            isi[missing[1]] = isi[missing[0]]
+            req = nb.SolveRequest(isi, req.in_row, req.c.overhead, False, missing)
+        d = nb.Solver(K, T, max_in=len(esis), max_out=len(missing))
+        d.staging[:len(esis), :T] = np.concatenate([src[~drop], rep[:len(esis) - int((~drop).sum())]])
+        d.upload(0, len(esis))
+        srcs.append(src); decs.append(d); reqs.append(req); miss.append(missing)
+    rcs = nb.Solver.plan_batch(decs, reqs, 6)
+    assert rcs == [0] * 7 + [1] + [0] * 16
+    good = [d for k, d in enumerate(decs) if rcs[k] == 0]
+    nb.Solver.run_batch(good, good[0])
+    for k, d in enumerate(decs):
+        if rcs[k] == 0:
+            assert np.array_equal(d.fetch_syms(len(miss[k])), srcs[k][miss[k]]), k
+        d.close()
+    # and through nanorq_repair_blocks with planning threads switched on
+    nb.lib().rqb_set_plan_threads(4)
+    try:
+        F, T2, K2 = 8 * 512 * 128, 128, 512
+        payload, oti, tags, rows = make_packets(F, T2, K2, 0, 0.1, 2, seed=77)
+        dec = nb.Decoder(*oti)
+        out = np.zeros(F, np.uint8)
+        io = nb.MemIO(out)
+        assert dec.add_symbols(tags, rows, io)[0] >= 0
+        assert dec.repair_blocks(io, list(range(8))) == [True] * 8
+        assert np.array_equal(out, payload)
+        dec.close(); io.close()
+    finally:
+        nb.lib().rqb_set_plan_threads(1)
