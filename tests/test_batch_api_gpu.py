@@ -303,9 +303,9 @@ def test_plan_batch_on_several_threads_gives_the_same_results():
         drop = workload.loss_pattern(K, 0.08, b)
         esis = workload.received_esis(K, drop, 2, 0)
         req, missing = nb.SolveRequest.for_decoder(K, esis, want_c=False)
-        if b == 7:  # make this one singular: the same repair symbol for two missing source symbols
-            isi = req.isi.copy()
-            isi[missing[1]] = isi[missing[0]]
+        if b == 7:  # make this one singular: one repair symbol stands in for four missing source symbols
+            isi = req.isi.copy()           # (two more equal rows than the overhead of 2 can make up for)
+            isi[missing[1]] = isi[missing[2]] = isi[missing[3]] = isi[missing[0]]
             req = nb.SolveRequest(isi, req.in_row, req.c.overhead, False, missing)
         d = nb.Solver(K, T, max_in=len(esis), max_out=len(missing))
         d.staging[:len(esis), :T] = np.concatenate([src[~drop], rep[:len(esis) - int((~drop).sum())]])
