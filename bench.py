@@ -566,7 +566,11 @@ def run_own(args, rank, world, local_rank):
                                       "analysed on the host (%d threads) and its solve program built and uploaded INSIDE the "
                                       "timed region, overlapped with the previous step's kernels; wall clock between device "
                                       "synchronisations" % threads,
-                       "host_plan_ms_per_block_one_thread": plan_ms},
+                       "host_plan_ms_per_block_one_thread": plan_ms,
+                       "value_bound": "host: the rank's %d planning threads build %d fresh decode programs per step (%.1f ms of "
+                                      "host work against %.1f ms of kernels); ranks of one node share its cores, so value is "
+                                      "flat in N on a node while kernel_only scales with the GPUs" % (
+                                          threads, NB, NB * plan_ms / threads, k_ms_step)},
             "kernel_only": kernel_only, "c4_literal": c4,
             "roofline": roofline, "row_axpy": row_axpy, "cpu_baseline": cpu, "e2e": e2e, "e2e_batch": e2e_batch,
             "gpu_launches": launches, "h2d_bytes_per_step": (h1 - h0) // args.steps, "clocks": clocks,
