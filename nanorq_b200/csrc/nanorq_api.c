@@ -950,20 +950,34 @@ size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, s
     struct repair_job *jobs = calloc(m, sizeof(*jobs));
     rqb_solver **sv = calloc(m, sizeof(*sv));
     int *state = calloc(m, sizeof(*state));
-    if (!jobs || !sv || !state) {
+    bool *res = calloc(m, sizeof(*res)); /* outcome per entry (ok[] is optional) */
+    if (!jobs || !sv || !state || !res) {
       free(jobs);
       free(sv);
       free(state);
+      free(res);
       return good;
     }
+#define SET_RESULT(k, v)              \
+  do {                                \
+    res[k] = (v);                     \
+    if (ok) ok[at + (k)] = res[k];    \
+  } while (0)
     /* requests first (cheap), then the analysis of all blocks side by side on the planning threads
      * (rqb_set_plan_threads; 1 = in this thread) */
     size_t np = 0;
     for (size_t k = 0; k < m; k++) {
       bool result = false;
+      int first = -1; /* a block listed twice is repaired once; the later entries report the same outcome */
+      for (size_t q = 0; q < k && first < 0; q++)
+        if (sbns[at + q] == sbns[at + k]) first = (int)q;
+      if (first >= 0) {
+        state[k] = -2 - first;
+        continue;
+      }
       state[k] = repair_request(rq, io, sbns[at + k], &jobs[k], &result);
-      if (state[k] == 0 && ok) ok[at + k] = result;
-      if (state[k] < 0 && ok) ok[at + k] = false;
+      if (state[k] == 0) SET_RESULT(k, result);
+      if (state[k] < 0) SET_RESULT(k, false);
       if (state[k] == 0 && result) good++;
       if (state[k] == 1) np++;
     }
@@ -978,6 +992,7 @@ size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, s
         free(jobs);
         free(sv);
         free(state);
+        free(res);
         return good;
       }
       size_t q = 0;
@@ -991,7 +1006,7 @@ size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, s
       for (size_t k = 0; k < m; k++)
         if (state[k] == 1) {
           state[k] = repair_planned(&jobs[k], rcs[q++]);
-          if (state[k] < 0 && ok) ok[at + k] = false;
+          if (state[k] < 0) SET_RESULT(k, false);
         }
       free(reqs);
       free(rcs);
@@ -1008,15 +1023,22 @@ size_t nanorq_repair_blocks(nanorq *rq, struct ioctx *io, const uint8_t *sbns, s
             rqb_solver_sync(jobs[k].b->sv);
             repair_job_free(&jobs[k]);
             state[k] = -1;
-            if (ok) ok[at + k] = false;
+            SET_RESULT(k, false);
           }
     }
     for (size_t k = 0; k < m; k++) {
+      if (state[k] <= -2) { /* listed before: entry -2 - state[k] has the outcome */
+        SET_RESULT(k, res[(size_t)(-2 - state[k])]);
+        good += res[k];
+        continue;
+      }
       if (state[k] != 1) continue;
       const bool r = repair_finish(rq, io, &jobs[k]);
-      if (ok) ok[at + k] = r;
+      SET_RESULT(k, r);
       good += r;
     }
+#undef SET_RESULT
+    free(res);
     free(jobs);
     free(sv);
     free(state);

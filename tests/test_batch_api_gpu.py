@@ -279,6 +279,14 @@ def test_repair_blocks_one_launch_for_all_blocks_of_an_object(pinned_out):
     assert rc > 0
     assert dec.repair_blocks(io, [5, 0, 3]) == [True, True, True]
     assert np.array_equal(out, payload)
+    # a block listed twice is repaired once
+    dec2 = nb.Decoder(*oti)
+    out2 = np.zeros(F, np.uint8)
+    io2 = nb.MemIO(out2)
+    assert dec2.add_symbols(tags, rows, io2)[0] >= 0
+    assert dec2.repair_blocks(io2, [1, 1, 2, 1, 0, 3, 4, 5, 6, 7, 7]) == [True] * 11
+    assert np.array_equal(out2, payload)
+    dec2.close(); io2.close()
     dec.close(); io.close()
     for b in keepalive:
         b.close()
