@@ -778,30 +778,23 @@ rqb_usolve_kernel(uint8_t *__restrict__ buf) {
 }
 
 // ---------------------------------------------------------------- LT kernel
-// One WARP per output symbol, four symbols per CTA: lane 0 expands Tuple[K', isi] into row indices
-// (about thirty dependent table look-ups), the warp then XORs the rows 512 bytes per pass.  Only warp-level
-// synchronisation: with a CTA per symbol every warp waited at a CTA barrier for one thread's tuple
-// expansion (13.5 barrier-stall cycles per issue in the round-1 capture).
-static constexpr int kLtWarps = 4;
-__global__ void __launch_bounds__(32 * kLtWarps)
+// one CTA per output symbol; lane 0 expands Tuple[K', isi] into row indices.
+__global__ void __launch_bounds__(128)
 rqb_lt_kernel(rqb_params P, const uint8_t *__restrict__ c, uint32_t c_pitch,
-              const uint32_t *__restrict__ isi, uint32_t n, uint8_t *__restrict__ out, uint32_t out_pitch,
+              const uint32_t *__restrict__ isi, uint8_t *__restrict__ out, uint32_t out_pitch,
               uint32_t width) {
-  __shared__ uint32_t idx[kLtWarps][RQB_MAX_LT_DEGREE];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sym = blockIdx.x * kLtWarps + warp;
-  if (sym >= n) return; // whole warp
-  int cnt = 0;
-  if (lane == 0) cnt = rqb_lt_indices(&P, c_rand_v, c_degree_cdf, isi[sym], idx[warp]);
-  cnt = __shfl_sync(0xffffffffu, cnt, 0);
-  __syncwarp(); // lane 0's writes to idx[] are visible to the other lanes
-  for (uint32_t v = lane * 16; v < width; v += 32 * 16) {
+  __shared__ uint32_t idx[RQB_MAX_LT_DEGREE];
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = rqb_lt_indices(&P, c_rand_v, c_degree_cdf, isi[blockIdx.x], idx);
+  __syncthreads();
+  const int n = cnt;
+  for (uint32_t v = threadIdx.x * 16; v < width; v += blockDim.x * 16) {
     uint4 acc = make_uint4(0, 0, 0, 0);
-    for (int k = 0; k < cnt; k++) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4 *>(c + (size_t)idx[warp][k] * c_pitch + v));
+    for (int k = 0; k < n; k++) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4 *>(c + (size_t)idx[k] * c_pitch + v));
       acc.x ^= x.x; acc.y ^= x.y; acc.z ^= x.z; acc.w ^= x.w;
     }
-    *reinterpret_cast<uint4 *>(out + (size_t)sym * out_pitch + v) = acc;
+    *reinterpret_cast<uint4 *>(out + (size_t)blockIdx.x * out_pitch + v) = acc;
   }
 }
 
@@ -1212,8 +1205,7 @@ int rqb_launch_lt(const rqb_params *P, const uint8_t *c, uint32_t c_pitch, const
   if (n == 0) return 0;
   int e = ensure_consts();
   if (e) return e;
-  rqb_lt_kernel<<<(n + kLtWarps - 1) / kLtWarps, 32 * kLtWarps, 0, (cudaStream_t)stream>>>(*P, c, c_pitch, isi_dev, n, out,
-                                                                                           out_pitch, width);
+  rqb_lt_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(*P, c, c_pitch, isi_dev, out, out_pitch, width);
   g_launches++;
   CK(cudaGetLastError());
   return 0;
