@@ -1139,6 +1139,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
     }
   }
   const int nnz = rptr[R];
+  FINE(20);
   /* column lists */
   int *cptr = sc_buf(sc, SC_CPTR, ((size_t)L + 1) * sizeof(int), 1);
   int *ridx = sc_buf(sc, SC_RIDX, sizeof(int) * (size_t)(nnz ? nnz : 1), 0);
@@ -1153,6 +1154,7 @@ int rqb_plan_build(const rqb_plan_request *req, rqb_plan **out) {
       for (int k = rptr[r]; k < rptr[r + 1]; k++) ridx[cur[cidx[k]]++] = r;
   }
   double t1 = now_s();
+  FINE(21);
 
   /* ---- 2. peeling */
   uint8_t *col_state = sc_buf(sc, SC_COLSTATE, (size_t)L, 1); /* 0 active, 1 peeled, 2 inactive */

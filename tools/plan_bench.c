@@ -22,6 +22,6 @@ int main(int argc,char**argv){
     if(rc==0){tot+=t1-t0;n++; rqb_plan_free(p);} 
   }
   printf("K=%d smem=%d mean %.3f ms over %d\n",K,smem,1e3*tot/n,n);
-  const char*nm[]={"3a G+sched","3b low rows","3c HDPC schur","3d GJ","3e HDPC solve","1+2 matrix+peel","4A tri","4B low+scan","4C1","4C2","4C3/4","4F tables","4E","4O out","write_pages","S load+needed","S chains A+B","S scan+C","S tables+TAB","S outputs"};
-  for(int k=0;k<20;k++) printf("  %-16s %.3f ms\n",nm[k],1e3*rqb_plan_fine[k]/n);
+  const char*nm[]={"3a G+sched","3b low rows","3c HDPC schur","3d GJ","3e HDPC solve","1+2 matrix+peel","4A tri","4B low+scan","4C1","4C2","4C3/4","4F tables","4E","4O out","write_pages","S load+needed","S chains A+B","S scan+C","S tables+TAB","S outputs","1 rows","1 column lists"};
+  for(int k=0;k<22;k++) printf("  %-16s %.3f ms\n",nm[k],1e3*rqb_plan_fine[k]/n);
 }
