@@ -285,6 +285,9 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
   uint32_t max_in, max_out;
   if (rq->max_esi) { /* decoder: every symbol that may arrive lands in its own input row */
     uint32_t spare = rq->max_esi >= K ? rq->max_esi - (uint32_t)K + 1 : 1;
+    /* nanorq_set_max_esi widens the ESI range, not the number of symbols a block can hold: a block
+     * is decodable long before it has collected K' repair symbols beyond its own size */
+    if (spare > (uint32_t)rq->P.Kprime + 1024u) spare = (uint32_t)rq->P.Kprime + 1024u;
     max_in = (uint32_t)rq->P.Kprime + spare;
     max_out = (uint32_t)K;
     b->mask_words = rq->max_esi / 32 + 2;
@@ -311,7 +314,7 @@ static struct block *get_block(nanorq *rq, uint8_t sbn) { /* get_block_encoder :
       block_free(b);
       return NULL;
     }
-    b->lazy_stage = malloc((size_t)max_in * b->pitch);
+    b->lazy_stage = calloc((size_t)max_in, b->pitch); /* zeroed: the pad bytes of a row travel with it */
     if (!b->lazy_stage) {
       block_free(b);
       return NULL;
@@ -551,6 +554,9 @@ void nanorq_encoder_reset(nanorq *rq, uint8_t sbn) { /* :453-469 */
   b->src_mem = NULL;
   b->nrep = 0;
   b->landed = b->staged_lo = b->staged_hi = 0;
+  b->written = b->out_decided = false; /* the next round may come with another output ioctx */
+  b->out_mem = NULL;
+  b->out_bytes = 0;
   if (b->mask) {
     memset(b->mask, 0, b->mask_words * sizeof(uint32_t));
     b->gaps = b->K;

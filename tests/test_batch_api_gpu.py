@@ -149,6 +149,31 @@ def test_pinned_output_block_completed_by_the_last_source_symbol():
     dec.close(); io.close(); pb.close(); ob.close()
 
 
+def test_decoder_reset_with_deferred_output_decodes_again():
+    """nanorq_encoder_reset (nanorq.h:79) on a decoder block whose output is handed back as a block
+    image: the second round is written too, into whatever ioctx it comes with."""
+    F, T, K = 600 * 1280, 1280, 600
+    dec = None
+    for rnd, (loss, seed) in enumerate([(0.0, 21), (0.1, 22)]):
+        payload, oti, tags, rows = make_packets(F, T, K, 0, loss, 2, seed=seed)
+        pb, parr = pinned_array(rows.size)
+        parr[:] = rows.reshape(-1)
+        ob, out = pinned_array(F)
+        out[:] = 0
+        io = nb.PinnedMemIO(out)
+        if dec is None:
+            dec = nb.Decoder(*oti)
+        else:
+            dec.encoder_reset(0)
+            assert dec.num_missing(0) == K and dec.num_repair(0) == 0
+        rc, _ = dec.add_symbols(tags, parr.reshape(rows.shape), io)
+        assert rc == (K if loss == 0.0 else len(tags))  # symbols after completion are ignored
+        assert dec.repair_block(io, 0)
+        assert np.array_equal(out, payload), rnd
+        io.close(); pb.close(); ob.close()
+    dec.close()
+
+
 def test_pinned_ioctx_with_the_per_symbol_api_only():
     """ioctx_from_pinned_mem behind the unchanged nanorq.h calls: load by DMA, output deferred."""
     F, T, K = 1000 * 200 - 33, 200, 1000

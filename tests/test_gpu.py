@@ -359,6 +359,28 @@ def test_api_decoder_needs_more_symbols_then_succeeds():
     assert dec.add_symbol(enc.encode(0, 0, io_in), api.tag(0, 0), io_out) == nb.SYM_IGN
 
 
+def test_api_decoder_wide_esi_range():
+    """nanorq_set_max_esi (nanorq.h:85) widens the ESI range up to 2^24-1; the block must not
+    reserve an input row per possible ESI.  Repair symbols with very large ESIs decode."""
+    K, T = 600, 1280
+    rng = np.random.default_rng(12)
+    payload = rng.integers(0, 256, K * T, dtype=np.uint8)
+    enc = nb.Encoder(K * T, T, K, 0, 8)
+    io_in = nb.MemIO(payload)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    assert dec.set_max_esi((1 << 24) - 1)
+    assert not dec.set_max_esi(1 << 24)
+    out = np.zeros(K * T, np.uint8)
+    io_out = nb.MemIO(out)
+    for esi in range(50, K):
+        assert dec.add_symbol(enc.encode(esi, 0, io_in), api.tag(0, esi), io_out) == nb.SYM_ADDED
+    far = [(1 << 24) - 1 - 7919 * i for i in range(52)]
+    for esi in far:
+        assert dec.add_symbol(enc.encode(esi, 0, io_in), api.tag(0, esi), io_out) == nb.SYM_ADDED
+    assert dec.repair_block(io_out, 0) is True
+    assert np.array_equal(out, payload)
+
+
 # ------------------------------------------------- context recycling / arena
 def test_solver_contexts_are_recycled_and_stay_correct():
     """rqb_solver_destroy keeps the context; a later create of the same shape gets it
