@@ -501,7 +501,7 @@ def run_own(args, rank, world, local_rank):
     # ---- e2e arms: host buffers through nanorq.h (per-symbol, the drop-in arm) and nanorq_batch.h
     NBE = e2e_blocks(threads)
 
-    def e2e_arm(so, fn, label):
+    def e2e_arm(so, fn, label, threads=threads, NBE=NBE):
         if args.skip_e2e:
             return None
         for w in range(max(args.warmup, 3)):
@@ -536,8 +536,11 @@ def run_own(args, rank, world, local_rank):
 
     e2e = e2e_arm(os.path.join(nb.api.LIB_DIR, "librq_roundtrip.so"), "rq_roundtrip_run",
                   "nanorq.h per-symbol calls, pageable buffers (bench/rq_roundtrip.c, the source the reference arm runs)")
+    # the batch arm's workers mostly wait for DMA (yielding their core): two per core keep the link busier
+    # (measured on 16 cores: 256 -> 264 Gbit/s; on 4 cores, a rank's share at N=8: 100 -> 143)
     e2e_batch = e2e_arm(os.path.join(nb.api.LIB_DIR, "librq_roundtrip_batch.so"), "rq_roundtrip_batch_run",
-                        "nanorq_batch.h range calls, page-locked buffers (bench/rq_roundtrip_batch.c)")
+                        "nanorq_batch.h range calls, page-locked buffers (bench/rq_roundtrip_batch.c), two workers per core",
+                        threads=2 * threads, NBE=e2e_blocks(2 * threads))
 
     # ---- cpu_baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
