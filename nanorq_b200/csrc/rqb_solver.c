@@ -404,6 +404,7 @@ struct rqb_solver {
   size_t bounce_cap;
   uint32_t *h_pairs, pairs_cap; /* pinned: (input row, emitted row) pairs of rqb_solver_copy_in_to_sym */
   int pairs_pending;            /* a copy kernel reading h_pairs has been queued since the last wait */
+  int batch_args_pending;       /* a batched launch's copy of h_args[1..] has been queued since the last wait */
   /* current program */
   rqb_plan *plan; /* owned unless shared */
   int plan_shared, has_c, timed;
@@ -725,6 +726,7 @@ static int solver_wait(rqb_solver *s) {
   s->pages_pending = 0;
   s->pairs_pending = 0;
   s->isi_pending = 0;
+  s->batch_args_pending = 0;
   return 0;
 }
 
@@ -1213,6 +1215,16 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   }
   cls_at[0] = 0;
   for (int c = 1; c < 4; c++) cls_at[c] = cls_at[c - 1] + cls_n[c - 1];
+  if (own->batch_args_pending) {
+    /* the copy engine may not have read the argument blocks of the owner's previous batch yet: they
+     * are only rewritten when this batch differs from it (a loop over the same blocks does not) */
+    int at[4] = {cls_at[0], cls_at[1], cls_at[2], cls_at[3]}, same = 1;
+    for (int k = 0; k < n && same; k++) same = !memcmp(&h[at[FLAVOUR_CLASS(sv[k]->plan)]++], sv[k]->h_args, sizeof(*h));
+    if (!same) {
+      int w = solver_wait(own);
+      if (w) return w;
+    }
+  }
   for (int k = 0; k < n; k++) {
     if (sv[k] != own && sv[k]->busy) {
       /* its uploads (symbols, program pages, arguments) are queued on its own stream: the launching
@@ -1226,6 +1238,7 @@ int rqb_solver_run_batch_on(rqb_solver **sv, int n, rqb_solver *own) {
   }
 #undef FLAVOUR_CLASS
   own->busy = 1;
+  own->batch_args_pending = 1;
   DEV(rqb_copy_h2d(d, h, (size_t)n * sizeof(rqb_solve_args), own->stream));
   if (own->want_timing) DEV(rqb_event_record(own->ev0, own->stream));
   for (int c = 0, at = 0; c < 4; at += cls_n[c], c++) {

@@ -99,3 +99,30 @@ def test_batched_launch_is_ordered_with_the_members_own_streams():
             assert np.array_equal(first, np.stack([orc_lt(K, T, Co, p.Kprime + k) for k in range(16)]))
             assert np.array_equal(second, np.stack([orc_lt(K, T, Co, int(x)) for x in isi]))
             e.close()
+
+
+def test_one_owner_launches_two_different_batches_back_to_back():
+    """The owner lends its argument buffer to a batched launch; a second batch with OTHER blocks on
+    the same owner, queued while the first may not even have started, must not disturb the first."""
+    K, T, n = 1024, 1280, 8
+    p = orc_params(K)
+    rng = np.random.default_rng(8)
+    srcs = [rng.integers(0, 256, (K, T), dtype=np.uint8) for _ in range(2 * n)]
+    encs = []
+    for b in range(2 * n):
+        e = nb.Solver(K, T, max_in=K, max_out=32)
+        e.staging[:K, :T] = srcs[b]
+        e.upload(0, K)
+        e.plan_encode(True, 16)
+        encs.append(e)
+    own = encs[0]
+    for rep in range(4):  # something long on the owner's stream first, so that the copies queue up behind it
+        nb.Solver.run_batch(encs[:n], own)
+    nb.Solver.run_batch([own] + encs[n:], own)
+    nb.Solver.run_batch(encs[:n], own)
+    for b, e in enumerate(encs):
+        got = e.fetch_syms(16)
+        Co, _, _ = orc_encode(K, T, srcs[b])
+        assert np.array_equal(got, np.stack([orc_lt(K, T, Co, p.Kprime + k) for k in range(16)])), b
+    for e in encs:
+        e.close()
