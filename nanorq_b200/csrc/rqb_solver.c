@@ -1144,10 +1144,10 @@ int rqb_solver_plan_encode(rqb_solver *s, int want_c, uint32_t n_rep) {
     }
     e->next = g_enc_plans;
     g_enc_plans = e;
-    enc_plans_trim(RQB_ENC_PLANS_MAX);
   }
-  e->refs++;
+  e->refs++; /* referenced before the cache is trimmed: the new entry is not a candidate */
   e->use = ++g_enc_clock;
+  enc_plans_trim(RQB_ENC_PLANS_MAX);
   pthread_mutex_unlock(&g_plan_mu);
   if (s->enc != e && s->enc && s->busy) { /* queued work may still read the previous program */
     int w = solver_wait(s);

@@ -1,0 +1,157 @@
+"""Seeded random sessions against nanorq.h + nanorq_batch.h on the GPU: random object shapes (ragged last
+symbol, several source blocks), random loss, duplicates, shuffled arrival, symbols produced by a mix of
+nanorq_encode / nanorq_encode_range and delivered by a mix of nanorq_decoder_add_symbol /
+nanorq_decoder_add_symbols (with holes), early repair attempts, pageable and page-locked output.
+Every session must end with the decoded object equal to the payload, and every repair symbol equal to
+the oracle's (the reference's encoder, oracle/_ref or the C restatement)."""
+import numpy as np
+import pytest
+
+import nanorq_b200 as nb
+from nanorq_b200 import api
+from oracle_lib import orc_encode, orc_lt, orc_params
+
+pytestmark = pytest.mark.gpu
+
+
+def session(seed):
+    rng = np.random.default_rng(seed)
+    T = int(rng.choice([8, 16, 24, 64, 104, 256, 1280]))
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        K = int(rng.integers(1, 40))       # tiny blocks: no device context until it is needed
+    elif kind == 1:
+        K = int(rng.integers(40, 300))     # around the lazy / eager boundary (256 symbols)
+    else:
+        K = int(rng.integers(300, 1400))
+    if K * T > (1 << 20):
+        K = (1 << 20) // T
+    nblocks = int(rng.integers(1, 4))
+    F = nblocks * K * T - int(rng.integers(0, T))  # the object's last symbol is short most of the time
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    Z = enc.blocks()
+    io_in = nb.MemIO(payload)
+    loss = float(rng.choice([0.0, 0.05, 0.2, 0.5]))
+    packets = []  # (tag, row)
+    extra = {}    # sbn -> next unused repair ESI
+    for sbn in range(Z):
+        Kb = enc.block_symbols(sbn)
+        drop = rng.random(Kb) < loss
+        n_rep = int(drop.sum()) + int(rng.integers(0, 4))
+        if rng.random() < 0.5:  # one range call
+            syms = enc.encode_range(sbn, 0, Kb + n_rep, io_in)
+            assert syms is not None, (seed, sbn, Kb, n_rep, T, api.last_error())
+        else:                   # per-symbol calls, repair symbols first
+            syms = np.zeros((Kb + n_rep, T), np.uint8)
+            for esi in list(range(Kb, Kb + n_rep)) + list(range(Kb)):
+                s = enc.encode(esi, sbn, io_in)
+                assert s is not None
+                syms[esi] = s
+        if seed % 5 == 0:  # repair symbols against the oracle
+            blk = np.zeros(Kb * T, np.uint8)
+            first = sum(enc.block_symbols(q) for q in range(sbn)) * T
+            blk[:min(Kb * T, F - first)] = payload[first:first + Kb * T]
+            p = orc_params(Kb)
+            Co, _, _ = orc_encode(Kb, T, blk)
+            for esi in range(Kb, Kb + min(n_rep, 6)):
+                assert np.array_equal(syms[esi], orc_lt(Kb, T, Co, esi + p.Kprime - Kb)), (seed, sbn, esi)
+        for esi in list(np.nonzero(~drop)[0]) + list(range(Kb, Kb + n_rep)):
+            packets.append((api.tag(sbn, int(esi)), syms[esi].copy()))
+        extra[sbn] = Kb + n_rep
+        if rng.random() < 0.3:  # the sender drops the block's state; a later request for more repair symbols reloads it
+            enc.encoder_cleanup(sbn)
+    # duplicates and arrival order
+    for _ in range(int(rng.integers(0, 6))):
+        packets.append(packets[int(rng.integers(0, len(packets)))])
+    if rng.random() < 0.6:
+        order = rng.permutation(len(packets))
+        packets = [packets[i] for i in order]
+    pinned = rng.random() < 0.5
+    keep = []
+    if pinned:
+        ob = nb.PinnedBuffer(F)
+        out = ob.arr
+        out[:] = 0xEE
+        keep.append(ob)
+        io = nb.PinnedMemIO(out)
+    else:
+        out = np.full(F, 0xEE, np.uint8)
+        io = nb.MemIO(out)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    k = 0
+    while k < len(packets):
+        if rng.random() < 0.5:  # a batch call over a ring with holes
+            n = int(rng.integers(1, 80))
+            chunk = packets[k:k + n]
+            tags, rows = [], []
+            for t, r in chunk:
+                if rng.random() < 0.1:
+                    tags.append(0xFFFFFFFF)
+                    rows.append(np.zeros(T, np.uint8))
+                tags.append(t)
+                rows.append(r)
+            if pinned and rng.random() < 0.5:
+                pb = nb.PinnedBuffer(len(rows) * T)
+                pb.arr[:] = np.stack(rows).reshape(-1)
+                data = pb.arr.reshape(len(rows), T)
+                keep.append(pb)
+            else:
+                data = np.stack(rows)
+            rc, st = dec.add_symbols(np.array(tags, np.uint32), data, io)
+            assert rc >= 0, (seed, rc)
+            k += len(chunk)
+        else:
+            t, r = packets[k]
+            assert dec.add_symbol(r, int(t), io) != nb.SYM_ERR, seed
+            k += 1
+        if rng.random() < 0.05:  # an impatient receiver: may or may not be decodable yet, must not break anything
+            dec.repair_block(io, int(rng.integers(0, Z)))
+    if rng.random() < 0.5:
+        oks = dec.repair_blocks(io, list(range(Z)))
+    else:
+        oks = [dec.repair_block(io, sbn) for sbn in range(Z)]
+    for sbn in range(Z):  # a singular matrix: two more repair symbols, as a receiver would ask for
+        tries = 0
+        while not oks[sbn] and tries < 6:
+            for _ in range(2):
+                esi = extra[sbn]
+                extra[sbn] += 1
+                s = enc.encode(esi, sbn, io_in)
+                assert dec.add_symbol(s, api.tag(sbn, esi), io) != nb.SYM_ERR
+            oks[sbn] = dec.repair_block(io, sbn)
+            tries += 1
+        assert oks[sbn], (seed, sbn)
+        assert dec.num_missing(sbn) == 0
+    assert np.array_equal(out, payload), seed
+    dec.close()
+    io.close()
+    enc.close()
+    io_in.close()
+    for b in keep:
+        b.close()
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_random_sessions(chunk):
+    for seed in range(chunk * 40, chunk * 40 + 40):
+        session(1000 + seed)
+
+
+def test_more_encoder_shapes_than_the_program_cache_holds():
+    """Encoder programs are cached per block size (48 entries, least recently used dropped): 70 sizes in a
+    row, each checked against the oracle, then the first sizes again."""
+    T = 16
+    sizes = list(range(300, 370)) + list(range(300, 310))
+    for K in sizes:
+        rng = np.random.default_rng(K)
+        payload = rng.integers(0, 256, K * T, dtype=np.uint8)
+        enc = nb.Encoder(K * T, T, K, 0, 8)
+        io = nb.MemIO(payload)
+        got = enc.encode_range(0, K, 3, io)
+        p = orc_params(K)
+        Co, _, _ = orc_encode(K, T, payload)
+        for k in range(3):
+            assert np.array_equal(got[k], orc_lt(K, T, Co, p.Kprime + k)), (K, k)
+        enc.close()
+        io.close()
