@@ -530,13 +530,18 @@ void rqb_solver_destroy(rqb_solver *s) {
   g_shell_bytes += solver_bytes(s);
   while (g_pool_bytes + g_shell_bytes > cache_limit()) {
     /* over the limit: the least recently used idle context goes (the last idle one in the list), or,
-     * when none is idle, the oldest one with work still queued; never the one just parked */
-    rqb_solver **victim = NULL;
+     * when none is idle, the oldest one with work still queued; the one just parked only when nothing
+     * else is left (it alone is larger than the limit) */
+    rqb_solver **victim = NULL, **self = NULL;
     for (rqb_solver **pp = &g_shells; *pp; pp = &(*pp)->next_shell) {
-      if (*pp == s) continue;
+      if (*pp == s) {
+        self = pp;
+        continue;
+      }
       if (!(*pp)->busy) victim = pp;
       else if (!victim) victim = pp;
     }
+    if (!victim) victim = self;
     if (!victim) break;
     rqb_solver *old = *victim;
     *victim = old->next_shell;

@@ -155,3 +155,40 @@ def test_more_encoder_shapes_than_the_program_cache_holds():
             assert np.array_equal(got[k], orc_lt(K, T, Co, p.Kprime + k)), (K, k)
         enc.close()
         io.close()
+
+
+def test_random_sessions_on_four_threads_at_once():
+    """The same sessions from four threads at a time (ctypes releases the GIL inside the library):
+    mixed block shapes contend for the context list, the buffer pool and the program cache."""
+    import threading
+    errors = []
+
+    def run(first):
+        try:
+            for seed in range(first, first + 25):
+                session(5000 + seed)
+        except BaseException as e:  # noqa: BLE001 -- reported in the main thread
+            errors.append((first, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(100 * t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_random_sessions_with_a_tiny_cache():
+    """A cache limit of 4 MiB: nearly every retired context and buffer is really freed and the next
+    block allocates afresh -- the eviction paths run all the time, results stay right, and what is
+    kept stays under the limit."""
+    _, limit = nb.cache_stats()
+    nb.release_cached()
+    nb.set_cache_limit(4 << 20)
+    try:
+        for seed in range(60):
+            session(9000 + seed)
+            assert nb.cache_stats()[0] <= (4 << 20)
+    finally:
+        nb.set_cache_limit(limit)
+        nb.release_cached()
