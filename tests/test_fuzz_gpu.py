@@ -14,23 +14,29 @@ from oracle_lib import orc_encode, orc_lt, orc_params
 pytestmark = pytest.mark.gpu
 
 
-def session(seed):
+def session(seed, big=False):
     rng = np.random.default_rng(seed)
     T = int(rng.choice([8, 16, 24, 64, 104, 256, 1280]))
     kind = rng.integers(0, 4)
-    if kind == 0:
+    if big:  # blocks of several MB: the HBM flavour, block images, several repair windows
+        T = int(rng.choice([512, 1000, 1280, 1496]))
+        K = int(rng.integers(1500, 9000))
+    elif kind == 0:
         K = int(rng.integers(1, 40))       # tiny blocks: no device context until it is needed
     elif kind == 1:
         K = int(rng.integers(40, 300))     # around the lazy / eager boundary (256 symbols)
     else:
         K = int(rng.integers(300, 1400))
-    if K * T > (1 << 20):
+    if K * T > (1 << 20) and not big:
         K = (1 << 20) // T
-    nblocks = int(rng.integers(1, 4))
+    nblocks = int(rng.integers(1, 4)) if not big else int(rng.integers(1, 3))
     F = nblocks * K * T - int(rng.integers(0, T))  # the object's last symbol is short most of the time
     payload = rng.integers(0, 256, F, dtype=np.uint8)
     enc = nb.Encoder(F, T, K, 0, 8)
     Z = enc.blocks()
+    spread = nb.device_count() > 1 and rng.random() < 0.5  # the blocks of the object on all GPUs of the box
+    if spread:
+        assert enc.set_devices(0) == nb.device_count()
     io_in = nb.MemIO(payload)
     loss = float(rng.choice([0.0, 0.05, 0.2, 0.5]))
     packets = []  # (tag, row)
@@ -79,6 +85,8 @@ def session(seed):
         out = np.full(F, 0xEE, np.uint8)
         io = nb.MemIO(out)
     dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    if spread:
+        assert dec.set_devices(0) == nb.device_count()
     k = 0
     while k < len(packets):
         if rng.random() < 0.5:  # a batch call over a ring with holes
@@ -138,6 +146,11 @@ def test_random_sessions(chunk):
         session(1000 + seed)
 
 
+def test_random_sessions_with_large_blocks():
+    for seed in range(16):
+        session(7000 + seed, big=True)
+
+
 def test_more_encoder_shapes_than_the_program_cache_holds():
     """Encoder programs are cached per block size (48 entries, least recently used dropped): 70 sizes in a
     row, each checked against the oracle, then the first sizes again."""
@@ -192,3 +205,50 @@ def test_random_sessions_with_a_tiny_cache():
     finally:
         nb.set_cache_limit(limit)
         nb.release_cached()
+
+
+@pytest.mark.parametrize("K,T,loss", [(10, 64, 0.0), (10, 64, 0.3), (1024, 1280, 0.05), (300, 104, 0.2)])
+def test_the_call_pattern_of_the_reference_benchmark(K, T, loss):
+    """benchmark.c:82-170 of the reference: the encoder loop calls nanorq_generate_symbols for every block and
+    then nanorq_encoder_reset(rq, 0); the decoder loop adds ALL packets again every round (blocks that are
+    already complete ignore theirs), repairs every block and resets block 0 only."""
+    rng = np.random.default_rng(K + T)
+    nblocks = 3
+    F = nblocks * K * T
+    payload = rng.integers(0, 256, F, dtype=np.uint8)
+    enc = nb.Encoder(F, T, K, 0, 8)
+    io_in = nb.MemIO(payload)
+    assert enc.precalculate()
+    Z = enc.blocks()
+    for rnd in range(3):
+        for sbn in range(Z):
+            assert enc.generate_symbols(sbn, io_in)
+        enc.encoder_reset(0)
+    packets = []
+    for sbn in range(Z):  # dump_block :44-72
+        Kb = enc.block_symbols(sbn)
+        assert enc.generate_symbols(sbn, io_in)
+        dropped = 0
+        for esi in range(Kb):
+            if rng.random() < loss:
+                dropped += 1
+            else:
+                packets.append((api.tag(sbn, esi), enc.encode(esi, sbn, io_in).copy()))
+        for esi in range(Kb, Kb + dropped + 2):
+            packets.append((api.tag(sbn, esi), enc.encode(esi, sbn, io_in).copy()))
+        enc.encoder_cleanup(sbn)
+    out = np.zeros(F, np.uint8)
+    io_out = nb.MemIO(out)
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    for rnd in range(3):
+        out[:K * T] = 0  # block 0 is decoded afresh every round
+        for t, r in packets:
+            assert dec.add_symbol(r, int(t), io_out) != nb.SYM_ERR
+        for sbn in range(Z):
+            assert dec.repair_block(io_out, sbn), (rnd, sbn)
+        assert np.array_equal(out, payload), rnd
+        dec.encoder_reset(0)
+    for sbn in range(Z):
+        dec.encoder_cleanup(sbn)
+    dec.close()
+    enc.close()
