@@ -9,7 +9,7 @@ import pytest
 
 import nanorq_b200 as nb
 from nanorq_b200 import api
-from oracle_lib import orc_encode, orc_lt, orc_params
+from oracle_lib import orc_decode, orc_encode, orc_lt, orc_params
 
 pytestmark = pytest.mark.gpu
 
@@ -252,3 +252,49 @@ def test_the_call_pattern_of_the_reference_benchmark(K, T, loss):
         dec.encoder_cleanup(sbn)
     dec.close()
     enc.close()
+
+
+def test_random_solver_requests_in_both_flavours():
+    """rqb200.h level: random decode requests (repair ESIs anywhere, shuffled arrival, overhead 0..20) run with
+    the flavour the planner picks and with the HBM flavour forced, including blocks batched into one launch;
+    recovered symbols, intermediate symbols and the verdict against the oracle."""
+    for seed in range(60):
+        rng = np.random.default_rng(12000 + seed)
+        K = int(rng.choice([rng.integers(1, 30), rng.integers(30, 300), rng.integers(300, 2500)]))
+        T = int(rng.choice([8, 16, 40, 64, 1280]))
+        p = orc_params(K)
+        nblk = int(rng.integers(1, 4))
+        jobs = []
+        for b in range(nblk):
+            src = rng.integers(0, 256, (K, T), dtype=np.uint8)
+            Co, _, _ = orc_encode(K, T, src)
+            drop = rng.random(K) < float(rng.choice([0.05, 0.3, 0.9]))
+            drop[int(rng.integers(0, K))] = True
+            rep = K + rng.choice(4 * K + 64, size=int(drop.sum()) + int(rng.choice([0, 1, 2, 20])), replace=False)
+            esis = np.concatenate([np.nonzero(~drop)[0], rep]).astype(np.uint32)
+            rng.shuffle(esis)
+            syms = np.stack([src[e] if e < K else orc_lt(K, T, Co, int(e) + p.Kprime - K) for e in esis])
+            rc_o, _, C_o, _, _ = orc_decode(K, T, esis, syms, want_C=True)
+            req, missing = nb.SolveRequest.for_decoder(K, esis)
+            jobs.append((src, esis, syms, rc_o, C_o, req, missing))
+        n_in = max(len(j[1]) for j in jobs)
+        for flavour in ("auto", "hbm"):
+            solvers, live = [], []
+            for src, esis, syms, rc_o, C_o, req, missing in jobs:
+                s = nb.Solver(K, T, max_in=n_in, max_out=max(len(missing), 1), flavour=flavour)
+                s.staging[:len(esis), :T] = syms
+                s.upload(0, len(esis))
+                rc = s.plan(req)
+                assert (rc == 0) == (rc_o == 0), (seed, flavour, rc, rc_o)
+                solvers.append(s)
+                if rc == 0:
+                    live.append(s)
+            if len(live) > 1:
+                nb.Solver.run_batch(live, live[0])
+            elif live:
+                live[0].run()
+            for s, (src, esis, syms, rc_o, C_o, req, missing) in zip(solvers, jobs):
+                if rc_o == 0:
+                    assert np.array_equal(s.fetch_syms(len(missing)), src[missing]), (seed, flavour)
+                    assert np.array_equal(s.fetch_c(), C_o), (seed, flavour)
+                s.close()
