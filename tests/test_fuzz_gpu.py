@@ -298,3 +298,61 @@ def test_random_solver_requests_in_both_flavours():
                     assert np.array_equal(s.fetch_syms(len(missing)), src[missing]), (seed, flavour)
                     assert np.array_equal(s.fetch_c(), C_o), (seed, flavour)
                 s.close()
+
+
+def test_random_schedules_replayed_like_the_reference_applies_them():
+    """rqb_schedule_replay / _stepwise on arbitrary op lists (not only the ones the reference's elimination
+    emits): random axpy / scal sequences with long dependency chains and repeated destinations, random marks
+    and row permutations; expected bytes = the literal order of precode_matrix_apply_sched + the swap walk of
+    precode_matrix_permute (lib/precode.c:3-32,379-389), row ops by the oracle."""
+    from oracle_lib import Op, oracle, ptr
+
+    def oracle_ops(ops):
+        o = (Op * len(ops))()
+        for k, (b, i, j) in enumerate(zip(ops["beta"], ops["i"], ops["j"])):
+            o[k].beta, o[k].i, o[k].j = int(b), int(i), int(j)
+        return o
+
+    def permute(D, P):
+        P = list(P)
+        for i in range(len(P)):
+            at = i
+            while P[at] >= 0:
+                D[[i, P[at]]] = D[[P[at], i]]
+                nxt = P[at]
+                P[at] = -1
+                at = nxt
+
+    for seed in range(40):
+        rng = np.random.default_rng(15000 + seed)
+        R = int(rng.integers(2, 200))
+        T = int(rng.choice([16, 48, 64, 1280]))
+        nops = int(rng.integers(1, 6 * R))
+        ops = np.zeros(nops, dtype=api.OP_DTYPE)
+        hot = rng.integers(0, R, size=max(1, R // 8))  # a few rows take part in most ops: chains and repeats
+        for k in range(nops):
+            i = int(rng.choice(hot)) if rng.random() < 0.5 else int(rng.integers(0, R))
+            if rng.random() < 0.85:
+                j = int(rng.integers(0, R - 1))
+                j += j >= i
+                ops[k] = (int(rng.choice([1, 1, 1, rng.integers(2, 256)])), i, j)
+            else:
+                ops[k] = (0, i, int(rng.integers(1, 256)))
+        m1 = int(rng.integers(1, nops + 1))
+        m0 = int(rng.integers(0, m1))
+        di = rng.permutation(R).astype(np.int32)
+        c = rng.permutation(R).astype(np.int32)
+        D = rng.integers(0, 256, (R, T), dtype=np.uint8)
+        order = list(range(0, m1)) + list(range(m0, -1, -1)) + list(range(m1, nops)) + list(range(0, m0 + 1))
+        seq = ops[order]
+        want = D.copy()
+        oracle().orc_apply_ops(ptr(want), T, T, oracle_ops(seq), len(seq))
+        permute(want, di)
+        permute(want, c)
+        for stepwise in (False, True):
+            m = nb.Matrix(R, T)
+            m.upload(D)
+            m.schedule_replay(ops, m0, m1, di, c, stepwise=stepwise)
+            got = m.download()
+            m.close()
+            assert np.array_equal(got, want), (seed, stepwise, R, T, nops, m0, m1)
