@@ -14,7 +14,7 @@ from oracle_lib import orc_decode, orc_encode, orc_lt, orc_params
 pytestmark = pytest.mark.gpu
 
 
-def session(seed, big=False):
+def session(seed, big=False, files=None):
     rng = np.random.default_rng(seed)
     T = int(rng.choice([8, 16, 24, 64, 104, 256, 1280]))
     kind = rng.integers(0, 4)
@@ -37,7 +37,12 @@ def session(seed, big=False):
     spread = nb.device_count() > 1 and rng.random() < 0.5  # the blocks of the object on all GPUs of the box
     if spread:
         assert enc.set_devices(0) == nb.device_count()
-    io_in = nb.MemIO(payload)
+    in_kind = rng.choice(["mem", "file", "mmap"]) if files else "mem"
+    if in_kind == "mem":
+        io_in = nb.MemIO(payload)
+    else:  # encode.c style: the object is read through a file ioctx
+        payload.tofile(files / ("in%d.bin" % seed))
+        io_in = nb.FileIO(files / ("in%d.bin" % seed), 1, mmap=in_kind == "mmap")
     loss = float(rng.choice([0.0, 0.05, 0.2, 0.5]))
     packets = []  # (tag, row)
     extra = {}    # sbn -> next unused repair ESI
@@ -74,8 +79,13 @@ def session(seed, big=False):
         order = rng.permutation(len(packets))
         packets = [packets[i] for i in order]
     pinned = rng.random() < 0.5
+    out_kind = rng.choice(["mem", "file", "mmap"]) if files else "mem"
     keep = []
-    if pinned:
+    if out_kind != "mem":  # decode.c style: the decoded object is written through a file ioctx
+        pinned = False
+        out = None
+        io = nb.FileIO(files / ("out%d.bin" % seed), 0, mmap=out_kind == "mmap")
+    elif pinned:
         ob = nb.PinnedBuffer(F)
         out = ob.arr
         out[:] = 0xEE
@@ -131,9 +141,11 @@ def session(seed, big=False):
             tries += 1
         assert oks[sbn], (seed, sbn)
         assert dec.num_missing(sbn) == 0
-    assert np.array_equal(out, payload), seed
     dec.close()
     io.close()
+    if out is None:
+        out = np.fromfile(files / ("out%d.bin" % seed), dtype=np.uint8)
+    assert len(out) == F and np.array_equal(out, payload), seed
     enc.close()
     io_in.close()
     for b in keep:
@@ -144,6 +156,11 @@ def session(seed, big=False):
 def test_random_sessions(chunk):
     for seed in range(chunk * 40, chunk * 40 + 40):
         session(1000 + seed)
+
+
+def test_random_sessions_through_file_ioctx(tmp_path):
+    for seed in range(40):
+        session(3000 + seed, files=tmp_path)
 
 
 def test_random_sessions_with_large_blocks():
