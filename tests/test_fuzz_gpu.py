@@ -373,3 +373,51 @@ def test_random_schedules_replayed_like_the_reference_applies_them():
             got = m.download()
             m.close()
             assert np.array_equal(got, want), (seed, stepwise, R, T, nops, m0, m1)
+
+
+def test_calls_with_arguments_out_of_range_are_refused():
+    """Block numbers beyond the object, ESIs beyond the range, short pitches, the wrong kind of object:
+    every call says no (0 / false / NANORQ_SYM_ERR / -1) and the objects keep working afterwards."""
+    K, T = 300, 64
+    rng = np.random.default_rng(4)
+    payload = rng.integers(0, 256, 2 * K * T, dtype=np.uint8)
+    enc = nb.Encoder(len(payload), T, K, 0, 8)
+    io_in = nb.MemIO(payload)
+    Z = enc.blocks()
+    assert Z == 2
+    assert enc.generate_symbols(Z, io_in) is False
+    assert enc.generate_symbols(255, io_in) is False
+    assert enc.encode(0, Z, io_in) is None
+    assert enc.encode(1 << 24, 0, io_in) is None
+    assert enc.encode_range(Z, 0, 4, io_in) is None
+    assert enc.encode_range(0, (1 << 24) - 2, 4, io_in) is None
+    assert enc.block_symbols(Z) == 0
+    wide = np.zeros((4, T - 8), np.uint8)
+    assert nb.lib().nanorq_encode_range(enc.h, 0, 0, 4, wide.ctypes.data, T - 8, io_in.ptr) == 0  # pitch < T
+    dec = nb.Decoder(enc.oti_common(), enc.oti_scheme_specific())
+    out = np.zeros(len(payload), np.uint8)
+    io_out = nb.MemIO(out)
+    sym = enc.encode(0, 0, io_in)
+    assert dec.add_symbol(sym, api.tag(Z, 0), io_out) == nb.SYM_ERR
+    assert dec.add_symbol(sym, api.tag(0, 3 * K), io_out) == nb.SYM_ERR  # beyond max_esi
+    assert dec.repair_block(io_out, Z) is False
+    assert dec.num_missing(Z) == 0 and dec.num_repair(Z) == 0
+    assert nb.lib().nanorq_encode_range(dec.h, 0, 0, 4, wide.ctypes.data, T, io_in.ptr) == 0  # a decoder object
+    rows = np.zeros((4, T), np.uint8)
+    tags = np.array([api.tag(0, 0)] * 4, np.uint32)
+    assert nb.lib().nanorq_decoder_add_symbols(dec.h, tags.ctypes.data_as(api.u32p), rows.ctypes.data, T - 1, 4, None,
+                                               io_out.ptr) == -1
+    rc, st = dec.add_symbols(np.array([api.tag(Z, 0), api.tag(0, 0), api.tag(0, 3 * K)], np.uint32),
+                             np.stack([sym, sym, sym]), io_out)
+    assert rc == -1 and st == [nb.SYM_ERR, nb.SYM_ADDED, nb.SYM_ERR]
+    assert dec.repair_blocks(io_out, [Z, 0, 200]) == [False, False, False]  # block 0 has one symbol so far
+    # after all that: a normal transfer still works
+    for sbn in range(Z):
+        syms = enc.encode_range(sbn, 0, K + 7, io_in)
+        tags = np.array([api.tag(sbn, e) for e in range(5, K + 7)], np.uint32)
+        rc, _ = dec.add_symbols(tags, syms[5:], io_out)
+        assert rc >= K - 6
+        assert dec.repair_block(io_out, sbn)
+    assert np.array_equal(out, payload)
+    dec.close()
+    enc.close()
