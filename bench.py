@@ -540,7 +540,7 @@ def run_own(args, rank, world, local_rank):
     # (measured on 16 cores: 256 -> 264 Gbit/s; on 4 cores, a rank's share at N=8: 100 -> 143)
     e2e_batch = e2e_arm(os.path.join(nb.api.LIB_DIR, "librq_roundtrip_batch.so"), "rq_roundtrip_batch_run",
                         "nanorq_batch.h range calls, page-locked buffers (bench/rq_roundtrip_batch.c), two workers per core",
-                        threads=2 * threads, NBE=e2e_blocks(2 * threads))
+                        threads=min(2 * threads, 64), NBE=e2e_blocks(min(2 * threads, 64)))
 
     # ---- cpu_baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
