@@ -48,7 +48,10 @@ size_t nanorq_encode(nanorq *rq, void *data, uint32_t esi, uint8_t sbn, struct i
 void nanorq_encoder_cleanup(nanorq *rq, uint8_t sbn); /* :437 */
 void nanorq_encoder_reset(nanorq *rq, uint8_t sbn);   /* :453 */
 nanorq *nanorq_decoder_new(uint64_t common, uint32_t specific); /* :336 */
-bool nanorq_set_max_esi(nanorq *rq, uint32_t max_esi);          /* :471 */
+/* :471 widens the ESI range a decoder accepts (default 2 K'); call it before the first symbol of a block.
+ * It does not widen the number of symbols a block holds: at most 2 K' + 1024 distinct symbols are kept per
+ * block (a block is decodable long before that), further ones are refused with NANORQ_SYM_ERR */
+bool nanorq_set_max_esi(nanorq *rq, uint32_t max_esi);
 /* :478 returns NANORQ_SYM_* */
 int nanorq_decoder_add_symbol(nanorq *rq, void *data, uint32_t tag, struct ioctx *io);
 size_t nanorq_num_missing(nanorq *rq, uint8_t sbn); /* :511 */
