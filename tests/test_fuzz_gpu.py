@@ -126,7 +126,9 @@ def session(seed, big=False, files=None):
         if rng.random() < 0.05:  # an impatient receiver: may or may not be decodable yet, must not break anything
             dec.repair_block(io, int(rng.integers(0, Z)))
     if rng.random() < 0.5:
+        api.lib().rqb_set_plan_threads(int(rng.choice([1, 3])))  # the blocks' programs built side by side or in turn
         oks = dec.repair_blocks(io, list(range(Z)))
+        api.lib().rqb_set_plan_threads(1)
     else:
         oks = [dec.repair_block(io, sbn) for sbn in range(Z)]
     for sbn in range(Z):  # a singular matrix: two more repair symbols, as a receiver would ask for
