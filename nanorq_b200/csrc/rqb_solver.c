@@ -591,6 +591,11 @@ int rqb_solver_create_ex(rqb_solver **out, int K, int Kparams, size_t T, uint32_
 int rqb_solver_device(const rqb_solver *s) { return s->dev; }
 void rqb_solver_set_flavour(rqb_solver *s, int flavour) { s->flavour = flavour == RQB_FLAVOUR_HBM ? RQB_FLAVOUR_HBM : RQB_FLAVOUR_AUTO; }
 
+static pthread_once_t g_usolve_hook_once = PTHREAD_ONCE_INIT;
+static void usolve_hook_install(void) {
+  if (!rqb_plan_usolve_hook) rqb_plan_usolve_hook = usolve_on_device;
+}
+
 int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, size_t T, uint32_t max_in,
                          uint32_t max_out) {
   *out = NULL;
@@ -604,7 +609,7 @@ int rqb_solver_create_on(rqb_solver **out, int want_dev, int K, int Kparams, siz
     return RQB_E_NODEVICE;
   }
   if (!max_out) max_out = 1;
-  if (!rqb_plan_usolve_hook) rqb_plan_usolve_hook = usolve_on_device; /* a GPU is present: the planner may use it */
+  pthread_once(&g_usolve_hook_once, usolve_hook_install); /* a GPU is present: the planner may use it */
   const int dev = want_dev >= 0 ? want_dev : rqb_dev_default();
   if (dev >= rqb_dev_count()) {
     snprintf(g_err, sizeof(g_err), "rqb_solver_create: no CUDA device %d", dev);
