@@ -526,11 +526,30 @@ static const base_matrix *base_get(const rqb_params *P) {
   while (m && m->Kp != Kp) m = m->next;
   if (!m) {
     const int rows = S + H + Kp;
+    const int n = Kp + S;
     m = calloc(1, sizeof(*m));
-    m->Kp = Kp;
-    m->rptr = calloc((size_t)rows + 2, sizeof(int));
-    m->deg = calloc((size_t)rows + 1, sizeof(int));
-    m->cidx = malloc(sizeof(int) * ((size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)Kp + 16));
+    int *cur = malloc(sizeof(int) * (size_t)(S + 1));
+    if (m) {
+      m->Kp = Kp;
+      m->rptr = calloc((size_t)rows + 2, sizeof(int));
+      m->deg = calloc((size_t)rows + 1, sizeof(int));
+      m->cidx = malloc(sizeof(int) * ((size_t)3 * B + 3 * (size_t)S + (size_t)RQB_MAX_LT_DEGREE * (size_t)Kp + 16));
+      m->hb1 = calloc((size_t)n + 1, 1);
+      m->hb2 = calloc((size_t)n + 1, 1);
+    }
+    if (!m || !cur || !m->rptr || !m->deg || !m->cidx || !m->hb1 || !m->hb2) { /* out of memory: nothing is cached */
+      if (m) {
+        free(m->rptr);
+        free(m->deg);
+        free(m->cidx);
+        free(m->hb1);
+        free(m->hb2);
+      }
+      free(m);
+      free(cur);
+      pthread_mutex_unlock(&g_base_mu);
+      return NULL;
+    }
     int *rptr = m->rptr, *cidx = m->cidx;
     for (int col = 0; col < B; col++) {
       int sub = col / S;
@@ -546,7 +565,6 @@ static const base_matrix *base_get(const rqb_params *P) {
       acc += c;
     }
     for (int r = S; r <= S + H; r++) rptr[r] = acc;
-    int *cur = malloc(sizeof(int) * (size_t)(S + 1));
     memcpy(cur, rptr, sizeof(int) * (size_t)S);
     for (int col = 0; col < B; col++) {
       int sub = col / S;
@@ -569,9 +587,6 @@ static const base_matrix *base_get(const rqb_params *P) {
     }
     for (int r = 0; r < rows; r++)
       for (int k = rptr[r]; k < rptr[r + 1]; k++) m->deg[r] += (cidx[k] < W);
-    const int n = Kp + S;
-    m->hb1 = calloc((size_t)n + 1, 1);
-    m->hb2 = calloc((size_t)n + 1, 1);
     for (int j = 0; j + 1 < n; j++) {
       uint32_t b1 = rqb_rand(rqb_rand_v, (uint32_t)j + 1, 6, (uint32_t)H);
       uint32_t b2 = (b1 + rqb_rand(rqb_rand_v, (uint32_t)j + 1, 7, (uint32_t)H - 1) + 1) % (uint32_t)H;
@@ -2002,6 +2017,13 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
   stask *t = malloc(sizeof(stask) * (nops ? nops : 1));
   uint32_t *lw = calloc((size_t)nrows + 1, 4), *lr = calloc((size_t)nrows + 1, 4);
   int64_t *open = malloc(sizeof(int64_t) * ((size_t)nrows + 1));
+  if (!t || !lw || !lr || !open) {
+    free(t);
+    free(lw);
+    free(lr);
+    free(open);
+    return -7;
+  }
   for (uint32_t r = 0; r < nrows; r++) open[r] = -1;
   size_t nt = 0;
   uint32_t maxlevel = 0;
@@ -2054,8 +2076,10 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
     builder bd;
     memset(&bd, 0, sizeof(bd));
     bd.sc = sc;
-    for (size_t k = 0; k < nt; k++) b_task(&bd, t[k].gf ? RQB_T_GF : RQB_T_XOR, base + t[k].dst, 0, t[k].level, t[k].src, t[k].n);
-    for (uint32_t k = 0; k < nrows; k++) {
+    if (!sc) rc = -7;
+    else sc->oom = 0;
+    for (size_t k = 0; k < nt && !rc; k++) b_task(&bd, t[k].gf ? RQB_T_GF : RQB_T_XOR, base + t[k].dst, 0, t[k].level, t[k].src, t[k].n);
+    for (uint32_t k = 0; k < nrows && !rc; k++) {
       uint32_t src = RQB_SRC(base + gather_map[k], 1);
       if (gather_map[k] >= nrows) {
         rc = -1;
@@ -2063,8 +2087,10 @@ int rqb_plan_from_schedule(const void *ops_v, size_t nops, uint32_t nrows, const
       }
       b_task(&bd, RQB_T_XOR, out_base + k, 0, maxlevel + 1, &src, 1);
     }
+    if (!rc && sc->oom) rc = -7;
+    rqb_plan *plan = rc ? NULL : plan_acquire();
+    if (!rc && !plan) rc = -7;
     if (!rc) {
-      rqb_plan *plan = plan_acquire();
       size_t tot_levels = 0;
       rc = write_pages(&bd, plan, zero_row, 0, &tot_levels, NULL, 0);
       if (rc) {

@@ -1410,6 +1410,7 @@ int rqb_matrix_create(rqb_matrix **out, size_t rows, size_t T) {
     return RQB_E_NODEVICE;
   }
   rqb_matrix *m = calloc(1, sizeof(*m));
+  if (!m) return RQB_E_ARG;
   m->rows = rows;
   m->T = T;
   m->pitch = round_up(T, 64);
@@ -1481,6 +1482,7 @@ int rqb_matrix_fill_random(rqb_matrix *m, uint64_t seed) {
 int rqb_ops_upload(rqb_oplist **out, const rqb_op *ops, size_t n) {
   *out = NULL;
   rqb_oplist *l = calloc(1, sizeof(*l));
+  if (!l) return RQB_E_ARG;
   l->n = n;
   int e = rqb_dev_malloc((void **)&l->d, n * sizeof(rqb_rowop));
   e = e ? e : rqb_copy_h2d(l->d, ops, n * sizeof(rqb_rowop), NULL);
@@ -1532,7 +1534,13 @@ static int replay_prepare(size_t nr, const rqb_op *ops, size_t nops, long m0, lo
   if (rows > nr || cols > nr || m0 < -1 || m1 < 0 || (size_t)m1 > nops || m0 >= (long)nops)
     return RQB_E_ARG;
   size_t napp = nops + 2 * (size_t)(m0 + 1), k = 0;
+  for (int pass = 0; pass < 2; pass++) { /* entries of the permutations: negative = fixed point, else a row */
+    const int *P = pass ? c : di;
+    for (size_t i = 0; i < (pass ? cols : rows); i++)
+      if (P[i] >= 0 && (size_t)P[i] >= (pass ? cols : rows)) return RQB_E_ARG;
+  }
   rqb_rowop *seq = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
+  if (!seq) return RQB_E_ARG;
   for (long q = 0; q < m1; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
   for (long q = m0; q >= 0; q--) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
   for (long q = m1; q < (long)nops; q++) memcpy(&seq[k++], &ops[q], sizeof(rqb_op));
@@ -1542,11 +1550,20 @@ static int replay_prepare(size_t nr, const rqb_op *ops, size_t nops, long m0, lo
       free(seq);
       return RQB_E_ARG;
     }
-  uint32_t *map = malloc(4 * nr);
+  uint32_t *map = malloc(4 * (nr ? nr : 1));
+  if (!map) {
+    free(seq);
+    return RQB_E_ARG;
+  }
   for (size_t r = 0; r < nr; r++) map[r] = (uint32_t)r;
   for (int pass = 0; pass < 2; pass++) {
     size_t n = pass ? cols : rows;
     int *P = malloc(sizeof(int) * (n ? n : 1));
+    if (!P) {
+      free(seq);
+      free(map);
+      return RQB_E_ARG;
+    }
     memcpy(P, pass ? c : di, sizeof(int) * n);
     for (size_t i = 0; i < n; i++) {
       size_t at = i;
@@ -1659,7 +1676,14 @@ int rqb_schedule_replay_stepwise(rqb_matrix *m, const rqb_op *ops, size_t nops, 
   /* levelise: an op runs after every earlier op that wrote one of its rows or
    * read its destination; ops of one level are then mutually independent */
   uint32_t *lw = calloc(m->rows, 4), *lr = calloc(m->rows, 4), *lev = malloc(4 * (napp ? napp : 1));
+  uint32_t *start = NULL, *cur = NULL;
+  rqb_rowop *sorted = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
   uint32_t nlev = 0;
+  if (!lw || !lr || !lev || !sorted) {
+  nomem:
+    free(seq); free(lw); free(lr); free(lev); free(start); free(cur); free(sorted); free(map);
+    return RQB_E_ARG;
+  }
   for (size_t q = 0; q < napp; q++) {
     uint32_t i = seq[q].i, l = lw[i] > lr[i] ? lw[i] : lr[i];
     if (seq[q].beta) {
@@ -1674,16 +1698,15 @@ int rqb_schedule_replay_stepwise(rqb_matrix *m, const rqb_op *ops, size_t nops, 
     lev[q] = l;
     if (l > nlev) nlev = l;
   }
-  uint32_t *start = calloc((size_t)nlev + 2, 4);
+  start = calloc((size_t)nlev + 2, 4);
+  cur = malloc(4 * ((size_t)nlev + 2));
+  if (!start || !cur) goto nomem;
   for (size_t q = 0; q < napp; q++) start[lev[q] + 1]++;
   for (uint32_t l = 0; l <= nlev; l++) start[l + 1] += start[l];
-  rqb_rowop *sorted = malloc(sizeof(rqb_rowop) * (napp ? napp : 1));
-  {
-    uint32_t *cur = malloc(4 * ((size_t)nlev + 2));
-    memcpy(cur, start, 4 * ((size_t)nlev + 2));
-    for (size_t q = 0; q < napp; q++) sorted[cur[lev[q]]++] = seq[q];
-    free(cur);
-  }
+  memcpy(cur, start, 4 * ((size_t)nlev + 2));
+  for (size_t q = 0; q < napp; q++) sorted[cur[lev[q]]++] = seq[q];
+  free(cur);
+  cur = NULL;
   size_t nr = m->rows;
   rqb_rowop *d_ops = NULL;
   uint32_t *d_map = NULL;
